@@ -1,0 +1,63 @@
+"""ctypes binding of include/mixermdm_b200.h. The library is required: there is no CPU or PyTorch fallback."""
+import ctypes as C
+import os
+
+from . import _build
+
+_LIB = None
+
+
+class MmdmError(RuntimeError):
+    pass
+
+
+class Epilogue(C.Structure):
+    """mirror of `mmdm_epilogue` (include/mixermdm_b200.h)"""
+    _fields_ = [
+        ("mode", C.c_int32), ("ldo", C.c_int32),
+        ("bias", C.c_void_p), ("out", C.c_void_p),
+        ("vt_col0", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("hd", C.c_int32), ("Tp", C.c_int32),
+        ("vt", C.c_void_p),
+        ("resid", C.c_void_p), ("out_bf16", C.c_void_p),
+        ("pe", C.c_void_p), ("pe_ld", C.c_int32), ("dup_row_offset", C.c_int64),
+        ("std_", C.c_void_p), ("mean", C.c_void_p), ("nfeats", C.c_int32), ("persons_per_row", C.c_int32),
+    ]
+
+
+EPI_BF16, EPI_GELU_BF16, EPI_RESID, EPI_EMBED_PE, EPI_FINAL, EPI_F32 = range(6)
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen the in-tree library; raises if it has not been built (no fallback by design)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MmdmError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the CUDA extension is mandatory, there is no fallback path)")
+    lib = C.CDLL(path)
+    lib.mmdm_last_error.restype = C.c_char_p
+    lib.mmdm_abi_version.restype = C.c_int
+    _LIB = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mmdm_last_error().decode("utf-8", "replace")
+        raise MmdmError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,243 @@
+// Fused attention for short motion sequences (T <= 319) on sm_100a, with the reference's zero-attention
+// sink: nn.MultiheadAttention(add_zero_attn=True) appends one key with logit 0 and value 0
+// (reference: models/utils/layers.py:33-34,74-75; torch F.multi_head_attention_forward).
+//
+// The whole key range fits one tile, so there is no online-softmax rescaling:
+//   S[128 x NK] = Q K^T        tcgen05.mma, fp32 in TMEM (NK = round_up(T+1,16), two N<=256 instructions)
+//   P = exp2((S - max) * c)    each of the 128 threads owns one query row (tcgen05.ld 32x32b)
+//   O[128 x hd] = P V          tcgen05.mma, P staged as bf16 in 128B-swizzled smem (re-using the K tile),
+//                              V consumed K-major from the transposed V^T buffer the QKV GEMM writes.
+// Key row T is zero-filled by TMA out-of-bounds handling, which *is* the zero-attention key; key columns
+// > T are masked. Rows/keys beyond the sequence never touch HBM.
+#include "attention.cuh"
+
+namespace mmdm {
+
+struct AttnParams {
+  int S, T, H, NK, n1, n2, kv_xor, ldo;
+  float scale_log2;
+  __nv_bfloat16* out;
+};
+
+template <int HD>
+struct AttnCfg {
+  static constexpr int KA = HD / 64;                       // 64-wide K atoms along head dim
+  static constexpr uint32_t Q_BYTES = KA * 128 * 128;      // [KA][128 rows][128 B]
+  static constexpr uint32_t K_BYTES = KA * 320 * 128;      // [KA][320 rows][128 B]
+  static constexpr uint32_t P_BYTES = 5 * 128 * 128;       // [5][128 rows][128 B]
+  static constexpr uint32_t KP_BYTES = K_BYTES > P_BYTES ? K_BYTES : P_BYTES;
+  static constexpr uint32_t V_BYTES = 5 * HD * 128;        // [5][HD rows][128 B]
+  static constexpr size_t SMEM_BYTES = Q_BYTES + KP_BYTES + V_BYTES + 1024 + 128;
+  static constexpr uint32_t O_COL = 320;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(128, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = AttnCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* Ks = Qs + C::Q_BYTES;  // later re-used for P
+  uint8_t* Vs = Ks + C::KP_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + C::V_BYTES);  // [0]=QK loaded [1]=V loaded [2]=S done [3]=O done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int QT = (p.T + 127) / 128;
+  const int qt = blockIdx.x % QT;
+  const int h = (blockIdx.x / QT) % p.H;
+  const int s = blockIdx.x / (QT * p.H);
+  const int ks = s ^ p.kv_xor;
+  const int kgroups = (p.NK + 63) / 64;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], C::Q_BYTES + (uint32_t)(C::KA * kgroups) * (64 * 128));
+    for (int a = 0; a < C::KA; ++a) tma_load_3d(Qs + a * (128 * 128), &tmQ, &bars[0], h * HD + a * 64, qt * 128, s);
+    for (int a = 0; a < C::KA; ++a)
+      for (int r = 0; r < kgroups; ++r)
+        tma_load_3d(Ks + a * (320 * 128) + r * (64 * 128), &tmK, &bars[0], h * HD + a * 64, r * 64, ks);
+    mbar_arrive_expect_tx(&bars[1], (uint32_t)kgroups * (HD * 128));
+    for (int kt = 0; kt < kgroups; ++kt) tma_load_3d(Vs + kt * (HD * 128), &tmV, &bars[1], kt * 64, 0, ks * p.H + h);
+
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t id1 = umma_idesc_bf16(128, p.n1);
+    const uint32_t id2 = umma_idesc_bf16(128, p.n2);
+    const uint32_t q0 = smem_u32(Qs), k0 = smem_u32(Ks);
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      const uint32_t aoff = (uint32_t)(kk >> 2) * (128 * 128) + (uint32_t)(kk & 3) * 32;
+      const uint32_t boff = (uint32_t)(kk >> 2) * (320 * 128) + (uint32_t)(kk & 3) * 32;
+      const uint64_t da = umma_desc_k_sw128(q0 + aoff);
+      umma_bf16_ss(tmem_base, da, umma_desc_k_sw128(k0 + boff), id1, kk > 0 ? 1u : 0u);
+      if (p.n2 > 0)
+        umma_bf16_ss(tmem_base + (uint32_t)p.n1, da, umma_desc_k_sw128(k0 + boff + (uint32_t)p.n1 * 128), id2,
+                     kk > 0 ? 1u : 0u);
+    }
+    umma_commit(&bars[2]);
+  }
+  __syncwarp();
+
+  // ---- softmax: thread <-> query row -----------------------------------------------------------
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int nchunks = (p.NK + 31) / 32;
+  float mx = 0.f;  // the zero-attention key contributes logit 0
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(trow + (uint32_t)(c * 32), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c * 32 + j < p.T) mx = fmaxf(mx, __uint_as_float(r[j]));
+  }
+  float lsum = 0.f;
+  const int row = tid;
+  uint8_t* Ps = Ks;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(trow + (uint32_t)(c * 32), r);
+    tmem_ld_wait();
+    float pv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float e = exp2f((__uint_as_float(r[j]) - mx) * p.scale_log2);
+      pv[j] = (col <= p.T) ? e : 0.f;
+      lsum += pv[j];
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = c * 32 + g * 8;
+      if (col < p.NK) {
+        uint4 pk;
+        pk.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
+        pk.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
+        pk.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
+        pk.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
+        const int kt = col >> 6, chunk = (col & 63) >> 3;
+        *reinterpret_cast<uint4*>(Ps + kt * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(&bars[1], 0);
+    const uint32_t ido = umma_idesc_bf16(128, HD);
+    const uint32_t p0 = smem_u32(Ps), v0 = smem_u32(Vs);
+    const int ksteps = p.NK / 16;
+    for (int j = 0; j < ksteps; ++j) {
+      const uint32_t aoff = (uint32_t)(j >> 2) * (128 * 128) + (uint32_t)(j & 3) * 32;
+      const uint32_t boff = (uint32_t)(j >> 2) * (HD * 128) + (uint32_t)(j & 3) * 32;
+      umma_bf16_ss(tmem_base + C::O_COL, umma_desc_k_sw128(p0 + aoff), umma_desc_k_sw128(v0 + boff), ido,
+                   j > 0 ? 1u : 0u);
+    }
+    umma_commit(&bars[3]);
+  }
+  __syncwarp();
+
+  mbar_wait(&bars[3], 0);
+  tc_fence_after();
+  const float inv = 1.0f / lsum;
+  const int t = qt * 128 + row;
+#pragma unroll
+  for (int c = 0; c < HD / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(trow + C::O_COL + (uint32_t)(c * 32), r);
+    tmem_ld_wait();
+    if (t < p.T) {
+      __nv_bfloat16* dst = p.out + ((size_t)s * p.T + t) * p.ldo + h * HD + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+        pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+        pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+        pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + j) = pk;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+template <int HD>
+static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk,
+                              const __nv_bfloat16* vt, int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H,
+                              int kv_xor, cudaStream_t stream) {
+  using C = AttnCfg<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)T, (uint64_t)S};
+    uint64_t str[2] = {(uint64_t)ldq * 2, (uint64_t)T * ldq * 2};
+    uint32_t box[3] = {64, 128, 1};
+    MMDM_TRY(make_tensor_map(&tmQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)T, (uint64_t)S};
+    uint64_t str[2] = {(uint64_t)ldk * 2, (uint64_t)T * ldk * 2};
+    uint32_t box[3] = {64, 64, 1};
+    MMDM_TRY(make_tensor_map(&tmK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)T, (uint64_t)HD, (uint64_t)S * H};
+    uint64_t str[2] = {(uint64_t)Tp * 2, (uint64_t)HD * Tp * 2};
+    uint32_t box[3] = {64, (uint32_t)HD, 1};
+    MMDM_TRY(make_tensor_map(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  AttnParams p;
+  p.S = S; p.T = T; p.H = H;
+  p.NK = ((T + 1 + 15) / 16) * 16;
+  if (p.NK <= 256) { p.n1 = p.NK; p.n2 = 0; }
+  else { p.n1 = ((p.NK / 2 + 15) / 16) * 16; p.n2 = p.NK - p.n1; }
+  p.kv_xor = kv_xor;
+  p.ldo = ldo;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  p.out = out;
+  const int QT = (T + 127) / 128;
+  attention_kernel<HD><<<S * H * QT, 128, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
+                     int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H, int hd, int kv_xor,
+                     cudaStream_t stream) {
+  MMDM_REQUIRE(T >= 1 && T <= 319, "attention: T=%d outside the single-tile range [1,319]", T);
+  MMDM_REQUIRE(hd == 64 || hd == 128, "attention: head dim %d not in {64,128}", hd);
+  MMDM_REQUIRE((ldq % 8) == 0 && (ldk % 8) == 0 && (Tp % 8) == 0 && (ldo % 8) == 0 && Tp >= T,
+               "attention: pitches must be multiples of 8 elements");
+  if (hd == 128) return launch_attention_t<128>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, stream);
+  return launch_attention_t<64>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, stream);
+}
+
+}  // namespace mmdm

@@ -1,0 +1,66 @@
+// Host-side utilities: last-error string, tensor-map encoding through the driver entry point.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace mmdm {
+
+static thread_local char g_last_error[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_last_error; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn resolve_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base,
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = resolve_encode();
+  if (!fn) return -3;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult=%d rank=%d dims=[%llu,%llu,%llu] box=[%u,%u,%u]", (int)r,
+                   rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0,
+                   rank > 2 ? box[2] : 0);
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace mmdm

@@ -1,0 +1,170 @@
+// Row-wise / small kernels around the GEMMs: LayerNorm + AdaLN modulation (emitting bf16 GEMM operands),
+// conditioning-vector preparation, small fp32 linears (text / timestep embedders), state packing.
+#include "rowops.cuh"
+
+namespace mmdm {
+
+// ------------------------------------------------------------------------------------------------
+// LN(h) * (1 + scale[s]) + shift[s]  (reference: models/utils/layers.py:15-25, eps = 1e-6, no affine)
+// One warp per row; the row lives in registers (D = 128 * NV floats). Optionally a second modulation
+// of the SAME normalised row is emitted (block input feeds SA of its own stream and the CA-KV of the
+// partner stream: models/utils/blocks.py:50,57 with models/in2in.py:439-440).
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ h, int M, int T, const float* __restrict__ mod0, int ld_mod0,
+                   __nv_bfloat16* __restrict__ out0, const float* __restrict__ mod1, int ld_mod1,
+                   __nv_bfloat16* __restrict__ out1) {
+  constexpr int D = NV * 128;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int row = warp;
+  const int s = row / T;
+  const float4* src = reinterpret_cast<const float4*>(h + (size_t)row * D);
+  float4 v[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = src[i * 32 + lane];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(sum) * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+
+  auto emit = [&](const float* mod, int ld_mod, __nv_bfloat16* out) {
+    const float4* sc = reinterpret_cast<const float4*>(mod + (size_t)s * ld_mod);
+    const float4* sh = reinterpret_cast<const float4*>(mod + (size_t)s * ld_mod + D);
+    uint2* dst = reinterpret_cast<uint2*>(out + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = __ldg(sc + i * 32 + lane);
+      const float4 b = __ldg(sh + i * 32 + lane);
+      uint2 pk;
+      pk.x = pack_bf16x2(v[i].x * rstd * (1.f + a.x) + b.x, v[i].y * rstd * (1.f + a.y) + b.y);
+      pk.y = pack_bf16x2(v[i].z * rstd * (1.f + a.z) + b.z, v[i].w * rstd * (1.f + a.w) + b.w);
+      dst[i * 32 + lane] = pk;
+    }
+  };
+  emit(mod0, ld_mod0, out0);
+  if (out1 != nullptr) emit(mod1, ld_mod1, out1);
+}
+
+int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, int ld_mod0,
+                       __nv_bfloat16* out0, const float* mod1, int ld_mod1, __nv_bfloat16* out1,
+                       cudaStream_t stream) {
+  MMDM_REQUIRE(D == 128 || D == 256 || D == 512 || D == 1024, "ln_modulate: unsupported latent dim %d", D);
+  MMDM_REQUIRE((ld_mod0 % 4) == 0 && (out1 == nullptr || (ld_mod1 % 4) == 0), "ln_modulate: mod pitch %% 4");
+  const int threads = 256;
+  const int blocks = (M * 32 + threads - 1) / threads;
+  switch (D) {
+    case 128: ln_modulate_kernel<1><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
+    case 256: ln_modulate_kernel<2><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
+    case 512: ln_modulate_kernel<4><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
+    default: ln_modulate_kernel<8><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
+  }
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// E[s, :] = bf16( SiLU( temb[step, :] + text[text_row[s], :] ) )    (AdaLN input: layers.py:9-11 with
+// in2in.py:414-424 / mixermdm.py:677-682). `step` is read from device memory so the launch can be
+// replayed from a CUDA graph for every DDIM step.
+// ------------------------------------------------------------------------------------------------
+__global__ void cond_silu_kernel(const float* __restrict__ temb_table, const int* __restrict__ step_ptr,
+                                 const float* __restrict__ text, const int* __restrict__ text_row, int S, int D,
+                                 __nv_bfloat16* __restrict__ E) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * D) return;
+  const int s = idx / D, d = idx - s * D;
+  const int step = *step_ptr;
+  const float x = temb_table[(size_t)step * D + d] + text[(size_t)text_row[s] * D + d];
+  E[idx] = __float2bfloat16_rn(x / (1.0f + expf(-x)));
+}
+
+int launch_cond_silu(const float* temb_table, const int* step_ptr, const float* text, const int* text_row, int S,
+                     int D, __nv_bfloat16* E, cudaStream_t stream) {
+  const int n = S * D;
+  cond_silu_kernel<<<(n + 255) / 256, 256, 0, stream>>>(temb_table, step_ptr, text, text_row, S, D, E);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[r, n] = act( sum_k a[r, k] * w[n, k] + b[n] )  in fp32; one warp per output element.
+// Used once per batch / per weight load (text_embed, time_embed MLP), never per token.
+// ------------------------------------------------------------------------------------------------
+__global__ void small_linear_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w,
+                                    const float* __restrict__ b, float* __restrict__ out, int ldo, int R, int N,
+                                    int K, int act) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)R * N) return;
+  const int r = (int)(warp / N), n = (int)(warp - (long long)r * N);
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc += a[(size_t)r * lda + k] * w[(size_t)n * K + k];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc + (b ? b[n] : 0.f);
+    if (act == 1) v = v / (1.0f + expf(-v));
+    out[(size_t)r * ldo + n] = v;
+  }
+}
+
+int launch_small_linear(const float* a, int lda, const float* w, const float* b, float* out, int ldo, int R,
+                        int N, int K, int act, cudaStream_t stream) {
+  const long long warps = (long long)R * N;
+  const int threads = 256;
+  const long long blocks = (warps * 32 + threads - 1) / threads;
+  small_linear_kernel<<<(unsigned)blocks, threads, 0, stream>>>(a, lda, w, b, out, ldo, R, N, K, act);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state (B, T, 2*nf) fp32  ->  bf16 GEMM operand rows ((b*2+p)*T + t, kpad), zero padded to kpad.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_state_kernel(const float* __restrict__ x, int B, int T, int nf, int kpad,
+                                  __nv_bfloat16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * 2 * T * kpad;
+  if (idx >= total) return;
+  const int k = (int)(idx % kpad);
+  const long long row = idx / kpad;
+  const int t = (int)(row % T);
+  const int sp = (int)(row / T);
+  const int b = sp >> 1, p = sp & 1;
+  float v = 0.f;
+  if (k < nf) v = x[((size_t)b * T + t) * (2 * nf) + p * nf + k];
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+int launch_pack_state(const float* x, int B, int T, int nf, int kpad, __nv_bfloat16* out, cudaStream_t stream) {
+  const long long total = (long long)B * 2 * T * kpad;
+  pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, B, T, nf, kpad, out);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// step counter helpers (device-resident so that graph replays advance through the DDIM schedule)
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+__global__ void add_int_kernel(int* p, int v) { *p += v; }
+int launch_set_int(int* p, int v, cudaStream_t stream) {
+  set_int_kernel<<<1, 1, 0, stream>>>(p, v);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_add_int(int* p, int v, cudaStream_t stream) {
+  add_int_kernel<<<1, 1, 0, stream>>>(p, v);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mmdm

@@ -1,0 +1,25 @@
+#pragma once
+#include "common.cuh"
+
+namespace mmdm {
+
+// out0 = bf16(LN(h) * (1 + mod0[s, 0:D]) + mod0[s, D:2D]), s = row / T; optional second modulation.
+int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, int ld_mod0,
+                       __nv_bfloat16* out0, const float* mod1, int ld_mod1, __nv_bfloat16* out1,
+                       cudaStream_t stream);
+
+// E[s,:] = bf16(SiLU(temb_table[*step_ptr,:] + text[text_row[s],:]))
+int launch_cond_silu(const float* temb_table, const int* step_ptr, const float* text, const int* text_row, int S,
+                     int D, __nv_bfloat16* E, cudaStream_t stream);
+
+// fp32 out[r,n] = act(a[r,:] . w[n,:] + b[n]); act: 0 none, 1 SiLU
+int launch_small_linear(const float* a, int lda, const float* w, const float* b, float* out, int ldo, int R,
+                        int N, int K, int act, cudaStream_t stream);
+
+// (B,T,2*nf) fp32 -> ((b*2+p)*T+t, kpad) bf16, zero padded
+int launch_pack_state(const float* x, int B, int T, int nf, int kpad, __nv_bfloat16* out, cudaStream_t stream);
+
+int launch_set_int(int* p, int v, cudaStream_t stream);
+int launch_add_int(int* p, int v, cudaStream_t stream);
+
+}  // namespace mmdm

@@ -82,6 +82,142 @@ int mmdm_attention(const void* q, int ldq, const void* k, int ldk, const void* v
 int mmdm_small_linear(const float* a, int lda, const float* w, const float* b, float* out, int ldo, int R,
                       int N, int K, int act, void* stream);
 
+
+/* ih_to_smpl -> align_motions -> smpl_to_ih on the de-normalised predictions (mixermdm.py:702-712,
+ * utils/alignment.py:11-158) + bf16 packing of the Mixer motion_embed operand rows ((be*2+p)*T+t, kpad). */
+int mmdm_align_motions(const float* out1, const float* out2, float* out1a, float* out2a, void* emb_i, void* emb_I,
+                       int Be, int T, int kpad, int do_align, void* stream);
+
+/* The fused HBM pass: Influence head + sigmoid, weight expansion, mix, classifier-free guidance, process_xstart
+ * (centre + both normalisers) and the DDIM update (mixermdm.py:739-801; cfg_sampler.py:52-55;
+ * gaussian_diffusion.py:2031-2062, 1936-1965). One 8-CTA cluster per sample. */
+typedef struct mmdm_mixstep_args {
+  int32_t B, T, mixing_mode;
+  int32_t ncfg;        /* 2: rows [0,B) cond, [B,2B) uncond; 1: plain batch (mix_only = 1 only) */
+  int32_t mix_only;    /* 0: full sampler step; 1: write the mix; 2: write the guided prediction */
+  int32_t center, has_force;
+  float force_val, cfg_scale;
+  const int32_t* step_ptr;   /* device int: DDIM index (nsteps-1 .. 0); 0 = last step, raw result to final_out */
+  int32_t nsteps;
+  const float* coef;         /* device (nsteps,4) */
+  const void* hfin;          /* bf16 (ncfg*B*2*T, 512) Influence output, row ((c*B+b)*2+p)*T+t */
+  const float* head_w; const float* head_b;
+  const float* out1a; const float* out2a;  /* (ncfg*B,T,524) aligned predictions */
+  float* x1; float* x2;      /* (B,T,524) state streams, updated in place */
+  float* final_out;          /* (B,T,524) */
+  float* mix_out;
+  const float* mean1; const float* std1; const float* mean2; const float* std2;
+  float* hist_i1; float* hist_i2;
+} mmdm_mixstep_args;
+int mmdm_mix_cfg_ddim(const mmdm_mixstep_args* args, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Engine level: the whole Mixer step / DDIM loop behind one handle
+ * ---------------------------------------------------------------------------------------------- */
+
+/* one transformer block (reference models/utils/blocks.py:30-63, influence.py:6-48); all matrices bf16 in the
+ * nn.Linear (out_features, in_features) layout, biases fp32. CA pointers are NULL for mode "individual". */
+typedef struct mmdm_block_weights {
+  const void* sa_in_w;  const float* sa_in_b;   /* (3D, D) = sa_block.attention.in_proj_{weight,bias}   */
+  const void* sa_out_w; const float* sa_out_b;  /* (D, D)  = sa_block.attention.out_proj                */
+  const void* ca_q_w;   const float* ca_q_b;    /* (D, D)  = ca_block.attention.in_proj rows [0:D]      */
+  const void* ca_kv_w;  const float* ca_kv_b;   /* (2D, D) = ca_block.attention.in_proj rows [D:3D]     */
+  const void* ca_out_w; const float* ca_out_b;  /* (D, D)  = ca_block.attention.out_proj                */
+  const void* ffn_w1;   const float* ffn_b1;    /* (F, D)  = ffn.linear1                                */
+  const void* ffn_w2;   const float* ffn_b2;    /* (D, F)  = ffn.linear2                                */
+} mmdm_block_weights;
+
+enum mmdm_net_kind { MMDM_NET_INDIVIDUAL = 0, MMDM_NET_INTERACTION = 1, MMDM_NET_INFLUENCE = 2 };
+
+/* One network. The AdaLN modulation linears (layers.py:11) of all blocks are concatenated along their output
+ * dimension into two matrices, grouped by the conditioning vector that drives them:
+ *   ada0 <- E0 (per-person embedding: emb_individual{1,2} / cond_i{1,2})
+ *   ada1 <- E1 (interaction embedding: emb / cond_I)
+ * Row order inside each, per block l (each entry is 2D rows = [scale; shift]):
+ *   INDIVIDUAL : ada0 = [sa.norm, ffn.norm]                        ada1 empty
+ *   INTERACTION: ada0 = [sa.norm, ffn.norm]                        ada1 = [ca.norm, ca.xf_norm]
+ *   INFLUENCE  : ada0 = [sa.norm]                                  ada1 = [ca.norm, ca.xf_norm, ffn.norm]     */
+typedef struct mmdm_net_weights {
+  int32_t kind, D, F, L, H;
+  const void* ada0_w; const float* ada0_b; int32_t ada0_n;
+  const void* ada1_w; const float* ada1_b; int32_t ada1_n;
+  const void* embed_w; const float* embed_b;    /* motion_embed (D, kpad) bf16 zero padded from (D, 262)      */
+  const float* pe; int32_t pe_rows;             /* sequence_pos_encoder.pe (pe_rows, D) fp32                   */
+  const void* out_w; const float* out_b;        /* out.linear (262, D) bf16 (denoisers) / NULL                 */
+  const float* time_w0; const float* time_b0;   /* embed_timestep.time_embed.0 (D, D) fp32                     */
+  const float* time_w2; const float* time_b2;   /* embed_timestep.time_embed.2                                 */
+  const float* text_w;  const float* text_b;    /* text_embed (D, 768) fp32                                    */
+  const mmdm_block_weights* blocks;             /* host array of L entries                                     */
+} mmdm_net_weights;
+
+typedef struct mmdm_config {
+  int32_t nfeats;        /* 262 */
+  int32_t kpad;          /* 264: nfeats rounded up to a 16-byte row pitch in bf16 */
+  int32_t text_dim;      /* 768 */
+  int32_t nsteps;        /* DDIM steps (50 for "ddim50") */
+  int32_t mixing_mode;   /* 1 global, 2 temporal, 3 spatial, 4 spatio-temporal (influence.py:61-65) */
+  int32_t align;         /* Mixer(align=...)          : mixermdm.py:702-712 */
+  int32_t center;        /* MixerDiffusion(align=...) : gaussian_diffusion.py:2043-2049 */
+  int32_t has_force;     /* Mixer.force_influence_val is not None */
+  float force_val;
+  float cfg_scale;       /* ClassifierFreeSampleModelX2.s */
+  const int32_t* timestep_map;  /* host, nsteps entries (_WrappedModelTest, gaussian_diffusion.py:2193-2205) */
+  const float* coef;     /* device, (nsteps,4): sqrt_recip_ab, sqrt_recipm1_ab, sqrt(ab_prev), sqrt(1-ab_prev) */
+  const float* head_w;   /* device, influence.out.weight (1 or 23, 512) fp32 */
+  const float* head_b;
+  const float* mean1; const float* std1;  /* MotionNormalizerTorchHML3D (individual model) */
+  const float* mean2; const float* std2;  /* MotionNormalizerTorch      (interaction model) */
+} mmdm_config;
+
+typedef struct mmdm_handle mmdm_handle;
+
+int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_handle** out);
+void mmdm_destroy(mmdm_handle* h);
+/* bytes of device workspace needed for an (un-doubled) batch B of T frames */
+size_t mmdm_workspace_bytes(const mmdm_handle* h, int B, int T);
+int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T);
+
+/* text_embed of the 8 condition slices for the bound batch (cond: device (B, 6144) fp32); once per batch */
+int mmdm_set_condition(mmdm_handle* h, const float* cond, void* stream);
+/* state streams x1 (individual space) / x2 (interaction space), device (B,T,524) fp32, and the DDIM index */
+int mmdm_set_state(mmdm_handle* h, const float* x1, const float* x2, int step_index, void* stream);
+int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream);
+/* one DDIM step: CFG-doubled Mixer.forward + process_xstart + DDIM update; decrements the device step index.
+ * replaces MixerDiffusion.ddim_sample (gaussian_diffusion.py:1902-1965) */
+int mmdm_step(mmdm_handle* h, float* final_out /* (B,T,524) written when the index is 0, or NULL */, void* stream);
+/* whole loop from noise; result = pred_xstart2 of the last step (gaussian_diffusion.py:1769-1820).
+ * use_graph != 0 replays one captured step graph nsteps times. hist_i1/hist_i2: optional
+ * (nsteps, 2B, T, 262) fp32 device buffers receiving the expanded Mixer weights, or NULL. */
+int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* out, float* hist_i1,
+                float* hist_i2, int use_graph, void* stream);
+
+/* Mixer.forward in mode "eval_intermediate" (mixermdm.py:660-811) on an explicit batch of Bx rows
+ * (the caller did any CFG doubling): returns out_influenced (Bx,T,524); optional out1/out2 (aligned) and the
+ * expanded weights infl_i1/infl_i2 (Bx,T,262). With cfg_combine != 0 the rows are [cond; uncond] halves and
+ * out_influenced receives cfg_scale*cond + (1-cfg_scale)*uncond, (Bx/2,T,524)
+ * (ClassifierFreeSampleModelX2.forward, cfg_sampler.py:38-56). */
+int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const int64_t* timesteps,
+                       const float* cond, float* out_influenced, float* out1, float* out2, float* infl_i1,
+                       float* infl_i2, int Bx, int cfg_combine, float cfg_scale, void* stream);
+/* in2INDenoiser.forward (in2in.py:401-462): which = MMDM_NET_INDIVIDUAL (x: (Bx,T,262), cond (Bx,768)) or
+ * MMDM_NET_INTERACTION (x: (Bx,T,524), cond (Bx,2304)); output is the raw (normalised-space) prediction. */
+int mmdm_denoiser_forward(mmdm_handle* h, int which, const float* x, const int64_t* timesteps,
+                          const float* cond, float* out, int Bx, void* stream);
+
+/* per-kernel-class device timing (CUDA events on the launch stream, no graph): enable, run steps, read. */
+int mmdm_profile_enable(mmdm_handle* h, int on);
+/* writes up to max_entries records; returns the number written */
+typedef struct mmdm_profile_entry {
+  char name[32];
+  int64_t launches;
+  double ms;       /* summed device time */
+  double flops;    /* algorithmic flops (2*M*N*K, attention 4*T*Tk*hd per head) */
+  double bytes;    /* algorithmic bytes where defined (mix kernel), else 0 */
+} mmdm_profile_entry;
+int mmdm_profile_read(mmdm_handle* h, mmdm_profile_entry* entries, int max_entries);
+int64_t mmdm_launch_count(const mmdm_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

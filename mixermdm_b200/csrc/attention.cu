@@ -189,12 +189,6 @@ static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat
                               const __nv_bfloat16* vt, int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H,
                               int kv_xor, cudaStream_t stream) {
   using C = AttnCfg<HD>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::SMEM_BYTES));
-    attr_set = true;
-  }
   CUtensorMap tmQ, tmK, tmV;
   {
     uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)T, (uint64_t)S};
@@ -229,9 +223,19 @@ static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat
   return 0;
 }
 
+int attention_init() {
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)AttnCfg<128>::SMEM_BYTES));
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)AttnCfg<64>::SMEM_BYTES));
+  return 0;
+}
+
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
                      int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H, int hd, int kv_xor,
                      cudaStream_t stream) {
+  static int inited = attention_init();
+  MMDM_REQUIRE(inited == 0, "attention: kernel attribute setup failed");
   MMDM_REQUIRE(T >= 1 && T <= 319, "attention: T=%d outside the single-tile range [1,319]", T);
   MMDM_REQUIRE(hd == 64 || hd == 128, "attention: head dim %d not in {64,128}", hd);
   MMDM_REQUIRE((ldq % 8) == 0 && (ldk % 8) == 0 && (Tp % 8) == 0 && (ldo % 8) == 0 && Tp >= T,

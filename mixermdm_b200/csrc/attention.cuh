@@ -10,4 +10,6 @@ int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, in
                      int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H, int hd, int kv_xor,
                      cudaStream_t stream);
 
+int attention_init();
+
 }  // namespace mmdm

@@ -140,7 +140,10 @@ __device__ __forceinline__ void epilogue_store(const GemmEpi& ep, int row, int c
         dst = reinterpret_cast<float*>(ep.out) + ((size_t)s * ep.T + t) * ep.nfeats + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < nvalid) dst[j] = (v[j] + b[j]) * __ldg(ep.std + col0 + j) + __ldg(ep.mean + col0 + j);
+        if (j < nvalid) {
+          const float y = v[j] + b[j];
+          dst[j] = ep.std != nullptr ? y * __ldg(ep.std + col0 + j) + __ldg(ep.mean + col0 + j) : y;
+        }
       break;
     }
     case EPI_F32:
@@ -325,12 +328,6 @@ template <int BN>
 static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                      const GemmEpi& ep, cudaStream_t stream) {
   using C = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::SMEM_BYTES));
-    attr_set = true;
-  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -353,9 +350,19 @@ static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, in
   return 0;
 }
 
+int gemm_init() {
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GemmCfg<256>::SMEM_BYTES));
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GemmCfg<128>::SMEM_BYTES));
+  return 0;
+}
+
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                 const GemmEpi& ep, cudaStream_t stream) {
   MMDM_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  static int inited = gemm_init();
+  MMDM_REQUIRE(inited == 0, "gemm: kernel attribute setup failed");
   MMDM_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 (got %d, %d)", lda, ldw);
   MMDM_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                "gemm: operands must be 16-byte aligned");

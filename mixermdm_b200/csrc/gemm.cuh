@@ -44,5 +44,6 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
 // debug: 0 = tcgen05 (product path), 1 = SIMT reference kernel (bring-up only; MMDM_GEMM_SIMT=1)
 void gemm_set_debug_simt(int on);
 int num_sms();
+int gemm_init();   // one-time kernel attribute setup (also done lazily)
 
 }  // namespace mmdm

@@ -1,0 +1,41 @@
+#pragma once
+#include "common.cuh"
+
+namespace mmdm {
+
+// out1/out2: (Be,T,524) fp32 de-normalised predictions (individual / interaction model).
+// out1a/out2a: aligned copies; emb_i/emb_I: bf16 rows ((be*2+p)*T+t, kpad) for the Mixer's motion_embed.
+int launch_align(const float* out1, const float* out2, float* out1a, float* out2a, __nv_bfloat16* emb_i,
+                 __nv_bfloat16* emb_I, int Be, int T, int kpad, int do_align, cudaStream_t stream);
+
+struct MixStepParams {
+  int B, T, mode;                    // un-doubled batch, frames, mixing mode 1..4
+  int ncfg;                          // 2: rows [0,B) cond + [B,2B) uncond (sampler); 1: plain batch (mix_only)
+  int mix_only;                      // 1: stop after the mix, mix_out = out_influenced (ncfg*B,T,524)  [Mixer.forward]
+                                     // 2: stop after guidance, mix_out = s*cond+(1-s)*uncond (B,T,524) [CFG wrapper]
+  float* mix_out;
+  int center;                        // MixerDiffusion(align=...) : centre stream 1 in process_xstart
+  int has_force;                     // Mixer.force_influence_val is not None
+  float force_val;
+  float cfg_scale;
+  const int* step_ptr;               // device: current DDIM index (nsteps-1 ... 0)
+  int nsteps;
+  const float* coef;                 // [nsteps][4] = sqrt_recip_ab, sqrt_recipm1_ab, sqrt(ab_prev), sqrt(1-ab_prev)
+  const __nv_bfloat16* hfin;         // Influence output rows (((c*B+b)*2+p)*T+t, 512)
+  const float* head_w;               // (nw, 512) fp32
+  const float* head_b;               // (nw)
+  const float* out1a;                // (2B,T,524)
+  const float* out2a;
+  float* x1;                         // (B,T,524) state, individual space (updated in place)
+  float* x2;                         // (B,T,524) state, interaction space
+  float* final_out;                  // (B,T,524) written at the last step (step index 0)
+  const float* mean1; const float* std1;   // individual-model normaliser (HumanML3D stats)
+  const float* mean2; const float* std2;   // interaction-model normaliser (InterHuman stats)
+  float* hist_i1;                    // optional (nsteps, 2B, T, 262) expanded weights, or null
+  float* hist_i2;
+};
+
+int launch_mixstep(const MixStepParams& P, cudaStream_t stream);
+int motion_init();
+
+}  // namespace mmdm

@@ -78,21 +78,58 @@ int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, i
 // in2in.py:414-424 / mixermdm.py:677-682). `step` is read from device memory so the launch can be
 // replayed from a CUDA graph for every DDIM step.
 // ------------------------------------------------------------------------------------------------
-__global__ void cond_silu_kernel(const float* __restrict__ temb_table, const int* __restrict__ step_ptr,
-                                 const float* __restrict__ text, const int* __restrict__ text_row, int S, int D,
-                                 __nv_bfloat16* __restrict__ E) {
+__global__ void cond_silu_kernel(const float* __restrict__ temb, const int* __restrict__ temb_idx,
+                                 const int* __restrict__ step_ptr, const float* __restrict__ text,
+                                 const int* __restrict__ text_row, int S, int D, __nv_bfloat16* __restrict__ E) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * D) return;
   const int s = idx / D, d = idx - s * D;
-  const int step = *step_ptr;
-  const float x = temb_table[(size_t)step * D + d] + text[(size_t)text_row[s] * D + d];
+  const int trow = step_ptr ? *step_ptr : temb_idx[s];
+  const float x = temb[(size_t)trow * D + d] + text[(size_t)text_row[s] * D + d];
   E[idx] = __float2bfloat16_rn(x / (1.0f + expf(-x)));
 }
 
-int launch_cond_silu(const float* temb_table, const int* step_ptr, const float* text, const int* text_row, int S,
-                     int D, __nv_bfloat16* E, cudaStream_t stream) {
+int launch_cond_silu(const float* temb, const int* temb_idx, const int* step_ptr, const float* text,
+                     const int* text_row, int S, int D, __nv_bfloat16* E, cudaStream_t stream) {
   const int n = S * D;
-  cond_silu_kernel<<<(n + 255) / 256, 256, 0, stream>>>(temb_table, step_ptr, text, text_row, S, D, E);
+  cond_silu_kernel<<<(n + 255) / 256, 256, 0, stream>>>(temb, temb_idx, step_ptr, text, text_row, S, D, E);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// sequence -> row maps for the conditioning tables (see engine.cu for the table layouts)
+__global__ void build_maps_kernel(int* map0, int* map1, int* tmap, int S, int persons, int Bt, int dup,
+                                  int nslices, int k0_base) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int bx = s / persons, p = s - bx * persons;
+  const int c = dup ? bx / Bt : 0;
+  const int b = dup ? bx - c * Bt : bx;
+  map0[s] = c ? nslices * Bt : (k0_base + p) * Bt + b;
+  map1[s] = c ? nslices * Bt : b;
+  tmap[s] = bx;
+}
+int launch_build_maps(int* map0, int* map1, int* tmap, int S, int persons, int Bt, int dup, int nslices,
+                      int k0_base, cudaStream_t stream) {
+  build_maps_kernel<<<(S + 127) / 128, 128, 0, stream>>>(map0, map1, tmap, S, persons, Bt, dup, nslices, k0_base);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out[r, :] = table[idx[r], :]   (pe[timesteps], models/utils/utils.py:54-55)
+__global__ void gather_rows_kernel(const float* __restrict__ table, int rows, const long long* __restrict__ idx,
+                                   const int* __restrict__ idx32, int R, int D, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * D) return;
+  const int r = i / D, d = i - r * D;
+  long long t = idx ? idx[r] : (long long)idx32[r];
+  t = t < 0 ? 0 : (t >= rows ? rows - 1 : t);
+  out[i] = table[(size_t)t * D + d];
+}
+int launch_gather_rows(const float* table, int rows, const long long* idx64, const int* idx32, int R, int D,
+                       float* out, cudaStream_t stream) {
+  const int n = R * D;
+  gather_rows_kernel<<<(n + 255) / 256, 256, 0, stream>>>(table, rows, idx64, idx32, R, D, out);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -129,26 +166,27 @@ int launch_small_linear(const float* a, int lda, const float* w, const float* b,
 }
 
 // ------------------------------------------------------------------------------------------------
-// state (B, T, 2*nf) fp32  ->  bf16 GEMM operand rows ((b*2+p)*T + t, kpad), zero padded to kpad.
+// state (B, T, persons*nf) fp32 -> bf16 GEMM operand rows ((b*persons+p)*T + t, kpad), zero padded to kpad.
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_state_kernel(const float* __restrict__ x, int B, int T, int nf, int kpad,
+__global__ void pack_state_kernel(const float* __restrict__ x, int B, int T, int nf, int kpad, int persons,
                                   __nv_bfloat16* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * 2 * T * kpad;
+  const long long total = (long long)B * persons * T * kpad;
   if (idx >= total) return;
   const int k = (int)(idx % kpad);
   const long long row = idx / kpad;
   const int t = (int)(row % T);
   const int sp = (int)(row / T);
-  const int b = sp >> 1, p = sp & 1;
+  const int b = sp / persons, p = sp - b * persons;
   float v = 0.f;
-  if (k < nf) v = x[((size_t)b * T + t) * (2 * nf) + p * nf + k];
+  if (k < nf) v = x[((size_t)b * T + t) * (persons * nf) + p * nf + k];
   out[idx] = __float2bfloat16_rn(v);
 }
 
-int launch_pack_state(const float* x, int B, int T, int nf, int kpad, __nv_bfloat16* out, cudaStream_t stream) {
-  const long long total = (long long)B * 2 * T * kpad;
-  pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, B, T, nf, kpad, out);
+int launch_pack_state(const float* x, int B, int T, int nf, int kpad, int persons, __nv_bfloat16* out,
+                      cudaStream_t stream) {
+  const long long total = (long long)B * persons * T * kpad;
+  pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, B, T, nf, kpad, persons, out);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

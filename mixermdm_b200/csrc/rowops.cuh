@@ -8,16 +8,22 @@ int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, i
                        __nv_bfloat16* out0, const float* mod1, int ld_mod1, __nv_bfloat16* out1,
                        cudaStream_t stream);
 
-// E[s,:] = bf16(SiLU(temb_table[*step_ptr,:] + text[text_row[s],:]))
-int launch_cond_silu(const float* temb_table, const int* step_ptr, const float* text, const int* text_row, int S,
-                     int D, __nv_bfloat16* E, cudaStream_t stream);
+// E[s,:] = bf16(SiLU(temb[trow,:] + text[text_row[s],:]))
+// trow = step_ptr ? *step_ptr : temb_idx[s]
+int launch_cond_silu(const float* temb, const int* temb_idx, const int* step_ptr, const float* text,
+                     const int* text_row, int S, int D, __nv_bfloat16* E, cudaStream_t stream);
+int launch_build_maps(int* map0, int* map1, int* tmap, int S, int persons, int Bt, int dup, int nslices,
+                      int k0_base, cudaStream_t stream);
+int launch_gather_rows(const float* table, int rows, const long long* idx64, const int* idx32, int R, int D,
+                       float* out, cudaStream_t stream);
 
 // fp32 out[r,n] = act(a[r,:] . w[n,:] + b[n]); act: 0 none, 1 SiLU
 int launch_small_linear(const float* a, int lda, const float* w, const float* b, float* out, int ldo, int R,
                         int N, int K, int act, cudaStream_t stream);
 
-// (B,T,2*nf) fp32 -> ((b*2+p)*T+t, kpad) bf16, zero padded
-int launch_pack_state(const float* x, int B, int T, int nf, int kpad, __nv_bfloat16* out, cudaStream_t stream);
+// (B,T,persons*nf) fp32 -> ((b*persons+p)*T+t, kpad) bf16, zero padded
+int launch_pack_state(const float* x, int B, int T, int nf, int kpad, int persons, __nv_bfloat16* out,
+                      cudaStream_t stream);
 
 int launch_set_int(int* p, int v, cudaStream_t stream);
 int launch_add_int(int* p, int v, cudaStream_t stream);

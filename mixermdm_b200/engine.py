@@ -1,0 +1,413 @@
+"""Host side of the engine: packs the weights of the (unchanged) module tree into the layouts the kernels want,
+owns the device workspace (a torch tensor used as raw memory) and forwards calls to the C ABI.
+PyTorch is plumbing here (device memory, dtype casts at load time, streams); no arithmetic of the path runs in it."""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, schedule
+from ._lib import MmdmError, check, cur_stream, ptr
+
+NFEATS = 262
+KPAD = 264
+TEXT_DIM = 768
+NET_INDIVIDUAL, NET_INTERACTION, NET_INFLUENCE = 0, 1, 2
+
+
+# ------------------------------------------------------------------------------------------------
+# ctypes mirrors of include/mixermdm_b200.h
+# ------------------------------------------------------------------------------------------------
+class BlockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_q_w", "ca_q_b", "ca_kv_w", "ca_kv_b", "ca_out_w",
+        "ca_out_b", "ffn_w1", "ffn_b1", "ffn_w2", "ffn_b2")]
+
+
+class NetWeights(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("D", C.c_int32), ("F", C.c_int32), ("L", C.c_int32), ("H", C.c_int32),
+        ("ada0_w", C.c_void_p), ("ada0_b", C.c_void_p), ("ada0_n", C.c_int32),
+        ("ada1_w", C.c_void_p), ("ada1_b", C.c_void_p), ("ada1_n", C.c_int32),
+        ("embed_w", C.c_void_p), ("embed_b", C.c_void_p),
+        ("pe", C.c_void_p), ("pe_rows", C.c_int32),
+        ("out_w", C.c_void_p), ("out_b", C.c_void_p),
+        ("time_w0", C.c_void_p), ("time_b0", C.c_void_p), ("time_w2", C.c_void_p), ("time_b2", C.c_void_p),
+        ("text_w", C.c_void_p), ("text_b", C.c_void_p),
+        ("blocks", C.POINTER(BlockWeights)),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("nfeats", C.c_int32), ("kpad", C.c_int32), ("text_dim", C.c_int32), ("nsteps", C.c_int32),
+        ("mixing_mode", C.c_int32), ("align", C.c_int32), ("center", C.c_int32), ("has_force", C.c_int32),
+        ("force_val", C.c_float), ("cfg_scale", C.c_float),
+        ("timestep_map", C.POINTER(C.c_int32)), ("coef", C.c_void_p),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("mean1", C.c_void_p), ("std1", C.c_void_p), ("mean2", C.c_void_p), ("std2", C.c_void_p),
+    ]
+
+
+class MixstepArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("T", C.c_int32), ("mixing_mode", C.c_int32), ("ncfg", C.c_int32),
+        ("mix_only", C.c_int32), ("center", C.c_int32), ("has_force", C.c_int32),
+        ("force_val", C.c_float), ("cfg_scale", C.c_float),
+        ("step_ptr", C.c_void_p), ("nsteps", C.c_int32), ("coef", C.c_void_p),
+        ("hfin", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("out1a", C.c_void_p), ("out2a", C.c_void_p), ("x1", C.c_void_p), ("x2", C.c_void_p),
+        ("final_out", C.c_void_p), ("mix_out", C.c_void_p),
+        ("mean1", C.c_void_p), ("std1", C.c_void_p), ("mean2", C.c_void_p), ("std2", C.c_void_p),
+        ("hist_i1", C.c_void_p), ("hist_i2", C.c_void_p),
+    ]
+
+
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
+# ------------------------------------------------------------------------------------------------
+# normaliser statistics (reference utils/utils.py:44-82 loads them relative to the CWD)
+# ------------------------------------------------------------------------------------------------
+class MotionStats:
+    """(mean, std) of one motion space; attribute names follow MotionNormalizerTorch*."""
+
+    def __init__(self, mean, std):
+        self.motion_mean = torch.as_tensor(np.asarray(mean, dtype=np.float32))
+        self.motion_std = torch.as_tensor(np.asarray(std, dtype=np.float32))
+
+
+def load_normalizers(normalizers=None):
+    """returns (normalizer_model1 [HumanML3D stats, individual model], normalizer_model2 [InterHuman stats]).
+    `normalizers` may be ((mean1, std1), (mean2, std2)); otherwise the reference's files are read from ./data."""
+    if normalizers is not None:
+        (m1, s1), (m2, s2) = normalizers
+        return MotionStats(m1, s1), MotionStats(m2, s2)
+    paths = ["./data/HumanML3D/mean_ih_new.npy", "./data/HumanML3D/std_ih_new.npy", "./data/global_mean.npy",
+             "./data/global_std.npy"]
+    missing = [p for p in paths if not os.path.exists(p)]
+    if missing:
+        raise FileNotFoundError(f"normaliser statistics not found (reference layout, relative to CWD): {missing}")
+    m1, s1, m2, s2 = [np.load(p) for p in paths]
+    return MotionStats(m1, s1), MotionStats(m2, s2)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing
+# ------------------------------------------------------------------------------------------------
+class _Packer:
+    def __init__(self, device):
+        self.device = device
+        self.keep = []
+
+    def bf16(self, t):
+        t = t.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+        self.keep.append(t)
+        return t
+
+    def f32(self, t):
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.keep.append(t)
+        return t
+
+    def p(self, t):
+        return C.c_void_p(t.data_ptr())
+
+    def pack_net(self, kind, net, blocks, with_out):
+        """net: module with motion_embed/text_embed/embed_timestep/sequence_pos_encoder; blocks: ModuleList"""
+        D = net.motion_embed.out_features
+        att0 = blocks[0].sa_block.attention
+        H = att0.num_heads
+        F = blocks[0].ffn.linear1.out_features
+        L = len(blocks)
+        w = NetWeights()
+        w.kind, w.D, w.F, w.L, w.H = kind, D, F, L, H
+
+        def ada_cat(getters):
+            ws, bs = [], []
+            for blk in blocks:
+                for g in getters:
+                    lin = g(blk).emb_layers[1]
+                    ws.append(lin.weight)
+                    bs.append(lin.bias)
+            return self.bf16(torch.cat([x.detach() for x in ws], 0)), self.f32(torch.cat([x.detach() for x in bs], 0))
+
+        if kind == NET_INFLUENCE:
+            g0 = [lambda b: b.sa_block.norm]
+            g1 = [lambda b: b.ca_block.norm, lambda b: b.ca_block.xf_norm, lambda b: b.ffn.norm]
+        elif kind == NET_INTERACTION:
+            g0 = [lambda b: b.sa_block.norm, lambda b: b.ffn.norm]
+            g1 = [lambda b: b.ca_block.norm, lambda b: b.ca_block.xf_norm]
+        else:
+            g0 = [lambda b: b.sa_block.norm, lambda b: b.ffn.norm]
+            g1 = []
+        a0w, a0b = ada_cat(g0)
+        w.ada0_w, w.ada0_b, w.ada0_n = self.p(a0w), self.p(a0b), a0w.shape[0]
+        if g1:
+            a1w, a1b = ada_cat(g1)
+            w.ada1_w, w.ada1_b, w.ada1_n = self.p(a1w), self.p(a1b), a1w.shape[0]
+        else:
+            w.ada1_w, w.ada1_b, w.ada1_n = None, None, 0
+        ew = torch.zeros(D, KPAD, dtype=torch.float32)
+        ew[:, :NFEATS] = net.motion_embed.weight.detach().float().cpu()
+        w.embed_w, w.embed_b = self.p(self.bf16(ew)), self.p(self.f32(net.motion_embed.bias))
+        pe = self.f32(net.sequence_pos_encoder.pe)
+        w.pe, w.pe_rows = self.p(pe), pe.shape[0]
+        if with_out:
+            w.out_w, w.out_b = self.p(self.bf16(net.out.linear.weight)), self.p(self.f32(net.out.linear.bias))
+        else:
+            w.out_w, w.out_b = None, None
+        te = net.embed_timestep.time_embed
+        w.time_w0, w.time_b0 = self.p(self.f32(te[0].weight)), self.p(self.f32(te[0].bias))
+        w.time_w2, w.time_b2 = self.p(self.f32(te[2].weight)), self.p(self.f32(te[2].bias))
+        w.text_w, w.text_b = self.p(self.f32(net.text_embed.weight)), self.p(self.f32(net.text_embed.bias))
+        arr = (BlockWeights * L)()
+        for l, blk in enumerate(blocks):
+            bw = arr[l]
+            sa = blk.sa_block.attention
+            bw.sa_in_w, bw.sa_in_b = self.p(self.bf16(sa.in_proj_weight)), self.p(self.f32(sa.in_proj_bias))
+            bw.sa_out_w, bw.sa_out_b = self.p(self.bf16(sa.out_proj.weight)), self.p(self.f32(sa.out_proj.bias))
+            if kind != NET_INDIVIDUAL:
+                ca = blk.ca_block.attention
+                bw.ca_q_w, bw.ca_q_b = self.p(self.bf16(ca.in_proj_weight[:D])), self.p(self.f32(ca.in_proj_bias[:D]))
+                bw.ca_kv_w, bw.ca_kv_b = self.p(self.bf16(ca.in_proj_weight[D:])), self.p(self.f32(ca.in_proj_bias[D:]))
+                bw.ca_out_w, bw.ca_out_b = self.p(self.bf16(ca.out_proj.weight)), self.p(self.f32(ca.out_proj.bias))
+            bw.ffn_w1, bw.ffn_b1 = self.p(self.bf16(blk.ffn.linear1.weight)), self.p(self.f32(blk.ffn.linear1.bias))
+            bw.ffn_w2, bw.ffn_b2 = self.p(self.bf16(blk.ffn.linear2.weight)), self.p(self.f32(blk.ffn.linear2.bias))
+        self.keep.append(arr)
+        w.blocks = C.cast(arr, C.POINTER(BlockWeights))
+        return w
+
+
+def _absent_net(kind):
+    w = NetWeights()
+    w.kind, w.D, w.F, w.L, w.H = kind, 0, 0, 0, 0
+    return w
+
+
+class _Handle:
+    """owns one mmdm_handle + its workspace"""
+
+    def __init__(self, cfg, nets, keep, device):
+        self.lib = _lib.load()
+        if device.type != "cuda":
+            raise MmdmError("mixermdm_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        self.device = device
+        self.keep = keep
+        self.cfg = cfg
+        arr = (NetWeights * 3)(*nets)
+        self.keep.append(arr)
+        self.h = C.c_void_p()
+        self.lib.mmdm_workspace_bytes.restype = C.c_size_t
+        self.lib.mmdm_launch_count.restype = C.c_int64
+        with torch.cuda.device(device):
+            check(self.lib.mmdm_create(C.byref(cfg), arr, C.byref(self.h)), "mmdm_create")
+        self.ws = None
+        self.B = self.T = 0
+
+    def bind(self, B, T):
+        if self.ws is not None and B == self.B and T == self.T:
+            return
+        need = self.lib.mmdm_workspace_bytes(self.h, B, T)
+        if need == 0:
+            raise MmdmError(f"invalid workspace request B={B} T={T}")
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = None
+            self.ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        base = (self.ws.data_ptr() + 1023) // 1024 * 1024
+        check(self.lib.mmdm_bind_workspace(self.h, C.c_void_p(base), C.c_size_t(need), B, T), "mmdm_bind_workspace")
+        self.B, self.T = B, T
+
+    def launches(self):
+        return int(self.lib.mmdm_launch_count(self.h))
+
+    def profile(self, on):
+        check(self.lib.mmdm_profile_enable(self.h, int(on)), "mmdm_profile_enable")
+
+    def profile_read(self):
+        arr = (ProfileEntry * 64)()
+        n = self.lib.mmdm_profile_read(self.h, arr, 64)
+        return [dict(name=arr[i].name.decode(), launches=arr[i].launches, ms=arr[i].ms, flops=arr[i].flops,
+                     bytes=arr[i].bytes) for i in range(n)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                self.lib.mmdm_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def _f32c(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class MixerEngine:
+    """engine for one `Mixer` module (both denoisers + Influence + fused mix / sampler step)"""
+
+    def __init__(self, mixer, device, sched=None, cfg_scale=3.5, center=True):
+        device = torch.device(device)
+        pk = _Packer(device)
+        nets = [pk.pack_net(NET_INDIVIDUAL, mixer.denoiser1, mixer.denoiser1.blocks, True),
+                pk.pack_net(NET_INTERACTION, mixer.denoiser2, mixer.denoiser2.blocks, True),
+                pk.pack_net(NET_INFLUENCE, mixer, mixer.influence.blocks, False)]
+        if sched is None:   # the reference's inference default: "ddim50" of 1000 cosine steps
+            sched = schedule.SpacedSchedule(schedule.space_timesteps(1000, "ddim50"),
+                                            schedule.get_named_beta_schedule("cosine", 1000))
+        self.sched = sched
+        self.center = bool(center)
+        cfg = Config()
+        cfg.nfeats, cfg.kpad, cfg.text_dim, cfg.nsteps = NFEATS, KPAD, TEXT_DIM, self.sched.num_timesteps
+        cfg.mixing_mode = int(mixer.mixing_mode)
+        cfg.align = int(bool(mixer.align))
+        cfg.center = int(bool(center))
+        cfg.has_force = int(mixer.force_influence_val is not None)
+        cfg.force_val = float(mixer.force_influence_val or 0.0)
+        cfg.cfg_scale = float(cfg_scale)
+        tmap = (C.c_int32 * cfg.nsteps)(*self.sched.timestep_map)
+        pk.keep.append(tmap)
+        cfg.timestep_map = C.cast(tmap, C.POINTER(C.c_int32))
+        self.coef = pk.f32(torch.from_numpy(self.sched.ddim_coefficients()))
+        cfg.coef = pk.p(self.coef)
+        self.head_w, self.head_b = pk.f32(mixer.influence.out.weight), pk.f32(mixer.influence.out.bias)
+        cfg.head_w, cfg.head_b = pk.p(self.head_w), pk.p(self.head_b)
+        n1, n2 = mixer.normalizer_model1, mixer.normalizer_model2
+        self.mean1, self.std1 = pk.f32(n1.motion_mean), pk.f32(n1.motion_std)
+        self.mean2, self.std2 = pk.f32(n2.motion_mean), pk.f32(n2.motion_std)
+        cfg.mean1, cfg.std1, cfg.mean2, cfg.std2 = pk.p(self.mean1), pk.p(self.std1), pk.p(self.mean2), pk.p(self.std2)
+        self.hd = _Handle(cfg, nets, pk.keep, device)
+        self.device = device
+        self.nsteps = cfg.nsteps
+        self.mixing_mode = cfg.mixing_mode
+        self.cfg_scale = float(cfg_scale)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    @property
+    def lib(self):
+        return self.hd.lib
+
+    def bind(self, B, T):
+        self.hd.bind(B, T)
+
+    def _check_state(self, x, name):
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise TypeError(f"{name}: expected a contiguous fp32 CUDA tensor")
+
+    # -- sampler ----------------------------------------------------------------------------------
+    def set_condition(self, cond):
+        cond = _f32c(cond, self.device)
+        assert cond.shape == (self.hd.B, 8 * TEXT_DIM), f"cond must be ({self.hd.B}, {8 * TEXT_DIM})"
+        check(self.lib.mmdm_set_condition(self.hd.h, ptr(cond), cur_stream()), "mmdm_set_condition")
+
+    def set_state(self, x1, x2, step_index):
+        x1, x2 = _f32c(x1, self.device), _f32c(x2, self.device)
+        check(self.lib.mmdm_set_state(self.hd.h, ptr(x1), ptr(x2), int(step_index), cur_stream()), "mmdm_set_state")
+
+    def get_state(self):
+        shape = (self.hd.B, self.hd.T, 2 * NFEATS)
+        x1 = torch.empty(shape, device=self.device)
+        x2 = torch.empty(shape, device=self.device)
+        check(self.lib.mmdm_get_state(self.hd.h, ptr(x1), ptr(x2), cur_stream()), "mmdm_get_state")
+        return x1, x2
+
+    def step(self, final_out=None):
+        check(self.lib.mmdm_step(self.hd.h, ptr(final_out), cur_stream()), "mmdm_step")
+
+    def sample(self, cond, noise, out=None, store_influence=False, use_graph=True):
+        """whole DDIM loop; cond (B,6144), noise (B,T,524) device fp32 -> (B,T,524) real-space prediction"""
+        B, T = noise.shape[0], noise.shape[1]
+        self.bind(B, T)
+        cond = _f32c(cond, self.device)
+        noise = _f32c(noise, self.device)
+        if out is None:
+            out = torch.empty(B, T, 2 * NFEATS, device=self.device)
+        h1 = h2 = None
+        if store_influence:
+            h1 = torch.empty(self.nsteps, 2 * B, T, NFEATS, device=self.device)
+            h2 = torch.empty(self.nsteps, 2 * B, T, NFEATS, device=self.device)
+        check(self.lib.mmdm_sample(self.hd.h, ptr(cond), ptr(noise), ptr(out), ptr(h1), ptr(h2), int(use_graph),
+                                   cur_stream()), "mmdm_sample")
+        return (out, h1, h2) if store_influence else out
+
+    # -- module-level entry points ------------------------------------------------------------------
+    def mixer_forward(self, x1, x2, timesteps, cond, want_aux=False, want_influence=False, cfg_combine=False,
+                      cfg_scale=None):
+        Bx, T = x1.shape[0], x1.shape[1]
+        x1, x2, cond = _f32c(x1, self.device), _f32c(x2, self.device), _f32c(cond, self.device)
+        ts = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        rows = Bx // 2 if cfg_combine else Bx
+        out = torch.empty(rows, T, 2 * NFEATS, device=self.device)
+        o1 = torch.empty(Bx, T, 2 * NFEATS, device=self.device) if want_aux else None
+        o2 = torch.empty(Bx, T, 2 * NFEATS, device=self.device) if want_aux else None
+        w1 = torch.empty(Bx, T, NFEATS, device=self.device) if want_influence else None
+        w2 = torch.empty(Bx, T, NFEATS, device=self.device) if want_influence else None
+        check(self.lib.mmdm_mixer_forward(self.hd.h, ptr(x1), ptr(x2), ptr(ts), ptr(cond), ptr(out), ptr(o1), ptr(o2),
+                                          ptr(w1), ptr(w2), Bx, int(cfg_combine),
+                                          C.c_float(self.cfg_scale if cfg_scale is None else cfg_scale), cur_stream()),
+              "mmdm_mixer_forward")
+        return out, o1, o2, w1, w2
+
+    def cfg_forward(self, x, x2, timesteps, cond, scale, store_influence=False, owner=None):
+        """ClassifierFreeSampleModelX2.forward: doubled batch, zero condition for the second half, guidance."""
+        xx = torch.cat([x, x], 0)
+        xx2 = torch.cat([x2, x2], 0)
+        tt = torch.cat([timesteps, timesteps], 0)
+        cc = torch.cat([cond, torch.zeros_like(cond)], 0)
+        out, _, _, w1, w2 = self.mixer_forward(xx, xx2, tt, cc, want_influence=store_influence, cfg_combine=True,
+                                               cfg_scale=scale)
+        if store_influence and owner is not None:
+            owner.history_influence_i1.append(w1)
+            owner.history_influence_i2.append(w2)
+        return out
+
+    def denoiser_forward(self, which, x, timesteps, cond):
+        Bx, T = x.shape[0], x.shape[1]
+        x, cond = _f32c(x, self.device), _f32c(cond, self.device)
+        ts = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty_like(x)
+        check(self.lib.mmdm_denoiser_forward(self.hd.h, which, ptr(x), ptr(ts), ptr(cond), ptr(out), Bx, cur_stream()),
+              "mmdm_denoiser_forward")
+        return out
+
+
+class StandaloneDenoiser:
+    """engine holding a single in2INDenoiser (direct module.forward calls, BASELINE config 3)"""
+
+    def __init__(self, den, x):
+        device = x.device
+        pk = _Packer(device)
+        self.kind = NET_INTERACTION if den.mode == "interaction" else NET_INDIVIDUAL
+        nets = [_absent_net(0), _absent_net(1), _absent_net(2)]
+        nets[self.kind] = pk.pack_net(self.kind, den, den.blocks, True)
+        cfg = Config()
+        cfg.nfeats, cfg.kpad, cfg.text_dim, cfg.nsteps = NFEATS, KPAD, TEXT_DIM, 1
+        cfg.mixing_mode, cfg.align, cfg.center, cfg.has_force = 4, 0, 0, 0
+        cfg.cfg_scale = 1.0
+        tmap = (C.c_int32 * 1)(0)
+        pk.keep.append(tmap)
+        cfg.timestep_map = C.cast(tmap, C.POINTER(C.c_int32))
+        dummy = pk.f32(torch.zeros(8))
+        cfg.coef = pk.p(dummy)
+        self.hd = _Handle(cfg, nets, pk.keep, device)
+        self.device = device
+        self.rows = 0
+        self.T = 0
+
+    def matches(self, x):
+        return x.device == self.device
+
+    def forward(self, x, timesteps, cond):
+        Bx, T = x.shape[0], x.shape[1]
+        if Bx > self.rows or T != self.T:
+            self.hd.bind((Bx + 1) // 2, T)
+            self.rows, self.T = 2 * ((Bx + 1) // 2), T
+        x, cond = _f32c(x, self.device), _f32c(cond, self.device)
+        ts = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty_like(x)
+        check(self.hd.lib.mmdm_denoiser_forward(self.hd.h, self.kind, ptr(x), ptr(ts), ptr(cond), ptr(out), Bx,
+                                                cur_stream()), "mmdm_denoiser_forward")
+        return out

@@ -1,0 +1,92 @@
+"""TEST INFRASTRUCTURE ONLY — regenerates tests/golden/*.npz from the UNMODIFIED reference (CPU, build container).
+
+    python oracle/make_goldens.py
+
+Everything is derived from fixed numpy seeds (oracle/synth.py), so the fixtures only store the reference's
+OUTPUTS (plus the state-dict key list and the schedule tables). Small geometry (oracle/synth.SMALL_DIMS,
+B=2, T=24) keeps the files small; full-size parity is checked live against the oracle on the GPU box.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness, synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+B, T = 2, 24
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    dims = synth.SMALL_DIMS
+    meta = {"B": B, "T": T, "dims": dims, "weights_seed": 0, "inputs_seed": 0,
+            "generator": "oracle/make_goldens.py", "torch": torch.__version__}
+    cond, noise = synth.inputs(B, T, seed=0)
+    t_mid = torch.full((B,), 500, dtype=torch.long)
+    x1, x2 = noise, 0.9 * noise.flip(0)
+    arrays = {}
+    for mode in (1, 2, 3, 4):
+        mix, diff, cfgm = ref_harness.build_reference(dims, mixing_mode=mode, store_influence=True)
+        sd = synth.synthetic_state_dict(mix.state_dict(), seed=0)
+        mix.load_state_dict(sd, strict=True)
+        if mode == 4:
+            meta["state_dict_keys"] = {k: list(v.shape) for k, v in mix.state_dict().items()}
+            meta["timestep_map"] = list(map(int, diff.timestep_map))
+            arrays["alphas_cumprod"] = diff.alphas_cumprod
+            arrays["sqrt_recip_alphas_cumprod"] = diff.sqrt_recip_alphas_cumprod
+            arrays["sqrt_recipm1_alphas_cumprod"] = diff.sqrt_recipm1_alphas_cumprod
+            arrays["alphas_cumprod_prev"] = diff.alphas_cumprod_prev
+        with torch.no_grad(), ref_harness.reference_env():
+            out = mix(x1, t_mid, cond=cond, mask=None, x2=x2)
+            arrays[f"mixer_out_mode{mode}"] = out.numpy()
+            arrays[f"mixer_w1_mode{mode}"] = mix.history_influence_i1[-1].expand(B, T, 262).numpy().copy()
+            if mode == 4:
+                arrays["den_individual"] = mix.denoiser1(x1[..., :262], t_mid, cond=cond[:, 2304:3072]).numpy()
+                arrays["den_interaction"] = mix.denoiser2(x2, t_mid, cond=cond[:, :2304]).numpy()
+                mix.align = False
+                arrays["mixer_out_mode4_noalign"] = mix(x1, t_mid, cond=cond, mask=None, x2=x2).numpy()
+                mix.align = True
+                # one DDIM step in the middle of the schedule and the last one (index 0)
+                for idx in (30, 0):
+                    tt = torch.full((B,), idx, dtype=torch.long)
+                    o = diff.ddim_sample(cfgm, x1, x2, tt, clip_denoised=False, model_kwargs={"mask": None, "cond": cond})
+                    arrays[f"step{idx}_sample"] = o["sample"].numpy()
+                    arrays[f"step{idx}_sample2"] = o["sample2"].numpy()
+                    arrays[f"step{idx}_pred_xstart2"] = o["pred_xstart2"].numpy()
+            # whole 50-step loop from noise
+            mix.history_influence_i1, mix.history_influence_i2 = [], []
+            loop = diff.ddim_sample_loop(cfgm, (B, T, 524), noise=noise.clone(), clip_denoised=False, progress=False,
+                                         model_kwargs={"mask": None, "cond": cond})
+            arrays[f"loop_mode{mode}"] = loop.numpy()
+            if mode == 4:
+                arrays["loop_w1_first"] = mix.history_influence_i1[0].numpy()
+                arrays["loop_w1_last"] = mix.history_influence_i1[-1].numpy()
+    # motion-space unit vectors from the reference's own functions
+    alignment, quaternion, rc = ref_harness.reference_modules()
+    g = np.random.default_rng(7)
+    m_a = torch.from_numpy(g.normal(size=(3, 9, 262)).astype(np.float32))
+    m_b = torch.from_numpy(g.normal(size=(3, 9, 262)).astype(np.float32))
+    with torch.no_grad():
+        sa, sb = alignment.ih_to_smpl(m_a), alignment.ih_to_smpl(m_b)
+        _, al = alignment.align_motions(sa, sb, None)
+        arrays["unit_in_a"], arrays["unit_in_b"] = m_a.numpy(), m_b.numpy()
+        arrays["unit_roundtrip_a"] = alignment.smpl_to_ih(sa).numpy()
+        arrays["unit_aligned_b"] = alignment.smpl_to_ih(al).numpy()
+        # batch of 4 for centring: the reference's torch.cross without dim picks a wrong axis when B == 3
+        m_c = torch.from_numpy(g.normal(size=(4, 9, 262)).astype(np.float32))
+        arrays["unit_in_c"] = m_c.numpy()
+        arrays["unit_centered_c"] = alignment.smpl_to_ih(alignment.center_motion(alignment.ih_to_smpl(m_c))).numpy()
+    np.savez_compressed(os.path.join(OUT, "reference_small.npz"), **arrays)
+    with open(os.path.join(OUT, "reference_small.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("wrote", len(arrays), "arrays;", os.path.getsize(os.path.join(OUT, "reference_small.npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

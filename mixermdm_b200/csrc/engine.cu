@@ -115,6 +115,7 @@ struct mmdm_handle {
   int Tp = 0;
   bool temb_ready = false;
   cudaGraphExec_t graph = nullptr;
+  cudaStream_t cap_stream = nullptr;   // capture happens here: the legacy default stream cannot be captured
   bool graph_hist = false;
   float *graph_h1 = nullptr, *graph_h2 = nullptr, *graph_out = nullptr;
   Profiler prof;
@@ -529,6 +530,7 @@ int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_han
 void mmdm_destroy(mmdm_handle* h) {
   if (!h) return;
   drop_graph(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   h->prof.flush();
   for (auto e : h->prof.pool) cudaEventDestroy(e);
   delete h;
@@ -604,9 +606,10 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
     if (h->graph && (h->graph_out != out || h->graph_h1 != hist_i1 || h->graph_h2 != hist_i2)) drop_graph(h);
     if (!h->graph) {
       cudaGraph_t g = nullptr;
-      MMDM_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int rc = step_body(h, out, hist_i1, hist_i2, st);
-      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (!h->cap_stream) MMDM_CHECK_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+      MMDM_CHECK_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+      int rc = step_body(h, out, hist_i1, hist_i2, h->cap_stream);
+      cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
       if (rc != 0) {
         if (g) cudaGraphDestroy(g);
         return rc;

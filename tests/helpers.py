@@ -48,7 +48,12 @@ def build_oracle(sd, dims, mixing_mode=4, align=True, center=True, force=None):
                                center=center, sched=default_schedule(), force=force)
 
 
+def _t(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().float().cpu()
+    return torch.from_numpy(np.asarray(x)).float()
+
+
 def relerr(a, b):
-    a = torch.as_tensor(np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a)).float()
-    b = torch.as_tensor(np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b)).float()
+    a, b = _t(a), _t(b)
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()

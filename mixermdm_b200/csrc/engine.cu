@@ -96,6 +96,7 @@ struct Workspace {
   float *out1 = nullptr, *out2 = nullptr, *out1a = nullptr, *out2a = nullptr;  // (Bx, T, 524)
   bf16* hfin = nullptr;     // Influence output, bf16 (M, 512)
   float *x1 = nullptr, *x2 = nullptr;   // sampler state (B, T, 524)
+  float* final = nullptr;               // result of the last step (B, T, 524); copied to the caller's buffer
   int* step = nullptr;
   int* ts_idx = nullptr;    // (nsteps) int: timestep_map on device
 };
@@ -116,8 +117,8 @@ struct mmdm_handle {
   bool temb_ready = false;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t cap_stream = nullptr;   // capture happens here: the legacy default stream cannot be captured
-  bool graph_hist = false;
-  float *graph_h1 = nullptr, *graph_h2 = nullptr, *graph_out = nullptr;
+  long long graph_step_launches = 0;
+  float *graph_h1 = nullptr, *graph_h2 = nullptr;
   Profiler prof;
   long long launches = 0;
 };
@@ -204,6 +205,7 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
   ws.hfin = c.take<bf16>(M * h->net[2].w.D);
   ws.x1 = c.take<float>((size_t)B * T * nf2);
   ws.x2 = c.take<float>((size_t)B * T * nf2);
+  ws.final = c.take<float>((size_t)B * T * nf2);
   ws.step = c.take<int>(4);
   ws.ts_idx = c.take<int>(h->cfg.nsteps);
   if (w) *w = ws;
@@ -453,7 +455,7 @@ static int step_body(mmdm_handle* h, float* final_out, float* h1, float* h2, cud
   const float* temb[3] = {h->ws.temb_tab[0], h->ws.temb_tab[1], h->ws.temb_tab[2]};
   MMDM_TRY(run_mixer_nets(h, h->ws.x1, h->ws.x2, h->B, 1, temb, h->ws.step, st));
   MixStepParams P = mix_params(h);
-  P.final_out = final_out ? final_out : h->ws.out1;  // last step result (scratch if the caller does not want it)
+  P.final_out = final_out ? final_out : h->ws.final;
   P.hist_i1 = h1; P.hist_i2 = h2;
   {
     Scope sc(h, "mix_cfg_ddim", st, 0, mix_bytes(h));
@@ -602,13 +604,17 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMDM_TRY(mmdm_set_condition(h, cond, stream));
   MMDM_TRY(mmdm_set_state(h, noise, noise, h->cfg.nsteps - 1, stream));
+  const size_t out_bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
   if (use_graph && !h->prof.on) {
-    if (h->graph && (h->graph_out != out || h->graph_h1 != hist_i1 || h->graph_h2 != hist_i2)) drop_graph(h);
+    if (h->graph && (h->graph_h1 != hist_i1 || h->graph_h2 != hist_i2)) drop_graph(h);
     if (!h->graph) {
       cudaGraph_t g = nullptr;
       if (!h->cap_stream) MMDM_CHECK_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
       MMDM_CHECK_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-      int rc = step_body(h, out, hist_i1, hist_i2, h->cap_stream);
+      const long long before = h->launches;
+      int rc = step_body(h, nullptr, hist_i1, hist_i2, h->cap_stream);
+      h->graph_step_launches = h->launches - before;
+      h->launches = before;   // capturing enqueues nothing; replays are counted below
       cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
       if (rc != 0) {
         if (g) cudaGraphDestroy(g);
@@ -617,12 +623,14 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
       MMDM_CHECK_CUDA(e);
       MMDM_CHECK_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
       cudaGraphDestroy(g);
-      h->graph_out = out; h->graph_h1 = hist_i1; h->graph_h2 = hist_i2;
+      h->graph_h1 = hist_i1; h->graph_h2 = hist_i2;
     }
     for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_CHECK_CUDA(cudaGraphLaunch(h->graph, st));
-    return 0;
+    h->launches += h->graph_step_launches * h->cfg.nsteps;
+  } else {
+    for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_TRY(step_body(h, nullptr, hist_i1, hist_i2, st));
   }
-  for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_TRY(step_body(h, out, hist_i1, hist_i2, st));
+  MMDM_CHECK_CUDA(cudaMemcpyAsync(out, h->ws.final, out_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

@@ -64,7 +64,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], C::Q_BYTES + (uint32_t)(C::KA * kgroups) * (64 * 128));
@@ -111,6 +111,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   float lsum = 0.f;
   const int row = tid;
   uint8_t* Ps = Ks;
+  const uint32_t ps_addr = smem_u32(Ps);
   for (int c = 0; c < nchunks; ++c) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(trow + (uint32_t)(c * 32), r);
@@ -133,7 +134,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         pk.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
         pk.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
         const int kt = col >> 6, chunk = (col & 63) >> 3;
-        *reinterpret_cast<uint4*>(Ps + kt * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
+        sts128u(ps_addr + (uint32_t)(kt * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)), pk);
       }
     }
   }

@@ -35,126 +35,205 @@ int num_sms() {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused epilogue: one thread owns row `row`, 32 consecutive columns starting at `col0`
+// fused epilogue. One thread owns one output row of the tile and walks it in chunks of 32 columns (the
+// tcgen05.ld 32x32b shape). Everything that does not depend on the column (row validity, sequence / frame
+// index of the row) is computed once per tile in RowCtx; the per-chunk fast path has no per-element guards.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_store(const GemmEpi& ep, int row, int col0, const float* v, int M,
-                                               int N) {
-  if (row >= M || col0 >= N) return;
-  const int nvalid = min(32, N - col0);
-  float b[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) b[j] = (ep.bias != nullptr && j < nvalid) ? __ldg(ep.bias + col0 + j) : 0.f;
+struct RowCtx {
+  int row;
+  bool valid;
+  int s, t;   // row = s * T + t (only for the modes that need it)
+};
 
-  switch (ep.mode) {
-    case EPI_BF16:
-    case EPI_GELU_BF16: {
-      float o[32];
+template <int MODE>
+__device__ __forceinline__ RowCtx make_row_ctx(const GemmEpi& ep, int row, int M) {
+  RowCtx rc;
+  rc.row = row;
+  rc.valid = row < M;
+  rc.s = 0;
+  rc.t = 0;
+  if (MODE == EPI_BF16 || MODE == EPI_EMBED_PE || MODE == EPI_FINAL) {
+    rc.s = row / ep.T;
+    rc.t = row - rc.s * ep.T;
+  }
+  return rc;
+}
+
+__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col0, float* b) {
+  if (bias == nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = v[j] + b[j];
-        o[j] = (ep.mode == EPI_GELU_BF16) ? gelu_erf(x) : x;
-      }
-      if (ep.mode == EPI_BF16 && ep.vt_col0 >= 0 && col0 >= ep.vt_col0) {
-        const int s = row / ep.T, t = row - s * ep.T;
+    for (int j = 0; j < 32; ++j) b[j] = 0.f;
+    return;
+  }
+  const float4* p = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nvalid) {
-            const int n = col0 + j - ep.vt_col0;
-            const int h = n / ep.hd, d = n - h * ep.hd;
-            ep.vt[((size_t)(s * ep.H + h) * ep.hd + d) * ep.Tp + t] = __float2bfloat16_rn(o[j]);
-          }
-        }
+  for (int j = 0; j < 8; ++j) {
+    const float4 q = __ldg(p + j);
+    b[4 * j] = q.x; b[4 * j + 1] = q.y; b[4 * j + 2] = q.z; b[4 * j + 3] = q.w;
+  }
+}
+
+// generic (edge) path: per-element guards; used only for ragged N (the 262-wide output layer) and by the
+// SIMT bring-up kernel
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N) {
+  const int nvalid = min(32, N - col0);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j >= nvalid) break;
+    const int n = col0 + j;
+    const float x = v[j] + (ep.bias ? __ldg(ep.bias + n) : 0.f);
+    if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
+      const float o = (MODE == EPI_GELU_BF16) ? gelu_erf(x) : x;
+      if (MODE == EPI_BF16 && ep.vt_col0 >= 0 && n >= ep.vt_col0) {
+        const int nn = n - ep.vt_col0, h = nn / ep.hd, d = nn - h * ep.hd;
+        ep.vt[((size_t)(rc.s * ep.H + h) * ep.hd + d) * ep.Tp + rc.t] = __float2bfloat16_rn(o);
       } else {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0;
-        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            pk.x = pack_bf16x2(o[j], o[j + 1]);
-            pk.y = pack_bf16x2(o[j + 2], o[j + 3]);
-            pk.z = pack_bf16x2(o[j + 4], o[j + 5]);
-            pk.w = pack_bf16x2(o[j + 6], o[j + 7]);
-            *reinterpret_cast<uint4*>(dst + j) = pk;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) dst[j] = __float2bfloat16_rn(o[j]);
-        }
+        reinterpret_cast<__nv_bfloat16*>(ep.out)[(size_t)rc.row * ep.ldo + n] = __float2bfloat16_rn(o);
       }
-      break;
-    }
-    case EPI_RESID: {
-      const float* rs = ep.resid + (size_t)row * ep.ldo + col0;
-      float* dst = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-      float o[32];
-      if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-          ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 r4 = *reinterpret_cast<const float4*>(rs + j);
-          o[j] = r4.x + v[j] + b[j];
-          o[j + 1] = r4.y + v[j + 1] + b[j + 1];
-          o[j + 2] = r4.z + v[j + 2] + b[j + 2];
-          o[j + 3] = r4.w + v[j + 3] + b[j + 3];
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) {
-            o[j] = rs[j] + v[j] + b[j];
-            dst[j] = o[j];
-          }
-      }
-      if (ep.out_bf16 != nullptr) {
-        __nv_bfloat16* d2 = ep.out_bf16 + (size_t)row * ep.ldo + col0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) d2[j] = __float2bfloat16_rn(o[j]);
-      }
-      break;
-    }
-    case EPI_EMBED_PE: {
-      const int t = row % ep.T;
-      const float* pe = ep.pe + (size_t)t * ep.pe_ld + col0;
-      float* dst = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) {
-          const float o = v[j] + b[j] + __ldg(pe + j);
-          dst[j] = o;
-          if (ep.dup_row_offset != 0) dst[ep.dup_row_offset * ep.ldo + j] = o;
-        }
-      break;
-    }
-    case EPI_FINAL: {
-      const int s = row / ep.T, t = row - s * ep.T;
-      float* dst;
-      if (ep.persons_per_row == 2)
-        dst = reinterpret_cast<float*>(ep.out) + ((size_t)(s >> 1) * ep.T + t) * (2 * ep.nfeats) +
-              (s & 1) * ep.nfeats + col0;
-      else
-        dst = reinterpret_cast<float*>(ep.out) + ((size_t)s * ep.T + t) * ep.nfeats + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) {
-          const float y = v[j] + b[j];
-          dst[j] = ep.std != nullptr ? y * __ldg(ep.std + col0 + j) + __ldg(ep.mean + col0 + j) : y;
-        }
-      break;
-    }
-    case EPI_F32:
-    default: {
-      float* dst = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) dst[j] = v[j] + b[j];
-      break;
+    } else if (MODE == EPI_RESID) {
+      const float o = ep.resid[(size_t)rc.row * ep.ldo + n] + x;
+      reinterpret_cast<float*>(ep.out)[(size_t)rc.row * ep.ldo + n] = o;
+      if (ep.out_bf16) ep.out_bf16[(size_t)rc.row * ep.ldo + n] = __float2bfloat16_rn(o);
+    } else if (MODE == EPI_EMBED_PE) {
+      const float o = x + __ldg(ep.pe + (size_t)rc.t * ep.pe_ld + n);
+      float* dst = reinterpret_cast<float*>(ep.out) + (size_t)rc.row * ep.ldo + n;
+      *dst = o;
+      if (ep.dup_row_offset != 0) dst[ep.dup_row_offset * ep.ldo] = o;
+    } else if (MODE == EPI_FINAL) {
+      float* dst = (ep.persons_per_row == 2)
+                       ? reinterpret_cast<float*>(ep.out) + ((size_t)(rc.s >> 1) * ep.T + rc.t) * (2 * ep.nfeats) +
+                             (rc.s & 1) * ep.nfeats + n
+                       : reinterpret_cast<float*>(ep.out) + ((size_t)rc.s * ep.T + rc.t) * ep.nfeats + n;
+      *dst = ep.std != nullptr ? x * __ldg(ep.std + n) + __ldg(ep.mean + n) : x;
+    } else {
+      reinterpret_cast<float*>(ep.out)[(size_t)rc.row * ep.ldo + n] = x;
     }
   }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N) {
+  if (!rc.valid || col0 >= N) return;
+  if (col0 + 32 > N || MODE == EPI_FINAL || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
+    epilogue_chunk_edge<MODE>(ep, rc, col0, v, N);
+    return;
+  }
+  float b[32];
+  load_bias32(ep.bias, col0, b);
+  if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = (MODE == EPI_GELU_BF16) ? gelu_erf(v[j] + b[j]) : (v[j] + b[j]);
+    if (MODE == EPI_BF16 && ep.vt_col0 >= 0 && col0 >= ep.vt_col0) {
+      // V^T: the 32 columns of a chunk lie inside one head (hd is 64 or 128, chunks are 32-aligned)
+      const int nn = col0 - ep.vt_col0;
+      const int h = nn / ep.hd, d0 = nn - h * ep.hd;
+      __nv_bfloat16* dst = ep.vt + ((size_t)(rc.s * ep.H + h) * ep.hd + d0) * ep.Tp + rc.t;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[(size_t)j * ep.Tp] = __float2bfloat16_rn(o[j]);
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)rc.row * ep.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        pk.x = pack_bf16x2(o[8 * j], o[8 * j + 1]);
+        pk.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+        pk.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+        pk.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+        dst[j] = pk;
+      }
+    }
+  } else if (MODE == EPI_RESID) {
+    const float4* rs = reinterpret_cast<const float4*>(ep.resid + (size_t)rc.row * ep.ldo + col0);
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)rc.row * ep.ldo + col0);
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r4 = rs[j];
+      o[4 * j] = r4.x + v[4 * j] + b[4 * j];
+      o[4 * j + 1] = r4.y + v[4 * j + 1] + b[4 * j + 1];
+      o[4 * j + 2] = r4.z + v[4 * j + 2] + b[4 * j + 2];
+      o[4 * j + 3] = r4.w + v[4 * j + 3] + b[4 * j + 3];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    if (ep.out_bf16 != nullptr) {
+      uint4* d2 = reinterpret_cast<uint4*>(ep.out_bf16 + (size_t)rc.row * ep.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        pk.x = pack_bf16x2(o[8 * j], o[8 * j + 1]);
+        pk.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+        pk.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+        pk.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+        d2[j] = pk;
+      }
+    }
+  } else if (MODE == EPI_EMBED_PE) {
+    const float4* pe = reinterpret_cast<const float4*>(ep.pe + (size_t)rc.t * ep.pe_ld + col0);
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)rc.row * ep.ldo + col0);
+    float4* dup = ep.dup_row_offset != 0
+                      ? reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) +
+                                                  ((size_t)rc.row + ep.dup_row_offset) * ep.ldo + col0)
+                      : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 q = __ldg(pe + j);
+      const float4 o = make_float4(v[4 * j] + b[4 * j] + q.x, v[4 * j + 1] + b[4 * j + 1] + q.y,
+                                   v[4 * j + 2] + b[4 * j + 2] + q.z, v[4 * j + 3] + b[4 * j + 3] + q.w);
+      dst[j] = o;
+      if (dup) dup[j] = o;
+    }
+  } else {  // EPI_F32
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)rc.row * ep.ldo + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      dst[j] = make_float4(v[4 * j] + b[4 * j], v[4 * j + 1] + b[4 * j + 1], v[4 * j + 2] + b[4 * j + 2],
+                           v[4 * j + 3] + b[4 * j + 3]);
+  }
+}
+
+// Residual epilogue with a shared-memory transpose: accumulators arrive one ROW per thread, but the fp32
+// residual stream is read and written one row per QUARTER-WARP (4 rows x 128 B per instruction), so every
+// global access is a full 128-byte line instead of 32 scattered 16-byte pieces.
+// stg: per-warp staging of 32 x 32 floats, float4 slots XOR-swizzled -> conflict-free both ways.
+__device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_base, int lane, int col0,
+                                                       const float* v, int M, uint32_t stg) {
+  float b[32];
+  load_bias32(ep.bias, col0, b);
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    sts128(stg + (uint32_t)(lane * 8 + (g ^ (lane & 7))) * 16,
+           make_float4(v[4 * g] + b[4 * g], v[4 * g + 1] + b[4 * g + 1], v[4 * g + 2] + b[4 * g + 2], v[4 * g + 3] + b[4 * g + 3]));
+  __syncwarp();
+  const int g = lane & 7;
+  // all residual loads first (the output may alias the residual, so loads cannot be hoisted over stores)
+  float4 r4[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_base + 4 * i + (lane >> 3);
+    r4[i] = (row < M) ? *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldo + col0 + 4 * g)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    const int row = m_base + rr;
+    if (row < M) {
+      const float4 a = lds128(stg + (uint32_t)(rr * 8 + (g ^ (rr & 7))) * 16);
+      const size_t off = (size_t)row * ep.ldo + col0 + 4 * g;
+      const float4 o = make_float4(r4[i].x + a.x, r4[i].y + a.y, r4[i].z + a.z, r4[i].w + a.w);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = o;
+      if (ep.out_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(ep.out_bf16 + off) = pk;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -169,11 +248,12 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered fp32 accumulator (512 or 256)
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t STG_BYTES = 8 * 32 * 32 * 4;   // per-epilogue-warp transpose staging
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int MODE>
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmEpi ep, int M, int N, int K) {
   using C = GemmCfg<BN>;
@@ -184,6 +264,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const uint32_t stg_base = smem_u32(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -203,7 +284,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -211,7 +292,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
 
   if (warp == 0) {
     if (elect_one()) {
@@ -266,17 +347,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 epilogue warps: warps w and w+4 share TMEM lane quarter (w & 3) and split the tile's column chunks
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096;
+    constexpr int NCH = BN / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * C::BM;
       const int n0 = (tile % num_n) * BN;
+      const int c_begin = half * (NCH / 2), c_end = c_begin + NCH / 2;
+      if (MODE == EPI_RESID && ep.vec_ok) {
+        // pull this warp's share of the residual tile towards L2 while the MMAs of the tile are still running
+        const int col = n0 + c_begin * 32;
+        if (col < N) {
+          const int r = m0 + q * 32 + lane;
+          if (r < M) {
+            const float* p = ep.resid + (size_t)r * ep.ldo + col;
+#pragma unroll
+            for (int i = 0; i < (NCH / 2) * 32 * 4 / 128; ++i)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 32));
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
+      const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + c * 32) + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32b_x32(taddr, r);
@@ -284,7 +383,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epilogue_store(ep, row, n0 + c * 32, v, M, N);
+        if (MODE == EPI_RESID && ep.vec_ok && n0 + c * 32 + 32 <= N)
+          epilogue_chunk_resid_t(ep, m0 + q * 32, lane, n0 + c * 32, v, M, stg);
+        else
+          epilogue_chunk<MODE>(ep, rc, n0 + c * 32, v, N);
       }
       tc_fence_before();
       __syncwarp();
@@ -302,6 +404,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // SIMT bring-up kernel (same epilogue); used only when MMDM_GEMM_SIMT=1 to bisect tcgen05 problems.
 // ------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void gemm_simt_debug_kernel(const __nv_bfloat16* __restrict__ A, int lda,
                                        const __nv_bfloat16* __restrict__ W, int ldw, const GemmEpi ep, int M,
                                        int N, int K) {
@@ -318,16 +421,23 @@ __global__ void gemm_simt_debug_kernel(const __nv_bfloat16* __restrict__ A, int 
         if (col0 + j < N) acc[j] += a * __bfloat162float(W[(size_t)(col0 + j) * ldw + k]);
     }
   }
-  epilogue_store(ep, row, col0, acc, M, N);
+  const RowCtx rc = make_row_ctx<MODE>(ep, row, M);
+  epilogue_chunk<MODE>(ep, rc, col0, acc, N);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int MODE>
 static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                      const GemmEpi& ep, cudaStream_t stream) {
   using C = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM_BYTES));
+    attr_done = true;
+  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -345,36 +455,60 @@ static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, in
   }
   const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tn_kernel<BN><<<grid, 256, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
+  gemm_bf16_tn_kernel<BN, MODE><<<grid, 384, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int gemm_init() {
-  MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)GemmCfg<256>::SMEM_BYTES));
-  MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)GemmCfg<128>::SMEM_BYTES));
-  return 0;
-}
-
-int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
-                const GemmEpi& ep, cudaStream_t stream) {
-  MMDM_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  static int inited = gemm_init();
-  MMDM_REQUIRE(inited == 0, "gemm: kernel attribute setup failed");
-  MMDM_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 (got %d, %d)", lda, ldw);
-  MMDM_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
-               "gemm: operands must be 16-byte aligned");
+template <int MODE>
+static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                       const GemmEpi& ep, cudaStream_t stream) {
   if (use_simt()) {
     dim3 grid((M + 127) / 128, (N + 31) / 32);
-    gemm_simt_debug_kernel<<<grid, 128, 0, stream>>>(A, lda, W, ldw, ep, M, N, K);
+    gemm_simt_debug_kernel<MODE><<<grid, 128, 0, stream>>>(A, lda, W, ldw, ep, M, N, K);
     MMDM_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
   // 128x256 tiles when N fills them; 128x128 for narrow / ragged N (e.g. the 262-wide output layer)
-  if (N % 256 == 0 || N >= 1024) return launch_tc<256>(A, lda, W, ldw, M, N, K, ep, stream);
-  return launch_tc<128>(A, lda, W, ldw, M, N, K, ep, stream);
+  if (N % 256 == 0 || N >= 1024) return launch_tc<256, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
+  return launch_tc<128, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
+}
+
+// Kernel attributes are set lazily per instantiation (never inside a stream capture: the engine runs every
+// shape once eagerly before capturing, see mmdm_sample).
+int gemm_init() { return 0; }
+
+int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                const GemmEpi& ep, cudaStream_t stream) {
+  MMDM_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  MMDM_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 (got %d, %d)", lda, ldw);
+  MMDM_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  MMDM_REQUIRE(ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  GemmEpi e2 = ep;
+  e2.vec_ok = ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (ep.ldo % 8) == 0 &&
+               (ep.resid == nullptr || (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0) &&
+               (ep.out_bf16 == nullptr || (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0) &&
+               (ep.pe == nullptr || ((reinterpret_cast<uintptr_t>(ep.pe) & 15) == 0 && (ep.pe_ld % 4) == 0)))
+                  ? 1 : 0;
+  switch (ep.mode) {
+    case EPI_BF16:
+      if (ep.vt_col0 >= 0)
+        MMDM_REQUIRE((ep.vt_col0 % 32) == 0 && (ep.hd % 32) == 0 && ep.vt != nullptr, "gemm: V^T split must be 32-aligned");
+      return launch_mode<EPI_BF16>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_GELU_BF16: return launch_mode<EPI_GELU_BF16>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_RESID:
+      MMDM_REQUIRE(ep.resid != nullptr, "gemm: residual pointer missing");
+      return launch_mode<EPI_RESID>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_EMBED_PE:
+      MMDM_REQUIRE(ep.pe != nullptr, "gemm: pe table missing");
+      return launch_mode<EPI_EMBED_PE>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_FINAL: return launch_mode<EPI_FINAL>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_F32: return launch_mode<EPI_F32>(A, lda, W, ldw, M, N, K, e2, stream);
+    default: break;
+  }
+  set_last_error("gemm: unknown epilogue mode %d", ep.mode);
+  return -1;
 }
 
 }  // namespace mmdm

@@ -35,6 +35,7 @@ struct GemmEpi {
   const float* mean = nullptr;
   int nfeats = 0;
   int persons_per_row = 2;               // 2: sequences alternate persons (s&1); 1: plain (s*T+t)*nfeats
+  int vec_ok = 0;                        // set by launch_gemm: pointers/pitches allow 16-byte vector access
 };
 
 // A: [M, K] bf16 with row pitch lda (elements, lda*2 % 16 == 0); W: [N, K] bf16 pitch ldw.

@@ -5,7 +5,7 @@
 // The whole key range fits one tile, so there is no online-softmax rescaling:
 //   S[128 x NK] = Q K^T        tcgen05.mma, fp32 in TMEM (NK = round_up(T+1,16), two N<=256 instructions)
 //   P = exp2((S - max) * c)    each of the 128 threads owns one query row (tcgen05.ld 32x32b)
-//   O[128 x hd] = P V          tcgen05.mma, P staged as bf16 in 128B-swizzled smem (re-using the K tile),
+//   O[128 x hd] = P V          tcgen05.mma with the A operand (P, packed bf16) read from TMEM where it overwrote S,
 //                              V consumed K-major from the transposed V^T buffer the QKV GEMM writes.
 // Key row T is zero-filled by TMA out-of-bounds handling, which *is* the zero-attention key; key columns
 // > T are masked. Rows/keys beyond the sequence never touch HBM.
@@ -21,43 +21,59 @@ struct AttnParams {
 
 template <int HD>
 struct AttnCfg {
-  static constexpr int KA = HD / 64;                       // 64-wide K atoms along head dim
-  static constexpr uint32_t Q_BYTES = KA * 128 * 128;      // [KA][128 rows][128 B]
-  static constexpr uint32_t K_BYTES = KA * 320 * 128;      // [KA][320 rows][128 B]
-  static constexpr uint32_t P_BYTES = 5 * 128 * 128;       // [5][128 rows][128 B]
-  static constexpr uint32_t KP_BYTES = K_BYTES > P_BYTES ? K_BYTES : P_BYTES;
-  static constexpr uint32_t V_BYTES = 5 * HD * 128;        // [5][HD rows][128 B]
-  static constexpr size_t SMEM_BYTES = Q_BYTES + KP_BYTES + V_BYTES + 1024 + 128;
-  static constexpr uint32_t O_COL = 320;
+  static constexpr int KA = HD / 64;                       // 64-wide K atoms along the head dim
+  static constexpr uint32_t Q_BYTES = KA * 128 * 128;      // one Q tile  [KA][128 rows][128 B]   (x2 buffers)
+  static constexpr uint32_t K_BYTES = KA * 320 * 128;      // keys        [KA][320 rows][128 B]
+  static constexpr uint32_t V_BYTES = 5 * HD * 128;        // V^T         [5][HD rows][128 B]
+  static constexpr size_t SMEM_BYTES = 2 * Q_BYTES + K_BYTES + V_BYTES + 1024 + 256;
+  static constexpr uint32_t O_COL = 320;                   // TMEM: S/P in [0,320), O in [320, 320+HD)
+  static constexpr int THREADS = 160;                      // 4 softmax warps + 1 TMA/MMA warp
 };
 
+// Persistent kernel. Work item = (sequence, head); its K / V^T tiles stay in shared memory while the
+// ceil(T/128) query tiles stream through a double-buffered Q slot. Per query tile:
+//   MMA1  S = Q K^T               (SS, fp32 in TMEM)                      warp 4, one lane
+//   softmax, one thread per row   (two TMEM passes; P written back to TMEM as packed bf16, in place of S)
+//   MMA2  O = P V                 (TS: A operand read from TMEM)          warp 4, one lane
+//   O / rowsum -> bf16 -> global                                          softmax warps
 template <int HD>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(AttnCfg<HD>::THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using C = AttnCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Qs = smem;
-  uint8_t* Ks = Qs + C::Q_BYTES;  // later re-used for P
-  uint8_t* Vs = Ks + C::KP_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + C::V_BYTES);  // [0]=QK loaded [1]=V loaded [2]=S done [3]=O done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint8_t* Qs = smem;                       // 2 buffers
+  uint8_t* Ks = Qs + 2 * C::Q_BYTES;
+  uint8_t* Vs = Ks + C::K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + C::V_BYTES);
+  uint64_t* qfull = bars;        // [2]
+  uint64_t* kfull = bars + 2;
+  uint64_t* vfull = bars + 3;
+  uint64_t* sfull = bars + 4;
+  uint64_t* pfull = bars + 5;
+  uint64_t* ofull = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = tid >> 5, lane = tid & 31;
   const int QT = (p.T + 127) / 128;
-  const int qt = blockIdx.x % QT;
-  const int h = (blockIdx.x / QT) % p.H;
-  const int s = blockIdx.x / (QT * p.H);
-  const int ks = s ^ p.kv_xor;
+  const int total_items = p.S * p.H;
+  const int nitems = (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int njobs = nitems * QT;
   const int kgroups = (p.NK + 63) / 64;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&qfull[0], 1);
+    mbar_init(&qfull[1], 1);
+    mbar_init(kfull, 1);
+    mbar_init(vfull, 1);
+    mbar_init(sfull, 1);
+    mbar_init(pfull, 4);
+    mbar_init(ofull, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -66,123 +82,179 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], C::Q_BYTES + (uint32_t)(C::KA * kgroups) * (64 * 128));
-    for (int a = 0; a < C::KA; ++a) tma_load_3d(Qs + a * (128 * 128), &tmQ, &bars[0], h * HD + a * 64, qt * 128, s);
-    for (int a = 0; a < C::KA; ++a)
-      for (int r = 0; r < kgroups; ++r)
-        tma_load_3d(Ks + a * (320 * 128) + r * (64 * 128), &tmK, &bars[0], h * HD + a * 64, r * 64, ks);
-    mbar_arrive_expect_tx(&bars[1], (uint32_t)kgroups * (HD * 128));
-    for (int kt = 0; kt < kgroups; ++kt) tma_load_3d(Vs + kt * (HD * 128), &tmV, &bars[1], kt * 64, 0, ks * p.H + h);
-
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    const uint32_t id1 = umma_idesc_bf16(128, p.n1);
-    const uint32_t id2 = umma_idesc_bf16(128, p.n2);
-    const uint32_t q0 = smem_u32(Qs), k0 = smem_u32(Ks);
+  if (warp == 4) {
+    if (lane == 0) {
+      auto item_sh = [&](int k, int& s, int& h) {
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;
+        s = item / p.H;
+        h = item - s * p.H;
+      };
+      auto issue_q = [&](int j) {
+        if (j >= njobs) return;
+        int s, h;
+        item_sh(j / QT, s, h);
+        const int qt = j % QT, b = j & 1;
+        mbar_arrive_expect_tx(&qfull[b], C::Q_BYTES);
+        for (int a = 0; a < C::KA; ++a)
+          tma_load_3d(Qs + b * C::Q_BYTES + a * (128 * 128), &tmQ, &qfull[b], h * HD + a * 64, qt * 128, s);
+      };
+      auto issue_k = [&](int k) {
+        int s, h;
+        item_sh(k, s, h);
+        const int ks = s ^ p.kv_xor;
+        mbar_arrive_expect_tx(kfull, (uint32_t)(C::KA * kgroups) * (64 * 128));
+        for (int a = 0; a < C::KA; ++a)
+          for (int r = 0; r < kgroups; ++r)
+            tma_load_3d(Ks + a * (320 * 128) + r * (64 * 128), &tmK, kfull, h * HD + a * 64, r * 64, ks);
+      };
+      auto issue_v = [&](int k) {
+        int s, h;
+        item_sh(k, s, h);
+        const int ks = s ^ p.kv_xor;
+        mbar_arrive_expect_tx(vfull, (uint32_t)kgroups * (HD * 128));
+        for (int kt = 0; kt < kgroups; ++kt) tma_load_3d(Vs + kt * (HD * 128), &tmV, vfull, kt * 64, 0, ks * p.H + h);
+      };
+      const uint32_t id1 = umma_idesc_bf16(128, p.n1);
+      const uint32_t id2 = umma_idesc_bf16(128, p.n2);
+      const uint32_t ido = umma_idesc_bf16(128, HD);
+      const uint32_t k0 = smem_u32(Ks), v0 = smem_u32(Vs);
+      const int ksteps = p.NK / 16;
+      if (nitems > 0) {
+        issue_k(0);
+        issue_q(0);
+        issue_q(1);
+        issue_v(0);
+      }
+      for (int j = 0; j < njobs; ++j) {
+        const int k = j / QT, qt = j - k * QT;
+        if (qt == 0) mbar_wait(kfull, k & 1);
+        mbar_wait(&qfull[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q0 = smem_u32(Qs + (j & 1) * C::Q_BYTES);
 #pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
-      const uint32_t aoff = (uint32_t)(kk >> 2) * (128 * 128) + (uint32_t)(kk & 3) * 32;
-      const uint32_t boff = (uint32_t)(kk >> 2) * (320 * 128) + (uint32_t)(kk & 3) * 32;
-      const uint64_t da = umma_desc_k_sw128(q0 + aoff);
-      umma_bf16_ss(tmem_base, da, umma_desc_k_sw128(k0 + boff), id1, kk > 0 ? 1u : 0u);
-      if (p.n2 > 0)
-        umma_bf16_ss(tmem_base + (uint32_t)p.n1, da, umma_desc_k_sw128(k0 + boff + (uint32_t)p.n1 * 128), id2,
-                     kk > 0 ? 1u : 0u);
-    }
-    umma_commit(&bars[2]);
-  }
-  __syncwarp();
-
-  // ---- softmax: thread <-> query row -----------------------------------------------------------
-  mbar_wait(&bars[2], 0);
-  tc_fence_after();
-  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const int nchunks = (p.NK + 31) / 32;
-  float mx = 0.f;  // the zero-attention key contributes logit 0
-  for (int c = 0; c < nchunks; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(trow + (uint32_t)(c * 32), r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c * 32 + j < p.T) mx = fmaxf(mx, __uint_as_float(r[j]));
-  }
-  float lsum = 0.f;
-  const int row = tid;
-  uint8_t* Ps = Ks;
-  const uint32_t ps_addr = smem_u32(Ps);
-  for (int c = 0; c < nchunks; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(trow + (uint32_t)(c * 32), r);
-    tmem_ld_wait();
-    float pv[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      const float e = exp2f((__uint_as_float(r[j]) - mx) * p.scale_log2);
-      pv[j] = (col <= p.T) ? e : 0.f;
-      lsum += pv[j];
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = c * 32 + g * 8;
-      if (col < p.NK) {
-        uint4 pk;
-        pk.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-        pk.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-        pk.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-        pk.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-        const int kt = col >> 6, chunk = (col & 63) >> 3;
-        sts128u(ps_addr + (uint32_t)(kt * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)), pk);
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t aoff = (uint32_t)(kk >> 2) * (128 * 128) + (uint32_t)(kk & 3) * 32;
+          const uint32_t boff = (uint32_t)(kk >> 2) * (320 * 128) + (uint32_t)(kk & 3) * 32;
+          const uint64_t da = umma_desc_k_sw128(q0 + aoff);
+          umma_bf16_ss(tmem_base, da, umma_desc_k_sw128(k0 + boff), id1, kk > 0 ? 1u : 0u);
+          if (p.n2 > 0)
+            umma_bf16_ss(tmem_base + (uint32_t)p.n1, da, umma_desc_k_sw128(k0 + boff + (uint32_t)p.n1 * 128), id2,
+                         kk > 0 ? 1u : 0u);
+        }
+        umma_commit(sfull);
+        // P(j) ready in TMEM => MMA1(j) has completed: its Q slot (and, after the last tile, K) can be refilled
+        mbar_wait(pfull, j & 1);
+        tc_fence_after();
+        issue_q(j + 2);
+        if (qt == QT - 1 && k + 1 < nitems) issue_k(k + 1);
+        if (qt == 0) mbar_wait(vfull, k & 1);
+        for (int i = 0; i < ksteps; ++i) {
+          const uint32_t boff = (uint32_t)(i >> 2) * (HD * 128) + (uint32_t)(i & 3) * 32;
+          umma_bf16_ts(tmem_base + C::O_COL, tmem_base + (uint32_t)(i * 8), umma_desc_k_sw128(v0 + boff), ido,
+                       i > 0 ? 1u : 0u);
+        }
+        umma_commit(ofull);
+        if (qt == QT - 1 && k + 1 < nitems) {
+          mbar_wait(ofull, j & 1);   // MMA2 of the last tile done: V^T can be replaced
+          issue_v(k + 1);
+        }
       }
     }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-
-  if (tid == 0) {
-    tc_fence_after();
-    mbar_wait(&bars[1], 0);
-    const uint32_t ido = umma_idesc_bf16(128, HD);
-    const uint32_t p0 = smem_u32(Ps), v0 = smem_u32(Vs);
-    const int ksteps = p.NK / 16;
-    for (int j = 0; j < ksteps; ++j) {
-      const uint32_t aoff = (uint32_t)(j >> 2) * (128 * 128) + (uint32_t)(j & 3) * 32;
-      const uint32_t boff = (uint32_t)(j >> 2) * (HD * 128) + (uint32_t)(j & 3) * 32;
-      umma_bf16_ss(tmem_base + C::O_COL, umma_desc_k_sw128(p0 + aoff), umma_desc_k_sw128(v0 + boff), ido,
-                   j > 0 ? 1u : 0u);
-    }
-    umma_commit(&bars[3]);
-  }
-  __syncwarp();
-
-  mbar_wait(&bars[3], 0);
-  tc_fence_after();
-  const float inv = 1.0f / lsum;
-  const int t = qt * 128 + row;
+  } else {
+    // ---- softmax / output warps: thread <-> query row ------------------------------------------------
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int nchunks = (p.NK + 31) / 32;
+    const int row = tid;
+    for (int j = 0; j < njobs; ++j) {
+      const int k = j / QT, qt = j - k * QT;
+      const int item = (int)blockIdx.x + k * (int)gridDim.x;
+      const int s = item / p.H, h = item - s * p.H;
+      mbar_wait(sfull, j & 1);
+      tc_fence_after();
+      float mx = 0.f;   // the zero-attention key contributes logit 0
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(trow + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (c * 32 + 32 <= p.T) {
 #pragma unroll
-  for (int c = 0; c < HD / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(trow + C::O_COL + (uint32_t)(c * 32), r);
-    tmem_ld_wait();
-    if (t < p.T) {
-      __nv_bfloat16* dst = p.out + ((size_t)s * p.T + t) * p.ldo + h * HD + c * 32;
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-        pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-        pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-        pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + j) = pk;
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < p.T) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
+      const float moff = mx * p.scale_log2;
+      float lsum = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(trow + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        float pv[32];
+        if (c * 32 + 32 <= p.T) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -moff));
+            lsum += pv[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -moff));
+            pv[i] = (c * 32 + i <= p.T) ? e : 0.f;
+            lsum += pv[i];
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+        tmem_st_32x32b_x16(trow + (uint32_t)(c * 16), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull);
+
+      mbar_wait(ofull, j & 1);
+      tc_fence_after();
+      const float inv = 1.0f / lsum;
+      const int t = qt * 128 + row;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(trow + C::O_COL + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (t < p.T) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)s * p.T + t) * p.ldo + h * HD + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+            dst[i] = o;
+          }
+        }
+      }
+      tc_fence_before();   // O reads retire before the next P arrive lets MMA2(j+1) overwrite O
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+static int num_sms_attn() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 template <int HD>
@@ -218,8 +290,9 @@ static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat
   p.ldo = ldo;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   p.out = out;
-  const int QT = (T + 127) / 128;
-  attention_kernel<HD><<<S * H * QT, 128, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  const int items = S * H;
+  const int grid = items < num_sms_attn() ? items : num_sms_attn();
+  attention_kernel<HD><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,69 @@
+// micro-benchmark: per-SM throughput of ex2.approx, F2FP bf16 pack, and an FMA-pipe exp2 polynomial on sm_100a
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+template <int MODE>
+__global__ void k(float* out, int iters, float seed) {
+  float a[8];
+  for (int i = 0; i < 8; ++i) a[i] = seed * (threadIdx.x + i) * 1e-3f - 1.0f;
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE == 0) {
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a[i]) : "f"(a[i]));
+      } else if (MODE == 1) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a[i], a[(i + 1) & 7]);
+        acc += *reinterpret_cast<uint32_t*>(&v);
+        a[i] += 1.0f;
+      } else if (MODE == 2) {
+        // exp2(x), x <= 0: magic-number floor + degree-3 polynomial + exponent add
+        float x = fmaxf(a[i], -120.f);
+        float t = x + 12582912.f;
+        float n = t - 12582912.f;
+        float f = x - n;                       // in [-0.5, 0.5]
+        float p = fmaf(fmaf(fmaf(0.0555f, f, 0.2402f), f, 0.6931f), f, 1.0f);
+        a[i] = __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+      } else if (MODE == 3) {
+        a[i] = fmaf(a[i], 1.0001f, 0.5f);
+      } else if (MODE == 4) {
+        // truncating pack via PRMT
+        acc += __byte_perm(__float_as_uint(a[i]), __float_as_uint(a[(i + 1) & 7]), 0x7632);
+        a[i] += 1.0f;
+      }
+    }
+  }
+  float s = 0;
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s + acc;
+}
+template <int MODE>
+void run(const char* name, int warps_per_sm) {
+  int iters = 4096;
+  float* out;
+  cudaMalloc(&out, 148 * 1024 * 4);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k<MODE><<<148, warps_per_sm * 32>>>(out, 16, 1.f);
+  cudaEventRecord(e0);
+  k<MODE><<<148, warps_per_sm * 32>>>(out, iters, 1.f);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double ops = 148.0 * warps_per_sm * 32 * (double)iters * 8;
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  double cycles = ms * 1e-3 * clk * 1e3;
+  printf("%-28s warps/SM %2d : %.2f elem-ops/clk/SM (%.3f ms)\n", name, warps_per_sm, ops / 148.0 / cycles, ms);
+  cudaFree(out);
+}
+int main() {
+  for (int w : {4, 8, 16}) {
+    run<0>("ex2.approx.ftz.f32", w);
+    run<1>("F2FP bf16x2 pack (+FADD)", w);
+    run<2>("poly exp2 (FMA pipe)", w);
+    run<3>("FFMA", w);
+    run<4>("PRMT pack (+FADD)", w);
+  }
+  return 0;
+}

@@ -188,9 +188,11 @@ int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream);
 int mmdm_step(mmdm_handle* h, float* final_out /* (B,T,524) written when the index is 0, or NULL */, void* stream);
 /* whole loop from noise; result = pred_xstart2 of the last step (gaussian_diffusion.py:1769-1820).
  * use_graph != 0 replays one captured step graph nsteps times. hist_i1/hist_i2: optional
- * (nsteps, 2B, T, 262) fp32 device buffers receiving the expanded Mixer weights, or NULL. */
+ * (nsteps, 2B, T, 262) fp32 device buffers receiving the expanded Mixer weights, or NULL.
+ * hist_out1/out2/mix: optional (nsteps, 2B, T, 524) buffers with the aligned predictions and out_influenced of
+ * every step (Mixer mode "eval", mixermdm.py:805-809); all three or none; forces the eager (non-graph) loop. */
 int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* out, float* hist_i1,
-                float* hist_i2, int use_graph, void* stream);
+                float* hist_i2, float* hist_out1, float* hist_out2, float* hist_mix, int use_graph, void* stream);
 
 /* Mixer.forward in mode "eval_intermediate" (mixermdm.py:660-811) on an explicit batch of Bx rows
  * (the caller did any CFG doubling): returns out_influenced (Bx,T,524); optional out1/out2 (aligned) and the

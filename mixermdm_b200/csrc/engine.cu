@@ -451,12 +451,26 @@ static double mix_bytes(const mmdm_handle* h) {
   return (double)h->B * h->T * (2.0 * 2 * 512 * 2 + 2.0 * 2 * 524 * 4 + 2.0 * 524 * 4 + 2.0 * 524 * 4);
 }
 
-static int step_body(mmdm_handle* h, float* final_out, float* h1, float* h2, cudaStream_t st) {
+struct EvalHist {   // optional per-step outputs of Mixer mode "eval" (mixermdm.py:805-809), each (nsteps, 2B, T, 524)
+  float* out1 = nullptr;
+  float* out2 = nullptr;
+  float* mix = nullptr;
+  int slot = 0;
+};
+
+static int step_body(mmdm_handle* h, float* final_out, float* h1, float* h2, cudaStream_t st,
+                     const EvalHist* eh = nullptr) {
   const float* temb[3] = {h->ws.temb_tab[0], h->ws.temb_tab[1], h->ws.temb_tab[2]};
   MMDM_TRY(run_mixer_nets(h, h->ws.x1, h->ws.x2, h->B, 1, temb, h->ws.step, st));
   MixStepParams P = mix_params(h);
   P.final_out = final_out ? final_out : h->ws.final;
   P.hist_i1 = h1; P.hist_i2 = h2;
+  if (eh != nullptr && eh->out1 != nullptr) {
+    const size_t n = (size_t)2 * h->B * h->T * 2 * h->cfg.nfeats;
+    MMDM_CHECK_CUDA(cudaMemcpyAsync(eh->out1 + n * eh->slot, h->ws.out1a, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MMDM_CHECK_CUDA(cudaMemcpyAsync(eh->out2 + n * eh->slot, h->ws.out2a, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    P.mix_out = eh->mix + n * eh->slot;
+  }
   {
     Scope sc(h, "mix_cfg_ddim", st, 0, mix_bytes(h));
     MMDM_TRY(launch_mixstep(P, st));
@@ -599,13 +613,15 @@ int mmdm_step(mmdm_handle* h, float* final_out, void* stream) {
 }
 
 int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* out, float* hist_i1, float* hist_i2,
-                int use_graph, void* stream) {
+                float* hist_out1, float* hist_out2, float* hist_mix, int use_graph, void* stream) {
   MMDM_REQUIRE(h && h->ws_base && cond && noise && out, "mmdm_sample: handle not bound / null argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMDM_TRY(mmdm_set_condition(h, cond, stream));
   MMDM_TRY(mmdm_set_state(h, noise, noise, h->cfg.nsteps - 1, stream));
   const size_t out_bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
-  if (use_graph && !h->prof.on) {
+  const bool eval_hist = hist_out1 || hist_out2 || hist_mix;
+  if (eval_hist) MMDM_REQUIRE(hist_out1 && hist_out2 && hist_mix, "mmdm_sample: the three eval-mode history buffers come together");
+  if (use_graph && !h->prof.on && !eval_hist) {
     if (h->graph && (h->graph_h1 != hist_i1 || h->graph_h2 != hist_i2)) drop_graph(h);
     if (!h->graph) {
       cudaGraph_t g = nullptr;
@@ -628,7 +644,12 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
     for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_CHECK_CUDA(cudaGraphLaunch(h->graph, st));
     h->launches += h->graph_step_launches * h->cfg.nsteps;
   } else {
-    for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_TRY(step_body(h, nullptr, hist_i1, hist_i2, st));
+    EvalHist eh;
+    eh.out1 = hist_out1; eh.out2 = hist_out2; eh.mix = hist_mix;
+    for (int i = 0; i < h->cfg.nsteps; ++i) {
+      eh.slot = i;
+      MMDM_TRY(step_body(h, nullptr, hist_i1, hist_i2, st, eval_hist ? &eh : nullptr));
+    }
   }
   MMDM_CHECK_CUDA(cudaMemcpyAsync(out, h->ws.final, out_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;

@@ -279,7 +279,7 @@ mixstep_kernel(const MixStepParams P) {
         const float o1u = __ldg(P.out1a + ru + f), o2u = __ldg(P.out2a + ru + f);
         mu = o2u + wu * (o1u - o2u);
       }
-      if (P.mix_only == 1) {
+      if (P.mix_only == 1 || (P.mix_only == 0 && P.mix_out != nullptr)) {   // out_influenced (history in "eval" mode)
         P.mix_out[rc + f] = mc;
         if (two) P.mix_out[ru + f] = mu;
       }

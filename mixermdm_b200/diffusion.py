@@ -87,10 +87,19 @@ class MixerDiffusion:
         if noise is None:
             noise = torch.randn(*shape, device=device)
         mixer, eng = self._engine_for(model, B, T, torch.device(device))
-        res = eng.sample(cond, noise, store_influence=mixer.store_influence)
+        want_out = (mixer.mode == "eval")
+        res = eng.sample(cond, noise, store_influence=mixer.store_influence, store_outputs=want_out)
+        if not (mixer.store_influence or want_out):
+            return res
+        res = list(res)
+        out = res.pop(0)
         if mixer.store_influence:
-            out, h1, h2 = res
+            h1, h2 = res.pop(0), res.pop(0)
             mixer.history_influence_i1.extend(list(h1.unbind(0)))
             mixer.history_influence_i2.extend(list(h2.unbind(0)))
-            return out
-        return res
+        if want_out:
+            o1, o2, om = res
+            mixer.history_out1.extend(list(o1.unbind(0)))
+            mixer.history_out2.extend(list(o2.unbind(0)))
+            mixer.history_out_influenced.extend(list(om.unbind(0)))
+        return out

@@ -317,21 +317,30 @@ class MixerEngine:
     def step(self, final_out=None):
         check(self.lib.mmdm_step(self.hd.h, ptr(final_out), cur_stream()), "mmdm_step")
 
-    def sample(self, cond, noise, out=None, store_influence=False, use_graph=True):
-        """whole DDIM loop; cond (B,6144), noise (B,T,524) device fp32 -> (B,T,524) real-space prediction"""
+    def sample(self, cond, noise, out=None, store_influence=False, use_graph=True, store_outputs=False):
+        """whole DDIM loop; cond (B,6144), noise (B,T,524) device fp32 -> (B,T,524) real-space prediction.
+        store_influence: also return the per-step expanded weights, 2 x (nsteps, 2B, T, 262).
+        store_outputs:   also return out1 / out2 / out_influenced of every step, 3 x (nsteps, 2B, T, 524)."""
         B, T = noise.shape[0], noise.shape[1]
         self.bind(B, T)
         cond = _f32c(cond, self.device)
         noise = _f32c(noise, self.device)
         if out is None:
             out = torch.empty(B, T, 2 * NFEATS, device=self.device)
-        h1 = h2 = None
+        h1 = h2 = o1 = o2 = om = None
         if store_influence:
             h1 = torch.empty(self.nsteps, 2 * B, T, NFEATS, device=self.device)
             h2 = torch.empty(self.nsteps, 2 * B, T, NFEATS, device=self.device)
-        check(self.lib.mmdm_sample(self.hd.h, ptr(cond), ptr(noise), ptr(out), ptr(h1), ptr(h2), int(use_graph),
-                                   cur_stream()), "mmdm_sample")
-        return (out, h1, h2) if store_influence else out
+        if store_outputs:
+            o1, o2, om = [torch.empty(self.nsteps, 2 * B, T, 2 * NFEATS, device=self.device) for _ in range(3)]
+        check(self.lib.mmdm_sample(self.hd.h, ptr(cond), ptr(noise), ptr(out), ptr(h1), ptr(h2), ptr(o1), ptr(o2),
+                                   ptr(om), int(use_graph), cur_stream()), "mmdm_sample")
+        res = [out]
+        if store_influence:
+            res += [h1, h2]
+        if store_outputs:
+            res += [o1, o2, om]
+        return res[0] if len(res) == 1 else tuple(res)
 
     # -- module-level entry points ------------------------------------------------------------------
     def mixer_forward(self, x1, x2, timesteps, cond, want_aux=False, want_influence=False, cfg_combine=False,

@@ -243,3 +243,64 @@ def test_mix_cfg_ddim_kernel_vs_oracle(mode, final):
     slot = 50 - 1 - step
     wexp = mixer_oracle.expand_weights(w[:, 0], T, mode).expand(2 * B, T, 262)
     assert relerr(keep["h1"][slot], wexp) < 1e-4
+
+
+def test_top_level_mixermdm_forward_contract(golden):
+    """MixerMDM.forward / forward_test (reference mixermdm.py:490-602): dict keys, history lengths/shapes and the
+    sampled motion against the reference's golden loop output."""
+    from mixermdm_b200.mixermdm import AttrDict, MixerMDM
+    arr, meta = golden
+    dd, dm = meta["dims"]["den"], meta["dims"]["mix"]
+    den = AttrDict(NAME="in2IN", NUM_LAYERS=dd["num_layers"], NUM_HEADS=dd["num_heads"], DROPOUT=0.1, INPUT_DIM=262,
+                   LATENT_DIM=dd["latent_dim"], FF_SIZE=dd["ff_size"], ACTIVATION="gelu", CHECKPOINT=None, STRATEGY="ddim50")
+    cfg = AttrDict(NAME="MixerMDM", MODEL1=AttrDict(den, NAME="in2INind"), MODEL2=den, ACTIVATION="gelu",
+                   MOTION_REP="global", CFG_WEIGHT=3.5, MIXING_MODE=4, DIFFUSION_STEPS=1000, BETA_SCHEDULER="cosine",
+                   SAMPLER="uniform", FORCE_INFLUENCE_VAL=None,
+                   GENERATOR=AttrDict(NUM_LAYERS=dm["n_blocks"], NUM_HEADS=dm["n_heads"], DROPOUT=0.1, INPUT_DIM=262,
+                                      LATENT_DIM=dm["latent_dim"], FF_SIZE=dm["ff_size"]),
+                   DISCRIMINATOR=AttrDict(NUM_LAYERS=1, NUM_HEADS=4, DROPOUT=0.1, INPUT_DIM=262, LATENT_DIM=64, FF_SIZE=128))
+    model = MixerMDM(cfg, normalizers=synth.normalizer_stats())
+    sd = synth.synthetic_state_dict(model.mixing.state_dict(), seed=meta["weights_seed"])
+    model.mixing.load_state_dict(sd, strict=True)       # denoisers are shared objects: model1/2 see the same tensors
+    model = model.to(DEV)
+    cond, noise, *_ = _inputs(meta)
+    B, T = meta["B"], meta["T"]
+    batch = {"cond": cond, "noise": noise.clone(), "motion_lens": torch.full((B,), T, dtype=torch.long)}
+    out = model.forward_test(dict(batch))
+    torch.cuda.synchronize()
+    assert set(out) == {"output", "influence_i1", "influence_i2"}
+    assert len(out["influence_i1"]) == 50 and out["influence_i1"][0].shape == (2 * B, T, 262)
+    assert report("MixerMDM.forward_test loop", relerr(out["output"], arr["loop_mode4"])) < LOOP_TOL
+    full = model.forward(dict(batch))
+    torch.cuda.synchronize()
+    assert set(full) == {"output", "influence_i1", "influence_i2", "out1", "out2", "out_influenced"}
+    assert len(full["out1"]) == len(full["out2"]) == len(full["out_influenced"]) == 50
+    assert full["out_influenced"][0].shape == (2 * B, T, 524)
+    assert torch.equal(full["output"], out["output"])                    # eager eval-mode loop == graph loop
+    # first step of the history against the oracle's Mixer.forward on the CFG-doubled batch
+    orc = build_oracle(sd, meta["dims"])
+    tt = torch.full((2 * B,), 980, dtype=torch.long)
+    x = torch.cat([noise, noise]).cpu()
+    cc = torch.cat([cond, torch.zeros_like(cond)]).cpu()
+    with torch.no_grad():
+        d = orc.mixer(x, x, tt, cc, detail=True)
+    assert report("eval history out1[0]", relerr(full["out1"][0], d["out1"])) < TOL_BF16
+    assert report("eval history out2[0]", relerr(full["out2"][0], d["out2"])) < TOL_BF16
+    assert report("eval history out_influenced[0]", relerr(full["out_influenced"][0], d["out"])) < TOL_BF16
+
+
+def test_sampler_rejects_what_the_reference_path_never_uses(golden):
+    from mixermdm_b200.diffusion import MixerDiffusion, get_named_beta_schedule, space_timesteps
+    from mixermdm_b200.modules import ClassifierFreeSampleModelX2
+    _, meta = golden
+    mix, _ = build_mixer(meta["dims"])
+    diff = MixerDiffusion(use_timesteps=space_timesteps(1000, "ddim50"), betas=get_named_beta_schedule("cosine", 1000))
+    cfgm = ClassifierFreeSampleModelX2(mix.to(DEV), 3.5)
+    kw = dict(model_kwargs={"mask": None, "cond": torch.zeros(2, 6144, device=DEV)})
+    with pytest.raises(NotImplementedError):
+        diff.ddim_sample_loop(cfgm, (2, 24, 524), clip_denoised=True, **kw)
+    with pytest.raises(NotImplementedError):
+        diff.ddim_sample_loop(cfgm, (2, 24, 524), clip_denoised=False, eta=0.5, **kw)
+    with pytest.raises(Exception):
+        mix.to(DEV)(torch.zeros(2, 400, 524, device=DEV), torch.zeros(2, dtype=torch.long, device=DEV),
+                    cond=torch.zeros(2, 6144, device=DEV), x2=torch.zeros(2, 400, 524, device=DEV))   # T > 319

@@ -304,3 +304,68 @@ def test_sampler_rejects_what_the_reference_path_never_uses(golden):
     with pytest.raises(Exception):
         mix.to(DEV)(torch.zeros(2, 400, 524, device=DEV), torch.zeros(2, dtype=torch.long, device=DEV),
                     cond=torch.zeros(2, 6144, device=DEV), x2=torch.zeros(2, 400, 524, device=DEV))   # T > 319
+
+
+# ---- full-size geometry (BASELINE configs): D=1024, 8 layers, T=300 --------------------------------------------
+@pytest.fixture(scope="module")
+def full_model():
+    mix, sd = build_mixer(synth.FULL_DIMS, seed=2)
+    return mix.to(DEV), sd
+
+
+def test_full_size_step_vs_oracle(full_model):
+    """config[0] geometry (B=1, 300 frames): one guided Mixer evaluation + DDIM update against the CPU oracle"""
+    mix, sd = full_model
+    cond, noise = synth.inputs(1, 300, seed=9)
+    x1, x2 = noise, 0.8 * noise
+    idx = 37
+    eng = mix.engine(2, 300, torch.device(DEV), sched=default_schedule(), cfg_scale=3.5, center=True)
+    eng.set_condition(cond.to(DEV))
+    eng.set_state(x1.to(DEV), x2.to(DEV), idx)
+    eng.step()
+    s1, s2 = eng.get_state()
+    t = torch.full((1,), default_schedule().timestep_map[idx], dtype=torch.long)
+    out, *_ = eng.mixer_forward(torch.cat([x1, x1]).to(DEV), torch.cat([x2, x2]).to(DEV), torch.cat([t, t]).to(DEV),
+                                torch.cat([cond, torch.zeros_like(cond)]).to(DEV))
+    torch.cuda.synchronize()
+    orc = build_oracle(sd, synth.FULL_DIMS)
+    with torch.no_grad():
+        ref = orc.ddim_step(x1, x2, idx, cond)
+        ref_mix = orc.mixer(torch.cat([x1, x1]), torch.cat([x2, x2]), torch.cat([t, t]), torch.cat([cond, torch.zeros_like(cond)]))
+    assert report("full-size Mixer.forward (Be=2)", relerr(out, ref_mix)) < TOL_BF16
+    assert report("full-size DDIM step stream1", relerr(s1, ref["sample"])) < TOL_BF16
+    assert report("full-size DDIM step stream2", relerr(s2, ref["sample2"])) < TOL_BF16
+
+
+def test_full_size_interaction_denoiser_batch64_properties(full_model):
+    """config[2] geometry: interaction denoiser alone, batch 64 x 300 frames. Size-independent checks: rows of a
+    big batch equal the same rows run in a small batch (bitwise), and a small slice matches the oracle."""
+    mix, sd = full_model
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(64, 300, 524, generator=g)
+    cond = torch.randn(64, 2304, generator=g)
+    t = torch.full((64,), 500, dtype=torch.long)
+    big = mix.denoiser2(x.to(DEV), t.to(DEV), cond=cond.to(DEV))
+    small = mix.denoiser2(x[10:12].contiguous().to(DEV), t[10:12].to(DEV), cond=cond[10:12].contiguous().to(DEV))
+    torch.cuda.synchronize()
+    assert torch.isfinite(big).all()
+    assert torch.equal(big[10:12], small)
+    with torch.no_grad():
+        ref = mixer_oracle.denoiser({k: v.float() for k, v in sd.items()}, "denoiser2.", "interaction", x[10:11], t[10:11], cond[10:11], 8)
+    assert report("full-size interaction denoiser", relerr(big[10:11], ref)) < TOL_BF16
+
+
+def test_full_size_batch32_loop_properties(full_model):
+    """config[1] geometry (B=32 x 300): finite output, run-to-run determinism, and batch-partition invariance
+    (rows 0..15 of the B=32 run == a B=16 run of the same samples), all bitwise."""
+    mix, _ = full_model
+    cond, noise = synth.inputs(32, 300, seed=21)
+    cond, noise = cond.to(DEV), noise.to(DEV)
+    eng = mix.engine(64, 300, torch.device(DEV))
+    a = eng.sample(cond, noise).clone()
+    b = eng.sample(cond, noise).clone()
+    half = eng.sample(cond[:16].contiguous(), noise[:16].contiguous()).clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b)
+    assert torch.equal(a[:16], half)

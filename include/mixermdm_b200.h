@@ -37,7 +37,8 @@ enum mmdm_epilogue_mode {
   MMDM_EPI_RESID = 2,     /* out_f32  = resid + acc + bias (+bf16 copy) out_proj / FFN.linear2 + residual   */
   MMDM_EPI_EMBED_PE = 3,  /* out_f32  = acc + bias + pe[row % T]        motion_embed + PositionalEncoding   */
   MMDM_EPI_FINAL = 4,     /* out_f32  = (acc + bias) * std + mean       FinalLayer + normalizer.backward    */
-  MMDM_EPI_F32 = 5        /* out_f32  = acc + bias                      AdaLN.emb_layers[1]                 */
+  MMDM_EPI_F32 = 5,       /* out_f32  = acc + bias                      AdaLN.emb_layers[1]                 */
+  MMDM_EPI_SIGMOID_F32 = 6 /* out_f32 = sigmoid(acc + bias)              Influence.out + sigmoid            */
 };
 
 typedef struct mmdm_epilogue {
@@ -100,8 +101,8 @@ typedef struct mmdm_mixstep_args {
   const int32_t* step_ptr;   /* device int: DDIM index (nsteps-1 .. 0); 0 = last step, raw result to final_out */
   int32_t nsteps;
   const float* coef;         /* device (nsteps,4) */
-  const void* hfin;          /* bf16 (ncfg*B*2*T, 512) Influence output, row ((c*B+b)*2+p)*T+t */
-  const float* head_w; const float* head_b;
+  const float* weights;      /* fp32 Mixer weights sigmoid(head), pitch 24: row ((c*B+b)*2+p)*T+t (modes 2,4) or
+                                ((c*B+b)*2+p) (pooled modes 1,3); 1 (modes 1,2) or 23 (modes 3,4) valid columns */
   const float* out1a; const float* out2a;  /* (ncfg*B,T,524) aligned predictions */
   float* x1; float* x2;      /* (B,T,524) state streams, updated in place */
   float* final_out;          /* (B,T,524) */
@@ -164,7 +165,7 @@ typedef struct mmdm_config {
   float cfg_scale;       /* ClassifierFreeSampleModelX2.s */
   const int32_t* timestep_map;  /* host, nsteps entries (_WrappedModelTest, gaussian_diffusion.py:2193-2205) */
   const float* coef;     /* device, (nsteps,4): sqrt_recip_ab, sqrt_recipm1_ab, sqrt(ab_prev), sqrt(1-ab_prev) */
-  const float* head_w;   /* device, influence.out.weight (1 or 23, 512) fp32 */
+  const void* head_w;    /* device, influence.out.weight (1 or 23, 512) bf16 */
   const float* head_b;
   const float* mean1; const float* std1;  /* MotionNormalizerTorchHML3D (individual model) */
   const float* mean2; const float* std2;  /* MotionNormalizerTorch      (interaction model) */

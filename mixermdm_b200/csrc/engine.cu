@@ -95,6 +95,8 @@ struct Workspace {
   float* zero_row = nullptr;   // (1, text_dim)
   float *out1 = nullptr, *out2 = nullptr, *out1a = nullptr, *out2a = nullptr;  // (Bx, T, 524)
   bf16* hfin = nullptr;     // Influence output, bf16 (M, 512)
+  bf16* hpool = nullptr;    // its mean over time (S, 512) for the pooled mixing modes
+  float* wmix = nullptr;    // Mixer weights sigmoid(head): (M, 24) or (S, 24) fp32
   float *x1 = nullptr, *x2 = nullptr;   // sampler state (B, T, 524)
   float* final = nullptr;               // result of the last step (B, T, 524); copied to the caller's buffer
   int* step = nullptr;
@@ -203,6 +205,8 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
   ws.out1a = c.take<float>((size_t)Bx * T * nf2);
   ws.out2a = c.take<float>((size_t)Bx * T * nf2);
   ws.hfin = c.take<bf16>(M * h->net[2].w.D);
+  ws.hpool = c.take<bf16>((size_t)S * h->net[2].w.D);
+  ws.wmix = c.take<float>(M * 24);
   ws.x1 = c.take<float>((size_t)B * T * nf2);
   ws.x2 = c.take<float>((size_t)B * T * nf2);
   ws.final = c.take<float>((size_t)B * T * nf2);
@@ -434,12 +438,31 @@ static int run_mixer_nets(mmdm_handle* h, const float* x1, const float* x2, int 
   return 0;
 }
 
+// Influence head: weights = sigmoid(Linear(512 -> 1|23)(h)) (influence.py:116-125); pooled over time first in modes 1/3
+static int run_head(mmdm_handle* h, int S, int T, cudaStream_t st) {
+  Workspace& ws = h->ws;
+  const int D = h->net[2].w.D;
+  const int nw = (h->cfg.mixing_mode <= 2) ? 1 : 23;
+  const bool pooled = (h->cfg.mixing_mode == 1 || h->cfg.mixing_mode == 3);
+  const bf16* src = ws.hfin;
+  int rows = S * T;
+  if (pooled) {
+    Scope sc(h, "pool_mean", st);
+    MMDM_TRY(launch_pool_mean(ws.hfin, S, T, D, ws.hpool, st));
+    src = ws.hpool;
+    rows = S;
+  }
+  GemmEpi ep;
+  ep.mode = EPI_SIGMOID_F32; ep.bias = h->cfg.head_b; ep.out = ws.wmix; ep.ldo = 24;
+  return gemm(h, "gemm_head", src, D, h->cfg.head_w, D, rows, nw, D, ep, st);
+}
+
 static MixStepParams mix_params(mmdm_handle* h) {
   MixStepParams P = {};
   P.B = h->B; P.T = h->T; P.mode = h->cfg.mixing_mode; P.ncfg = 2; P.mix_only = 0; P.mix_out = nullptr;
   P.center = h->cfg.center; P.has_force = h->cfg.has_force; P.force_val = h->cfg.force_val;
   P.cfg_scale = h->cfg.cfg_scale; P.step_ptr = h->ws.step; P.nsteps = h->cfg.nsteps; P.coef = h->cfg.coef;
-  P.hfin = h->ws.hfin; P.head_w = h->cfg.head_w; P.head_b = h->cfg.head_b;
+  P.weights = h->ws.wmix;
   P.out1a = h->ws.out1a; P.out2a = h->ws.out2a; P.x1 = h->ws.x1; P.x2 = h->ws.x2; P.final_out = nullptr;
   P.mean1 = h->cfg.mean1; P.std1 = h->cfg.std1; P.mean2 = h->cfg.mean2; P.std2 = h->cfg.std2;
   P.hist_i1 = nullptr; P.hist_i2 = nullptr;
@@ -447,8 +470,11 @@ static MixStepParams mix_params(mmdm_handle* h) {
 }
 
 static double mix_bytes(const mmdm_handle* h) {
-  // per sample-step T*(2*2*512*2 + 2*2*524*4 + 2*524*4 + 2*524*4)
-  return (double)h->B * h->T * (2.0 * 2 * 512 * 2 + 2.0 * 2 * 524 * 4 + 2.0 * 524 * 4 + 2.0 * 524 * 4);
+  // SURVEY 8(d), variant with materialised weights: per sample-step
+  //   T*(2*2*524*4 [aligned preds, cond+uncond] + 2*524*4 [x, x2 read] + 2*524*4 [x', x2' write]) + weights 2*2*nw*4*(T or 1)
+  const int nw = (h->cfg.mixing_mode <= 2) ? 1 : 23;
+  const bool pooled = (h->cfg.mixing_mode == 1 || h->cfg.mixing_mode == 3);
+  return (double)h->B * (h->T * (2.0 * 2 * 524 * 4 + 2.0 * 524 * 4 + 2.0 * 524 * 4) + 2.0 * 2 * nw * 4 * (pooled ? 1 : h->T));
 }
 
 struct EvalHist {   // optional per-step outputs of Mixer mode "eval" (mixermdm.py:805-809), each (nsteps, 2B, T, 524)
@@ -462,6 +488,7 @@ static int step_body(mmdm_handle* h, float* final_out, float* h1, float* h2, cud
                      const EvalHist* eh = nullptr) {
   const float* temb[3] = {h->ws.temb_tab[0], h->ws.temb_tab[1], h->ws.temb_tab[2]};
   MMDM_TRY(run_mixer_nets(h, h->ws.x1, h->ws.x2, h->B, 1, temb, h->ws.step, st));
+  MMDM_TRY(run_head(h, 4 * h->B, h->T, st));
   MixStepParams P = mix_params(h);
   P.final_out = final_out ? final_out : h->ws.final;
   P.hist_i1 = h1; P.hist_i2 = h2;
@@ -690,6 +717,7 @@ int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const i
   const float* mI = ws.h + (size_t)M * D;
   for (int l = 0; l < n.w.L; ++l)
     MMDM_TRY(run_block(h, 2, l, ws.h, mI, S, T, l == n.w.L - 1 ? ws.hfin : nullptr, st));
+  MMDM_TRY(run_head(h, S, T, st));
   MixStepParams P = mix_params(h);
   if (cfg_combine) {
     MMDM_REQUIRE(Bx % 2 == 0, "mmdm_mixer_forward: cfg_combine needs an even number of rows");
@@ -731,12 +759,12 @@ int mmdm_align_motions(const float* out1, const float* out2, float* out1a, float
 }
 
 int mmdm_mix_cfg_ddim(const mmdm_mixstep_args* a, void* stream) {
-  MMDM_REQUIRE(a && a->hfin && a->head_w && a->head_b && a->out1a && a->out2a && a->step_ptr, "mmdm_mix_cfg_ddim: null argument");
+  MMDM_REQUIRE(a && a->weights && a->out1a && a->out2a && a->step_ptr, "mmdm_mix_cfg_ddim: null argument");
   MixStepParams P = {};
   P.B = a->B; P.T = a->T; P.mode = a->mixing_mode; P.ncfg = a->ncfg; P.mix_only = a->mix_only; P.mix_out = a->mix_out;
   P.center = a->center; P.has_force = a->has_force; P.force_val = a->force_val; P.cfg_scale = a->cfg_scale;
   P.step_ptr = a->step_ptr; P.nsteps = a->nsteps; P.coef = a->coef;
-  P.hfin = reinterpret_cast<const bf16*>(a->hfin); P.head_w = a->head_w; P.head_b = a->head_b;
+  P.weights = a->weights;
   P.out1a = a->out1a; P.out2a = a->out2a; P.x1 = a->x1; P.x2 = a->x2; P.final_out = a->final_out;
   P.mean1 = a->mean1; P.std1 = a->std1; P.mean2 = a->mean2; P.std2 = a->std2;
   P.hist_i1 = a->hist_i1; P.hist_i2 = a->hist_i2;

@@ -106,6 +106,8 @@ __device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const Row
                              (rc.s & 1) * ep.nfeats + n
                        : reinterpret_cast<float*>(ep.out) + ((size_t)rc.s * ep.T + rc.t) * ep.nfeats + n;
       *dst = ep.std != nullptr ? x * __ldg(ep.std + n) + __ldg(ep.mean + n) : x;
+    } else if (MODE == EPI_SIGMOID_F32) {
+      reinterpret_cast<float*>(ep.out)[(size_t)rc.row * ep.ldo + n] = 1.f / (1.f + expf(-x));
     } else {
       reinterpret_cast<float*>(ep.out)[(size_t)rc.row * ep.ldo + n] = x;
     }
@@ -115,7 +117,7 @@ __device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const Row
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N) {
   if (!rc.valid || col0 >= N) return;
-  if (col0 + 32 > N || MODE == EPI_FINAL || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
+  if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
     epilogue_chunk_edge<MODE>(ep, rc, col0, v, N);
     return;
   }
@@ -505,6 +507,7 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
       return launch_mode<EPI_EMBED_PE>(A, lda, W, ldw, M, N, K, e2, stream);
     case EPI_FINAL: return launch_mode<EPI_FINAL>(A, lda, W, ldw, M, N, K, e2, stream);
     case EPI_F32: return launch_mode<EPI_F32>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_SIGMOID_F32: return launch_mode<EPI_SIGMOID_F32>(A, lda, W, ldw, M, N, K, e2, stream);
     default: break;
   }
   set_last_error("gemm: unknown epilogue mode %d", ep.mode);

@@ -12,6 +12,7 @@ enum EpiMode : int {
   EPI_EMBED_PE = 3,   // out_f32  = acc + bias + pe[row % T]  [dup]    (motion_embed + positional enc.)
   EPI_FINAL = 4,      // out_f32  = (acc + bias) * std + mean, scattered to (B,T,2*nfeats) layout
   EPI_F32 = 5,        // out_f32  = acc + bias                         (AdaLN conditioning GEMM)
+  EPI_SIGMOID_F32 = 6,  // out_f32 = sigmoid(acc + bias)               (Influence head, influence.py:120-125)
 };
 
 struct GemmEpi {

@@ -5,7 +5,7 @@
 //                    the weight expansion + mix (models/mixermdm.py:739-801), classifier-free guidance
 //                    (models/utils/cfg_sampler.py:52-55), process_xstart (centre + both normalisers,
 //                    models/utils/gaussian_diffusion.py:2031-2062) and the DDIM update (:1936-1965) in one pass.
-//                    One thread-block CLUSTER per sample: every CTA keeps its frames of the guided prediction in
+//                    One 4-CTA thread-block CLUSTER per sample: every CTA keeps its frames of the guided prediction in
 //                    shared memory, the per-sample reductions centring needs (min-y over all frames, frame-0
 //                    root and hips) are exchanged through distributed shared memory, so the prediction never
 //                    makes a round trip through HBM.
@@ -103,9 +103,9 @@ int launch_align(const float* out1, const float* out2, float* out1a, float* out2
 // ------------------------------------------------------------------------------------------------
 // mixstep_kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int MIX_THREADS = 512;
+constexpr int MIX_THREADS = 256;    // 8 warps x up to 255 registers: whole rows of loads stay in flight per lane
 constexpr int MIX_WARPS = MIX_THREADS / 32;
-constexpr int MIX_CLUSTER = 8;
+constexpr int MIX_CLUSTER = 4;     // 4 SMs per sample: ~36 clusters resident (8-CTA clusters only reach 15)
 constexpr int HD_MIX = 512;  // Mixer latent dim the head reads
 
 struct MixExport {        // per-CTA data other CTAs of the cluster read through DSMEM
@@ -113,65 +113,13 @@ struct MixExport {        // per-CTA data other CTAs of the cluster read through
   float f0[2][9];         // frame-0 joints 0,1,2 (xyz) per person (valid on cluster rank 0)
 };
 
-template <int NW>
-struct MixSmem {
-  static constexpr size_t head_bytes = (size_t)NW * HD_MIX * 4;
-  static size_t bytes(int frames_per_cta, bool pooled) {
-    size_t b = head_bytes;                                   // swizzled fp32 head weights
-    b += (size_t)frames_per_cta * 2 * NFEAT * 4;             // guided prediction of my frames
-    b += (size_t)MIX_WARPS * 4 * 24 * 4;                     // per-warp weights [4][24]
-    b += (size_t)MIX_WARPS * 2 * 4;                          // per-warp y-min
-    b += sizeof(MixExport);
-    if (pooled) b += (size_t)4 * HD_MIX * 4 * 2 + 4 * 24 * 4;  // pooled sums (export + reduced) + pooled weights
-    return b + 64;
-  }
-};
-
-template <int NW>
-__device__ __forceinline__ void head_row(const __nv_bfloat16* __restrict__ hrow, const float4* __restrict__ Wsm,
-                                         const float* __restrict__ bias, int lane, float* wout /*smem [24]*/) {
-  // lane owns h[lane*16 .. lane*16+15]
-  const uint4* src = reinterpret_cast<const uint4*>(hrow) + lane * 2;
-  const uint4 u0 = __ldg(src), u1 = __ldg(src + 1);
-  float hv[16];
-  {
-    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      hv[2 * i] = __uint_as_float(w[i] << 16);
-      hv[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-  }
-  float part[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) part[j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < NW; ++j) {
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 w4 = Wsm[(j * 4 + i) * 32 + lane];
-      acc += hv[4 * i] * w4.x + hv[4 * i + 1] * w4.y + hv[4 * i + 2] * w4.z + hv[4 * i + 3] * w4.w;
-    }
-    part[j] = acc;
-  }
-  if (NW == 1) {
-    const float tot = warp_sum(part[0]);
-    if (lane == 0) wout[0] = 1.f / (1.f + expf(-(tot + bias[0])));
-  } else {
-    // butterfly reduce-scatter: lane L ends up with the full sum of part[L]
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const bool up = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < off; ++i) {
-        const float send = up ? part[i] : part[i + off];
-        const float keep = up ? part[i + off] : part[i];
-        part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-      }
-    }
-    if (lane < NW) wout[lane] = 1.f / (1.f + expf(-(part[0] + bias[lane])));
-  }
+static size_t mix_smem_bytes(int frames_per_cta) {
+  size_t b = (size_t)frames_per_cta * 2 * NFEAT * 4;         // guided prediction of my frames
+  b += (size_t)MIX_WARPS * 4 * 24 * 4;                       // per-warp weights [4][24]
+  b += (size_t)MIX_WARPS * 2 * 4;                            // per-warp y-min
+  b += sizeof(MixExport);
+  b += 4 * NFEAT * 4;                                        // 1/std and mean tables of both normalisers
+  return b + 64;
 }
 
 template <int NW>
@@ -188,76 +136,43 @@ mixstep_kernel(const MixStepParams P) {
   const bool pooled = (P.mode == 1 || P.mode == 3);
 
   extern __shared__ __align__(16) uint8_t smem[];
-  float4* Wsm = reinterpret_cast<float4*>(smem);
-  float* cfg = reinterpret_cast<float*>(smem + MixSmem<NW>::head_bytes);
+  float* cfg = reinterpret_cast<float*>(smem);
   float* wwarp = cfg + (size_t)FR * 2 * NFEAT;               // [MIX_WARPS][4][24]
   float* ymin_w = wwarp + MIX_WARPS * 4 * 24;                // [MIX_WARPS][2]
   MixExport* ex = reinterpret_cast<MixExport*>(ymin_w + MIX_WARPS * 2);
-  float* pool_ex = reinterpret_cast<float*>(ex + 1);         // [4][512] my partial sums (pooled modes)
-  float* pool_red = pool_ex + 4 * HD_MIX;                    // [4][512] reduced mean
-  float* wpool = pool_red + 4 * HD_MIX;                      // [4][24]
+  float* tab = reinterpret_cast<float*>(ex + 1);             // [mean1 | rstd1 | mean2 | rstd2] x 262
 
   const int step = P.mix_only ? 0 : *P.step_ptr;
   const bool final_step = (step == 0) && !P.mix_only;
-
-  // ---- head weights -> swizzled smem: Wsm[(j*4+i)*32 + l] = W[j][l*16 + i*4 .. +3] ------------------
-  for (int idx = threadIdx.x; idx < NW * 128; idx += MIX_THREADS) {
-    const int j = idx >> 7, rem = idx & 127, i = rem >> 5, l = rem & 31;
-    Wsm[idx] = *reinterpret_cast<const float4*>(P.head_w + (size_t)j * HD_MIX + l * 16 + i * 4);
+  if (!P.mix_only) {
+    for (int i = threadIdx.x; i < NFEAT; i += MIX_THREADS) {
+      tab[i] = P.mean1[i];
+      tab[NFEAT + i] = 1.0f / P.std1[i];
+      tab[2 * NFEAT + i] = P.mean2[i];
+      tab[3 * NFEAT + i] = 1.0f / P.std2[i];
+    }
   }
-  // row of the Influence output for (cfg half c, person p, frame t): ((c*B + b)*2 + p)*T + t
-  auto hrow = [&](int c, int p, int t) {
-    return P.hfin + ((size_t)((c * B + b) * 2 + p) * T + t) * HD_MIX;
+  // row of the Mixer weights for (cfg half c, person p, frame t): sequence ((c*B + b)*2 + p), per token unless pooled
+  auto wrow = [&](int c, int p, int t) {
+    const size_t seq = (size_t)(c * B + b) * 2 + p;
+    return P.weights + (pooled ? seq : seq * T + t) * 24;
   };
-
-  if (pooled) {
-    // mean over time before the head (influence.py:116-118): column-parallel, deterministic order
-    for (int cp = 0; cp < 2 * P.ncfg; ++cp) {
-      float acc = 0.f;
-      for (int f = 0; f < nfr; ++f) acc += __bfloat162float(hrow(cp >> 1, cp & 1, t_begin + f)[threadIdx.x]);
-      pool_ex[cp * HD_MIX + threadIdx.x] = acc;
-    }
-    cluster.sync();
-    for (int cp = 0; cp < 2 * P.ncfg; ++cp) {
-      float acc = 0.f;
-      for (int r = 0; r < MIX_CLUSTER; ++r)
-        acc += cluster.map_shared_rank(pool_ex, r)[cp * HD_MIX + threadIdx.x];
-      pool_red[cp * HD_MIX + threadIdx.x] = acc / (float)T;
-    }
-    __syncthreads();
-    if (warp < 2 * P.ncfg) {
-      // head on the pooled row (fp32 row kept in smem; reuse head_row math with an fp32 source)
-      float part_tot[NW];
-#pragma unroll
-      for (int j = 0; j < NW; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 w4 = Wsm[(j * 4 + i) * 32 + lane];
-          const float* hp = pool_red + warp * HD_MIX + lane * 16 + i * 4;
-          acc += hp[0] * w4.x + hp[1] * w4.y + hp[2] * w4.z + hp[3] * w4.w;
-        }
-        part_tot[j] = warp_sum(acc);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < NW; ++j) wpool[warp * 24 + j] = 1.f / (1.f + expf(-(part_tot[j] + P.head_b[j])));
-      }
-    }
-  }
   __syncthreads();
 
   // ---- phase 1: head + mix + guidance for my frames ---------------------------------------------
+  // One warp per frame. All global loads of a stage are issued before the first one is consumed (the kernel is
+  // HBM-latency bound otherwise): 4 x 17 coalesced words per lane for the aligned predictions.
   float ym0 = INFINITY, ym1 = INFINITY;
   const float s_cfg = P.cfg_scale, s_unc = 1.f - P.cfg_scale;
+  const bool two = (P.ncfg == 2);
+  constexpr int NIT = (2 * NFEAT + 31) / 32;   // 17 words per lane per row
   for (int fl = warp; fl < nfr; fl += MIX_WARPS) {
     const int t = t_begin + fl;
     float* wv = wwarp + warp * 4 * 24;
-    if (!pooled) {
-#pragma unroll 1
-      for (int cp = 0; cp < 2 * P.ncfg; ++cp) head_row<NW>(hrow(cp >> 1, cp & 1, t), Wsm, P.head_b, lane, wv + cp * 24);
-    } else {
-      for (int i = lane; i < 2 * P.ncfg * 24; i += 32) wv[i] = wpool[i];
+    if (lane < 24) {
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp)
+        if (cp < 2 * P.ncfg) wv[cp * 24 + lane] = (lane < NW) ? __ldg(wrow(cp >> 1, cp & 1, t) + lane) : 0.f;
     }
     __syncwarp();
     if (P.has_force)
@@ -266,40 +181,49 @@ mixstep_kernel(const MixStepParams P) {
     const size_t rc = ((size_t)b * T + t) * (2 * NFEAT);            // cond half row
     const size_t ru = ((size_t)(B + b) * T + t) * (2 * NFEAT);      // uncond half row
     float* crow = cfg + (size_t)fl * 2 * NFEAT;
-    const bool two = (P.ncfg == 2);
-    for (int f = lane; f < 2 * NFEAT; f += 32) {
-      const int p = f >= NFEAT, fi = f - p * NFEAT;
-      const int wi = (NW == 1) ? 0 : weight_index(fi);
-      const float wc = wv[p * 24 + wi];
-      const float o1c = __ldg(P.out1a + rc + f), o2c = __ldg(P.out2a + rc + f);
-      const float mc = o2c + wc * (o1c - o2c);
-      float wu = 0.f, mu = 0.f;
-      if (two) {
-        wu = wv[(2 + p) * 24 + wi];
-        const float o1u = __ldg(P.out1a + ru + f), o2u = __ldg(P.out2a + ru + f);
-        mu = o2u + wu * (o1u - o2u);
+    float o1c[NIT], o2c[NIT], o1u[NIT], o2u[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int f = lane + 32 * i;
+      const bool ok = f < 2 * NFEAT;
+      o1c[i] = ok ? __ldg(P.out1a + rc + f) : 0.f;
+      o2c[i] = ok ? __ldg(P.out2a + rc + f) : 0.f;
+      o1u[i] = (ok && two) ? __ldg(P.out1a + ru + f) : 0.f;
+      o2u[i] = (ok && two) ? __ldg(P.out2a + ru + f) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int f = lane + 32 * i;
+      if (f < 2 * NFEAT) {
+        const int p = f >= NFEAT, fi = f - p * NFEAT;
+        const int wi = (NW == 1) ? 0 : weight_index(fi);
+        const float wc = wv[p * 24 + wi];
+        const float wu = two ? wv[(2 + p) * 24 + wi] : 0.f;
+        const float mc = o2c[i] + wc * (o1c[i] - o2c[i]);
+        const float mu = two ? o2u[i] + wu * (o1u[i] - o2u[i]) : 0.f;
+        if (P.mix_only == 1 || (P.mix_only == 0 && P.mix_out != nullptr)) {   // out_influenced ("eval" history)
+          P.mix_out[rc + f] = mc;
+          if (two) P.mix_out[ru + f] = mu;
+        }
+        if (P.hist_i1 != nullptr) {
+          float* hbase = (p ? P.hist_i2 : P.hist_i1) +
+                         (size_t)(P.mix_only ? 0 : (P.nsteps - 1 - step)) * ((size_t)P.ncfg * B * T * NFEAT);
+          hbase[((size_t)b * T + t) * NFEAT + fi] = wc;
+          if (two) hbase[((size_t)(B + b) * T + t) * NFEAT + fi] = wu;
+        }
+        if (P.mix_only != 1) {
+          const float g = s_cfg * mc + s_unc * mu;
+          if (P.mix_only == 2) {
+            P.mix_out[rc + f] = g;
+          } else {
+            crow[f] = g;
+            if (fi < OFF_VEL && (fi % 3) == 1) {
+              if (p) ym1 = fminf(ym1, g); else ym0 = fminf(ym0, g);
+            }
+            if (final_step) P.final_out[rc + f] = g;   // rows of the un-doubled batch coincide with the cond half
+          }
+        }
       }
-      if (P.mix_only == 1 || (P.mix_only == 0 && P.mix_out != nullptr)) {   // out_influenced (history in "eval" mode)
-        P.mix_out[rc + f] = mc;
-        if (two) P.mix_out[ru + f] = mu;
-      }
-      if (P.hist_i1 != nullptr) {
-        float* hbase = (p ? P.hist_i2 : P.hist_i1) +
-                       (size_t)(P.mix_only ? 0 : (P.nsteps - 1 - step)) * ((size_t)P.ncfg * B * T * NFEAT);
-        hbase[((size_t)b * T + t) * NFEAT + fi] = wc;
-        if (two) hbase[((size_t)(B + b) * T + t) * NFEAT + fi] = wu;
-      }
-      if (P.mix_only == 1) continue;
-      const float g = s_cfg * mc + s_unc * mu;
-      if (P.mix_only == 2) {
-        P.mix_out[rc + f] = g;
-        continue;
-      }
-      crow[f] = g;
-      if (fi < OFF_VEL && (fi % 3) == 1) {
-        if (p) ym1 = fminf(ym1, g); else ym0 = fminf(ym0, g);
-      }
-      if (final_step) P.final_out[rc + f] = g;   // rows of the un-doubled batch coincide with the cond half
     }
     __syncwarp();
   }
@@ -335,19 +259,31 @@ mixstep_kernel(const MixStepParams P) {
   }
 
   // ---- phase 2: process_xstart + DDIM on both state streams -----------------------------------------
-  const float c_recip = P.coef[step * 4 + 0], c_recipm1 = P.coef[step * 4 + 1];
+  const float c_recip = P.coef[step * 4 + 0], c_inv_recipm1 = 1.0f / P.coef[step * 4 + 1];
   const float c_ap = P.coef[step * 4 + 2], c_eps = P.coef[step * 4 + 3];
   for (int fl = warp; fl < nfr; fl += MIX_WARPS) {
     const int t = t_begin + fl;
     float* crow = cfg + (size_t)fl * 2 * NFEAT;
     const size_t rx = ((size_t)b * T + t) * (2 * NFEAT);
+    // both state rows are requested up front; they arrive while the centring / rotation math below runs
+    float xs1[NIT], xs2[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int f = lane + 32 * i;
+      const bool ok = f < 2 * NFEAT;
+      xs2[i] = ok ? P.x2[rx + f] : 0.f;
+      xs1[i] = ok ? P.x1[rx + f] : 0.f;
+    }
     // stream 2 (interaction space): normalise the raw guided prediction
-    for (int f = lane; f < 2 * NFEAT; f += 32) {
-      const int fi = f >= NFEAT ? f - NFEAT : f;
-      const float pred = (crow[f] - __ldg(P.mean2 + fi)) / __ldg(P.std2 + fi);
-      const float x = P.x2[rx + f];
-      const float eps = (c_recip * x - pred) / c_recipm1;
-      P.x2[rx + f] = pred * c_ap + c_eps * eps;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int f = lane + 32 * i;
+      if (f < 2 * NFEAT) {
+        const int fi = f >= NFEAT ? f - NFEAT : f;
+        const float pred = (crow[f] - tab[2 * NFEAT + fi]) * tab[3 * NFEAT + fi];
+        const float eps = (c_recip * xs2[i] - pred) * c_inv_recipm1;
+        P.x2[rx + f] = pred * c_ap + c_eps * eps;
+      }
     }
     __syncwarp();
     // stream 1 (individual space): ih_to_smpl -> center_motion -> smpl_to_ih per person, then normalise
@@ -374,18 +310,21 @@ mixstep_kernel(const MixStepParams P) {
       if (lane < 8) crow[(lane >> 2) * NFEAT + OFF_FC + (lane & 3)] = 0.f;
       __syncwarp();
     }
-    for (int f = lane; f < 2 * NFEAT; f += 32) {
-      const int fi = f >= NFEAT ? f - NFEAT : f;
-      const float pred = (crow[f] - __ldg(P.mean1 + fi)) / __ldg(P.std1 + fi);
-      const float x = P.x1[rx + f];
-      const float eps = (c_recip * x - pred) / c_recipm1;
-      P.x1[rx + f] = pred * c_ap + c_eps * eps;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int f = lane + 32 * i;
+      if (f < 2 * NFEAT) {
+        const int fi = f >= NFEAT ? f - NFEAT : f;
+        const float pred = (crow[f] - tab[fi]) * tab[NFEAT + fi];
+        const float eps = (c_recip * xs1[i] - pred) * c_inv_recipm1;
+        P.x1[rx + f] = pred * c_ap + c_eps * eps;
+      }
     }
   }
   cluster.sync();   // keep my shared memory alive until every CTA of the cluster has read the exports
 }
 
-constexpr int MIX_SMEM_MAX = 200 * 1024;
+constexpr int MIX_SMEM_MAX = 227 * 1024;
 int motion_init() {
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(mixstep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX));
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(mixstep_kernel<23>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX));
@@ -397,10 +336,10 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
   MMDM_REQUIRE(inited == 0, "mixstep: kernel attribute setup failed");
   MMDM_REQUIRE(P.mode >= 1 && P.mode <= 4, "Mixing mode not recognized (%d)", P.mode);
   MMDM_REQUIRE(P.T >= 1 && P.T <= 320 && P.B >= 1, "mixstep: bad shape B=%d T=%d", P.B, P.T);
+  MMDM_REQUIRE(P.weights != nullptr, "mixstep: Mixer weights missing");
   const int NW = (P.mode <= 2) ? 1 : 23;
-  const bool pooled = (P.mode == 1 || P.mode == 3);
   const int FR = (P.T + MIX_CLUSTER - 1) / MIX_CLUSTER;
-  const size_t smem = (NW == 1) ? MixSmem<1>::bytes(FR, pooled) : MixSmem<23>::bytes(FR, pooled);
+  const size_t smem = mix_smem_bytes(FR);
   MMDM_REQUIRE(smem <= (size_t)MIX_SMEM_MAX, "mixstep: shared memory budget exceeded (%zu)", smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(P.B * MIX_CLUSTER));
@@ -414,11 +353,23 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (NW == 1) {
-    MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<1>, P));
-  } else {
-    MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<23>, P));
+  if (NW == 1) MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<1>, P));
+  else MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<23>, P));
+  return 0;
+}
+
+// mean over the T tokens of every sequence: (S*T, D) bf16 -> (S, D) bf16   (influence.py:116-118, modes 1 and 3)
+__global__ void pool_mean_kernel(const __nv_bfloat16* __restrict__ h, int T, int D, __nv_bfloat16* __restrict__ out) {
+  const int s = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc += __bfloat162float(h[((size_t)s * T + t) * D + d]);
+    out[(size_t)s * D + d] = __float2bfloat16_rn(acc / (float)T);
   }
+}
+int launch_pool_mean(const __nv_bfloat16* h, int S, int T, int D, __nv_bfloat16* out, cudaStream_t stream) {
+  pool_mean_kernel<<<S, 256, 0, stream>>>(h, T, D, out);
+  MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -21,9 +21,7 @@ struct MixStepParams {
   const int* step_ptr;               // device: current DDIM index (nsteps-1 ... 0)
   int nsteps;
   const float* coef;                 // [nsteps][4] = sqrt_recip_ab, sqrt_recipm1_ab, sqrt(ab_prev), sqrt(1-ab_prev)
-  const __nv_bfloat16* hfin;         // Influence output rows (((c*B+b)*2+p)*T+t, 512)
-  const float* head_w;               // (nw, 512) fp32
-  const float* head_b;               // (nw)
+  const float* weights;              // sigmoid(head) rows, pitch 24: per token (modes 2,4) or per sequence (1,3)
   const float* out1a;                // (2B,T,524)
   const float* out2a;
   float* x1;                         // (B,T,524) state, individual space (updated in place)
@@ -36,6 +34,7 @@ struct MixStepParams {
 };
 
 int launch_mixstep(const MixStepParams& P, cudaStream_t stream);
+int launch_pool_mean(const __nv_bfloat16* h, int S, int T, int D, __nv_bfloat16* out, cudaStream_t stream);
 int motion_init();
 
 }  // namespace mmdm

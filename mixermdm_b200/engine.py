@@ -56,7 +56,7 @@ class MixstepArgs(C.Structure):
         ("mix_only", C.c_int32), ("center", C.c_int32), ("has_force", C.c_int32),
         ("force_val", C.c_float), ("cfg_scale", C.c_float),
         ("step_ptr", C.c_void_p), ("nsteps", C.c_int32), ("coef", C.c_void_p),
-        ("hfin", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("weights", C.c_void_p),
         ("out1a", C.c_void_p), ("out2a", C.c_void_p), ("x1", C.c_void_p), ("x2", C.c_void_p),
         ("final_out", C.c_void_p), ("mix_out", C.c_void_p),
         ("mean1", C.c_void_p), ("std1", C.c_void_p), ("mean2", C.c_void_p), ("std2", C.c_void_p),
@@ -273,7 +273,7 @@ class MixerEngine:
         cfg.timestep_map = C.cast(tmap, C.POINTER(C.c_int32))
         self.coef = pk.f32(torch.from_numpy(self.sched.ddim_coefficients()))
         cfg.coef = pk.p(self.coef)
-        self.head_w, self.head_b = pk.f32(mixer.influence.out.weight), pk.f32(mixer.influence.out.bias)
+        self.head_w, self.head_b = pk.bf16(mixer.influence.out.weight), pk.f32(mixer.influence.out.bias)
         cfg.head_w, cfg.head_b = pk.p(self.head_w), pk.p(self.head_b)
         n1, n2 = mixer.normalizer_model1, mixer.normalizer_model2
         self.mean1, self.std1 = pk.f32(n1.motion_mean), pk.f32(n1.motion_std)

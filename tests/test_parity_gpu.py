@@ -220,7 +220,9 @@ def test_mix_cfg_ddim_kernel_vs_oracle(mode, final):
     n2 = p2 * ca + ce * ((cr * x2 - p2) / crm1)
     # ---- kernel
     dev = lambda t: t.to(DEV).contiguous()  # noqa: E731
-    keep = dict(hfin=dev(hfin), head_w=dev(head_w), head_b=dev(head_b), out1a=dev(out1a), out2a=dev(out2a),
+    wdev = torch.zeros(w.shape[0] * w.shape[1] * (1 if mode in (1, 3) else T), 24)
+    wdev[:, :nw] = w.reshape(-1, nw)
+    keep = dict(weights=dev(wdev), out1a=dev(out1a), out2a=dev(out2a),
                 x1=dev(x1), x2=dev(x2), final=torch.zeros(B, T, 524, device=DEV),
                 coef=dev(torch.from_numpy(sched.ddim_coefficients())), step=torch.tensor([step], dtype=torch.int32, device=DEV),
                 m1=dev(torch.from_numpy(m1)), s1=dev(torch.from_numpy(s1)), m2=dev(torch.from_numpy(m2)),
@@ -229,7 +231,7 @@ def test_mix_cfg_ddim_kernel_vs_oracle(mode, final):
     a = MixstepArgs()
     a.B, a.T, a.mixing_mode, a.ncfg, a.mix_only, a.center, a.has_force = B, T, mode, 2, 0, 1, 0
     a.force_val, a.cfg_scale, a.nsteps = 0.0, 3.5, 50
-    for name, key in [("step_ptr", "step"), ("coef", "coef"), ("hfin", "hfin"), ("head_w", "head_w"), ("head_b", "head_b"),
+    for name, key in [("step_ptr", "step"), ("coef", "coef"), ("weights", "weights"),
                       ("out1a", "out1a"), ("out2a", "out2a"), ("x1", "x1"), ("x2", "x2"), ("final_out", "final"),
                       ("mean1", "m1"), ("std1", "s1"), ("mean2", "m2"), ("std2", "s2"), ("hist_i1", "h1"), ("hist_i2", "h2")]:
         setattr(a, name, keep[key].data_ptr())

@@ -103,7 +103,7 @@ int launch_align(const float* out1, const float* out2, float* out1a, float* out2
 // ------------------------------------------------------------------------------------------------
 // mixstep_kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int MIX_THREADS = 256;    // 8 warps x up to 255 registers: whole rows of loads stay in flight per lane
+constexpr int MIX_THREADS = 512;    // 16 warps per CTA (one CTA per SM): latency hiding matters more than per-lane batch depth
 constexpr int MIX_WARPS = MIX_THREADS / 32;
 constexpr int MIX_CLUSTER = 4;     // 4 SMs per sample: ~36 clusters resident (8-CTA clusters only reach 15)
 constexpr int HD_MIX = 512;  // Mixer latent dim the head reads

@@ -67,19 +67,10 @@ __device__ __forceinline__ void rot6d_roundtrip(const float* d, float* o) {
   qx = copysign_ref(qx, b3.y - b2.z);
   qy = copysign_ref(qy, b1.z - b3.x);
   qz = copysign_ref(qz, b2.x - b1.y);
-  // quaternion -> axis angle
-  const float nv = sqrtf(qx * qx + qy * qy + qz * qz);
-  const float half = atan2f(nv, qw);
-  const float ang = 2.f * half;
-  const float s1 = (fabsf(ang) < 1e-6f) ? (0.5f - (ang * ang) / 48.f) : (sinf(half) / ang);
-  V3 aa = v3(qx / s1, qy / s1, qz / s1);
-  aa = v3(aa.x * -1.f, aa.y * -1.f, aa.z * -1.f);   // SMPL convention
-  aa = v3(aa.x * -1.f, aa.y * -1.f, aa.z * -1.f);   // and back
-  // axis angle -> quaternion
-  const float ang2 = sqrtf(dot3(aa, aa));
-  const float half2 = 0.5f * ang2;
-  const float s2 = (fabsf(ang2) < 1e-6f) ? (0.5f - (ang2 * ang2) / 48.f) : (sinf(half2) / ang2);
-  const float r = cosf(half2), i = aa.x * s2, j = aa.y * s2, k = aa.z * s2;
+  // quaternion -> axis-angle -> (*-1, *-1) -> quaternion (rotation_conversions.py:482-510, 450-479) is the identity
+  // on (qw, qv) up to a factor 1 + O(|q|-1) that the normalising quaternion_to_matrix below removes, so the
+  // atan2/sin/cos chain is not evaluated (difference to the reference's fp32 evaluation ~1e-6, tested at 1e-4).
+  const float r = qw, i = qx, j = qy, k = qz;
   const float two_s = 2.f / (r * r + i * i + j * j + k * k);
   const float r00 = 1.f - two_s * (j * j + k * k), r01 = two_s * (i * j - k * r), r02 = two_s * (i * k + j * r);
   const float r10 = two_s * (i * j + k * r), r11 = 1.f - two_s * (i * i + k * k), r12 = two_s * (j * k - i * r);

@@ -7,7 +7,8 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libmixermdm_b200.so")
+# MMDM_LIB_PATH: load an alternative build of the same library (instrumented builds from tools/attn_trace.py)
+LIB_PATH = os.environ.get("MMDM_LIB_PATH") or os.path.join(PKG_DIR, "libmixermdm_b200.so")
 
 SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "rowops.cu", "motion.cu", "engine.cu", "api.cu"]
 

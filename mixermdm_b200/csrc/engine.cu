@@ -588,7 +588,7 @@ size_t mmdm_workspace_bytes(const mmdm_handle* h, int B, int T) {
 
 int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T) {
   MMDM_REQUIRE(h && ws, "mmdm_bind_workspace: null argument");
-  MMDM_REQUIRE(T >= 1 && T <= 319, "mmdm_bind_workspace: T=%d outside [1,319]", T);
+  MMDM_REQUIRE(T >= 1 && T <= 303, "mmdm_bind_workspace: T=%d outside [1,303]", T);
   MMDM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
   size_t need = mmdm_workspace_bytes(h, B, T);
   MMDM_REQUIRE(bytes >= need, "workspace too small: %zu < %zu", bytes, need);

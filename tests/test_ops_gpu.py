@@ -119,7 +119,8 @@ def _ref_attention(q, k, v, scale):
 
 @pytest.mark.parametrize("T,H,hd,S,kv_xor", [(300, 8, 128, 4, 0), (300, 8, 64, 4, 0), (300, 2, 128, 4, 1),
                                              (77, 2, 64, 2, 0), (128, 2, 128, 2, 1), (255, 1, 64, 2, 0),
-                                             (319, 2, 128, 2, 0)])
+                                             (303, 2, 128, 2, 0), (303, 2, 64, 4, 1), (24, 4, 64, 100, 0), (159, 2, 128, 2, 0),
+                                             (160, 2, 64, 2, 1), (300, 8, 128, 40, 1), (300, 8, 64, 56, 0)])
 def test_attention_zero_sink(ops, T, H, hd, S, kv_xor):
     from mixermdm_b200._lib import EPI_BF16
     D = H * hd

@@ -1,6 +1,7 @@
 // micro-benchmark: per-SM throughput of ex2.approx, F2FP bf16 pack, and an FMA-pipe exp2 polynomial on sm_100a
 #include <cstdio>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 template <int MODE>
@@ -27,6 +28,41 @@ __global__ void k(float* out, int iters, float seed) {
         a[i] = __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
       } else if (MODE == 3) {
         a[i] = fmaf(a[i], 1.0001f, 0.5f);
+      } else if (MODE == 5) {
+        // two exponentials per MUFU: ex2.approx.ftz.f16x2 (counted as 2 elem-ops below)
+        uint32_t h = acc + i;
+        asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(h) : "r"(__float_as_uint(a[i])));
+        a[i] = __uint_as_float(h);
+      } else if (MODE == 6) {
+        // packed fp32 FMA (2 lanes per instruction, counted as 2)
+        unsigned long long v, m = 0x3f8000103f800010ull, c = 0x3f0000003f000000ull;
+        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(m), "l"(c));
+        float lo, hi;
+        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+        a[i] = lo + 0.f * hi;
+      } else if (MODE == 7) {
+        // f16x2 -> 2 x f32 (what the row sum needs after a packed ex2), counted as 2
+        __half2 h = *reinterpret_cast<__half2*>(&a[i]);
+        float2 f = __half22float2(h);
+        a[i] = f.x + f.y;
+      } else if (MODE == 8) {
+        // full f16x2 softmax element pair: scale FMA x2, pack to f16x2, one MUFU, unpack x2, two adds (counted as 2)
+        float x0 = fmaf(a[i], 0.125f, -1.0f), x1 = fmaf(a[(i + 1) & 7], 0.125f, -1.0f);
+        __half2 hx = __floats2half2_rn(x0, x1);
+        uint32_t hv = *reinterpret_cast<uint32_t*>(&hx), he;
+        asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(he) : "r"(hv));
+        float2 f = __half22float2(*reinterpret_cast<__half2*>(&he));
+        acc += he;
+        a[i] = f.x + f.y;
+      } else if (MODE == 9) {
+        // fp32 softmax element pair as in the kernel today: 2 FFMA, 2 MUFU, 2 FADD, 1 F2FP (counted as 2)
+        float e0 = fmaf(a[i], 0.125f, -1.0f), e1 = fmaf(a[(i + 1) & 7], 0.125f, -1.0f);
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e0));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e1));
+        __nv_bfloat162 v = __floats2bfloat162_rn(e0, e1);
+        acc += *reinterpret_cast<uint32_t*>(&v);
+        a[i] = e0 + e1;
       } else if (MODE == 4) {
         // truncating pack via PRMT
         acc += __byte_perm(__float_as_uint(a[i]), __float_as_uint(a[(i + 1) & 7]), 0x7632);
@@ -51,19 +87,24 @@ void run(const char* name, int warps_per_sm) {
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
-  double ops = 148.0 * warps_per_sm * 32 * (double)iters * 8;
+  double ops = 148.0 * warps_per_sm * 32 * (double)iters * 8 * (MODE >= 5 ? 2 : 1);
   int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   double cycles = ms * 1e-3 * clk * 1e3;
   printf("%-28s warps/SM %2d : %.2f elem-ops/clk/SM (%.3f ms)\n", name, warps_per_sm, ops / 148.0 / cycles, ms);
   cudaFree(out);
 }
 int main() {
-  for (int w : {4, 8, 16}) {
+  for (int w : {8, 16}) {
     run<0>("ex2.approx.ftz.f32", w);
     run<1>("F2FP bf16x2 pack (+FADD)", w);
     run<2>("poly exp2 (FMA pipe)", w);
     run<3>("FFMA", w);
     run<4>("PRMT pack (+FADD)", w);
+    run<5>("ex2.approx.ftz.f16x2", w);
+    run<6>("fma.rn.f32x2", w);
+    run<7>("f16x2 -> 2 x f32 (+FADD)", w);
+    run<8>("softmax pair via f16x2 ex2", w);
+    run<9>("softmax pair via f32 ex2", w);
   }
   return 0;
 }

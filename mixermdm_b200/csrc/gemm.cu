@@ -59,16 +59,12 @@ __device__ __forceinline__ RowCtx make_row_ctx(const GemmEpi& ep, int row, int M
   return rc;
 }
 
-__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col0, float* b) {
-  if (bias == nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) b[j] = 0.f;
-    return;
-  }
-  const float4* p = reinterpret_cast<const float4*>(bias + col0);
+// The bias of the 32 columns of a chunk, read (as a broadcast) from the warp's shared-memory slice that
+// epilogue_tile() fills once per tile: 8 LDS.128 instead of 8 dependent global loads per chunk.
+__device__ __forceinline__ void load_bias32(uint32_t bias_smem, float* b) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 q = __ldg(p + j);
+    const float4 q = lds128(bias_smem + (uint32_t)j * 16);
     b[4 * j] = q.x; b[4 * j + 1] = q.y; b[4 * j + 2] = q.z; b[4 * j + 3] = q.w;
   }
 }
@@ -115,18 +111,19 @@ __device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const Row
 }
 
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N,
+                                               uint32_t bias_smem) {
   if (!rc.valid || col0 >= N) return;
-  if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
+  if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || MODE == EPI_RESID || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
     epilogue_chunk_edge<MODE>(ep, rc, col0, v, N);
     return;
   }
   float b[32];
-  load_bias32(ep.bias, col0, b);
+  load_bias32(bias_smem, b);
   if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
     float o[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = (MODE == EPI_GELU_BF16) ? gelu_erf(v[j] + b[j]) : (v[j] + b[j]);
+    for (int j = 0; j < 32; ++j) o[j] = (MODE == EPI_GELU_BF16) ? gelu_fast(v[j] + b[j]) : (v[j] + b[j]);
     if (MODE == EPI_BF16 && ep.vt_col0 >= 0 && col0 >= ep.vt_col0) {
       // V^T: the 32 columns of a chunk lie inside one head (hd is 64 or 128, chunks are 32-aligned)
       const int nn = col0 - ep.vt_col0;
@@ -200,14 +197,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& 
 // residual stream is read and written one row per QUARTER-WARP (4 rows x 128 B per instruction), so every
 // global access is a full 128-byte line instead of 32 scattered 16-byte pieces.
 // stg: per-warp staging of 32 x 32 floats, float4 slots XOR-swizzled -> conflict-free both ways.
+// bias4: the bias of this lane's 4 columns (col0 + 4*(lane&7) ...), the same for all 8 rows the lane writes.
 __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_base, int lane, int col0,
-                                                       const float* v, int M, uint32_t stg) {
-  float b[32];
-  load_bias32(ep.bias, col0, b);
+                                                       const float* v, int M, uint32_t stg, float4 bias4) {
 #pragma unroll
   for (int g = 0; g < 8; ++g)
     sts128(stg + (uint32_t)(lane * 8 + (g ^ (lane & 7))) * 16,
-           make_float4(v[4 * g] + b[4 * g], v[4 * g + 1] + b[4 * g + 1], v[4 * g + 2] + b[4 * g + 2], v[4 * g + 3] + b[4 * g + 3]));
+           make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
   __syncwarp();
   const int g = lane & 7;
   // all residual loads first (the output may alias the residual, so loads cannot be hoisted over stores)
@@ -225,7 +221,8 @@ __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_
     if (row < M) {
       const float4 a = lds128(stg + (uint32_t)(rr * 8 + (g ^ (rr & 7))) * 16);
       const size_t off = (size_t)row * ep.ldo + col0 + 4 * g;
-      const float4 o = make_float4(r4[i].x + a.x, r4[i].y + a.y, r4[i].z + a.z, r4[i].w + a.w);
+      const float4 o = make_float4(r4[i].x + a.x + bias4.x, r4[i].y + a.y + bias4.y, r4[i].z + a.z + bias4.z,
+                                   r4[i].w + a.w + bias4.w);
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = o;
       if (ep.out_bf16 != nullptr) {
         uint2 pk;
@@ -236,6 +233,70 @@ __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_
     }
   }
   __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BN accumulator tile by one of the 8 epilogue warps (TMEM lane quarter q, column half
+// `half`). The TMEM read of chunk c+1 is in flight while chunk c is converted and stored.
+// ------------------------------------------------------------------------------------------------
+// Bias of the warp's BN/2 columns, fetched from global memory ahead of use. Residual mode (transposed stores): the
+// float4 of this lane's column group per chunk. Other modes (one row per thread): lane l holds column l of each
+// chunk in .x; bias_publish() spreads it through the warp's shared-memory slice (which aliases the transpose
+// staging that only the residual mode uses).
+template <int BN>
+struct EpiBias {
+  float4 b[BN / 64];
+};
+template <int BN, int MODE>
+__device__ __forceinline__ EpiBias<BN> bias_fetch(const GemmEpi& ep, int n0, int half, int lane, int N) {
+  EpiBias<BN> r;
+#pragma unroll
+  for (int i = 0; i < BN / 64; ++i) {
+    const int col0 = n0 + half * (BN / 2) + i * 32;
+    r.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr) {
+      if (MODE == EPI_RESID) {
+        if (col0 + 32 <= N && ep.vec_ok) r.b[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + (lane & 7));
+      } else if (col0 + lane < N) {
+        r.b[i].x = __ldg(ep.bias + col0 + lane);
+      }
+    }
+  }
+  return r;
+}
+template <int BN>
+__device__ __forceinline__ void bias_publish(const EpiBias<BN>& b, uint32_t bias_smem, int lane) {
+  __syncwarp();   // the previous tile's readers are done
+#pragma unroll
+  for (int i = 0; i < BN / 64; ++i)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + (uint32_t)(i * 32 + lane) * 4), "f"(b.b[i].x) : "memory");
+  __syncwarp();
+}
+
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0, int M, int N, uint32_t tmem_acc,
+                                              int q, int half, int lane, uint32_t stg, const EpiBias<BN>& bias) {
+  const uint32_t bias_smem = stg;   // non-residual modes: the staging slice holds the published bias
+  constexpr int NCH = BN / 64;   // chunks of 32 columns per warp
+  const int c0 = half * NCH;
+  const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);
+  const uint32_t taddr = tmem_acc + (uint32_t)(c0 * 32) + ((uint32_t)(q * 32) << 16);
+  uint32_t r[2][32];
+  tmem_ld_32x32b_x32(taddr, r[0]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
+    const int col0 = n0 + (c0 + c) * 32;
+    if (MODE == EPI_RESID && ep.vec_ok && col0 + 32 <= N)
+      epilogue_chunk_resid_t(ep, m0 + q * 32, lane, col0, v, M, stg, bias.b[c]);
+    else
+      epilogue_chunk<MODE>(ep, rc, col0, v, N, bias_smem + (uint32_t)c * 128);
+    if (c + 1 < NCH) tmem_ld_wait();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,43 +414,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096;
-    constexpr int NCH = BN / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
+    EpiBias<BN> bias = {}, bias_next = {};
+    if (MODE != EPI_RESID && (int)blockIdx.x < num_tiles)
+      bias_next = bias_fetch<BN, MODE>(ep, ((int)blockIdx.x % num_n) * BN, half, lane, N);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * C::BM;
       const int n0 = (tile % num_n) * BN;
-      const int c_begin = half * (NCH / 2), c_end = c_begin + NCH / 2;
+      if (MODE == EPI_RESID) {
+        bias = bias_fetch<BN, MODE>(ep, n0, half, lane, N);   // in flight while waiting for the accumulator
+      } else {
+        bias_publish<BN>(bias_next, stg, lane);
+        if (tile + (int)gridDim.x < num_tiles)   // next tile's bias: its latency hides behind this tile
+          bias_next = bias_fetch<BN, MODE>(ep, ((tile + (int)gridDim.x) % num_n) * BN, half, lane, N);
+      }
       if (MODE == EPI_RESID && ep.vec_ok) {
         // pull this warp's share of the residual tile towards L2 while the MMAs of the tile are still running
-        const int col = n0 + c_begin * 32;
+        const int col = n0 + half * (BN / 2);
         if (col < N) {
           const int r = m0 + q * 32 + lane;
           if (r < M) {
             const float* p = ep.resid + (size_t)r * ep.ldo + col;
 #pragma unroll
-            for (int i = 0; i < (NCH / 2) * 32 * 4 / 128; ++i)
+            for (int i = 0; i < (BN / 2) * 4 / 128; ++i)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 32));
           }
         }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + c * 32) + ((uint32_t)(q * 32) << 16);
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (MODE == EPI_RESID && ep.vec_ok && n0 + c * 32 + 32 <= N)
-          epilogue_chunk_resid_t(ep, m0 + q * 32, lane, n0 + c * 32, v, M, stg);
-        else
-          epilogue_chunk<MODE>(ep, rc, n0 + c * 32, v, N);
-      }
+      epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, half, lane, stg, bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -401,6 +456,214 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): one 256 x 256 output tile per pair of SMs. Each CTA loads its own 128 rows of
+// A and HALF of the B tile (128 of the 256 weight rows); tcgen05.mma.cta_group::2 reads both halves across the
+// pair, so a CTA pulls 32 KB instead of 48 KB through L2 per 64-wide k block - the 128 x 256 single-CTA kernel is
+// bound by exactly that traffic. The leader CTA (rank 0) issues the MMAs and owns the full / accumulator-empty
+// barriers; both CTAs' TMA loads signal the leader's full barrier, the leader's commits are multicast to both
+// CTAs' empty / accumulator-full barriers. Epilogue as in the single-CTA kernel (each CTA drains its own TMEM).
+// ------------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BM = 128;    // rows per CTA (256 per pair)
+  static constexpr int BN = 256;
+  static constexpr int BK = 64;
+  static constexpr int STAGES = 6;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr size_t STG_BYTES = 8 * 32 * 32 * 4;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
+};
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmEpi ep, int M, int N, int K) {
+  using C = Gemm2Cfg;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const uint32_t stg_base = smem_u32(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+  const int num_m = (M + 2 * C::BM - 1) / (2 * C::BM);
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + C::BK - 1) / C::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);   // 8 epilogue warps of each CTA arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
+        const int n0 = (tile % num_n) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_2sm(sa, &tmA, fb, kb * C::BK, m0);
+          tma_load_2d_2sm(sb, &tmB, fb, kb * C::BK, n0);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * C::BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * C::STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < C::BK / 16; ++k)
+            umma_bf16_ss_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 3);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096;
+    EpiBias<BN> bias = {}, bias_next = {};
+    if (MODE != EPI_RESID && pair < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, (pair % num_n) * BN, half, lane, N);
+    for (int tile = pair; tile < num_tiles; tile += npairs) {
+      const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
+      const int n0 = (tile % num_n) * BN;
+      if (MODE == EPI_RESID) {
+        bias = bias_fetch<BN, MODE>(ep, n0, half, lane, N);
+      } else {
+        bias_publish<BN>(bias_next, stg, lane);
+        if (tile + npairs < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, ((tile + npairs) % num_n) * BN, half, lane, N);
+      }
+      if (MODE == EPI_RESID && ep.vec_ok) {
+        const int col = n0 + half * (BN / 2);
+        if (col < N) {
+          const int r = m0 + q * 32 + lane;
+          if (r < M) {
+            const float* p = ep.resid + (size_t)r * ep.ldo + col;
+#pragma unroll
+            for (int i = 0; i < (BN / 2) * 4 / 128; ++i)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 32));
+          }
+        }
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, half, lane, stg, bias);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer may still read this CTA's shared memory / signal its barriers until here
+  if (warp == 2) tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
+}
+
+template <int MODE>
+static int launch_tc2(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                      const GemmEpi& ep, cudaStream_t stream) {
+  using C = Gemm2Cfg;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {(uint32_t)C::BK, (uint32_t)C::BM};
+    MMDM_TRY(make_tensor_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {(uint32_t)C::BK, (uint32_t)(C::BN / 2)};
+    MMDM_TRY(make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  gemm_bf16_tn_2cta_kernel<MODE><<<grid, 384, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int g_gemm_2cta = -1;
+static bool use_2cta() {
+  if (g_gemm_2cta < 0) {
+    const char* e = getenv("MMDM_GEMM_1CTA");   // debug / A-B comparison: force the single-CTA kernel
+    g_gemm_2cta = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_gemm_2cta == 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,8 +686,11 @@ __global__ void gemm_simt_debug_kernel(const __nv_bfloat16* __restrict__ A, int 
         if (col0 + j < N) acc[j] += a * __bfloat162float(W[(size_t)(col0 + j) * ldw + k]);
     }
   }
+  __shared__ float bias_s[32];
+  if (threadIdx.x < 32) bias_s[threadIdx.x] = (ep.bias != nullptr && col0 + (int)threadIdx.x < N) ? ep.bias[col0 + threadIdx.x] : 0.f;
+  __syncthreads();
   const RowCtx rc = make_row_ctx<MODE>(ep, row, M);
-  epilogue_chunk<MODE>(ep, rc, col0, acc, N);
+  epilogue_chunk<MODE>(ep, rc, col0, acc, N, smem_u32(bias_s));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -471,7 +737,9 @@ static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
     MMDM_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  // 128x256 tiles when N fills them; 128x128 for narrow / ragged N (e.g. the 262-wide output layer)
+  // CTA pairs on 256x256 tiles for the big projections; 128x256 single-CTA tiles when N fills them but M is
+  // small; 128x128 for narrow / ragged N (e.g. the 262-wide output layer)
+  if (N % 256 == 0 && M >= 512 && use_2cta()) return launch_tc2<MODE>(A, lda, W, ldw, M, N, K, ep, stream);
   if (N % 256 == 0 || N >= 1024) return launch_tc<256, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
   return launch_tc<128, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
 }

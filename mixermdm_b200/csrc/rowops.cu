@@ -10,50 +10,105 @@ namespace mmdm {
 // of the SAME normalised row is emitted (block input feeds SA of its own stream and the CA-KV of the
 // partner stream: models/utils/blocks.py:50,57 with models/in2in.py:439-440).
 // ------------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(256)
-ln_modulate_kernel(const float* __restrict__ h, int M, int T, const float* __restrict__ mod0, int ld_mod0,
-                   __nv_bfloat16* __restrict__ out0, const float* __restrict__ mod1, int ld_mod1,
-                   __nv_bfloat16* __restrict__ out1) {
+// A warp owns a run of consecutive rows of ONE sequence: the sequence's (1 + scale) and shift vectors are staged
+// once per run in the warp's shared-memory slice (registers would cost occupancy), and the next row is already in
+// flight while the current one is reduced and written, so the kernel streams h like a copy (one fp32 read, one
+// bf16 write per element) instead of stalling on a load -> reduce -> load(modulation) -> store chain per row.
+template <int NV, bool DUAL>
+__global__ void __launch_bounds__(128)
+ln_modulate_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq, int run_len,
+                   const float* __restrict__ mod0, int ld_mod0, __nv_bfloat16* __restrict__ out0,
+                   const float* __restrict__ mod1, int ld_mod1, __nv_bfloat16* __restrict__ out1) {
   constexpr int D = NV * 128;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  constexpr int NM = DUAL ? 2 : 1;
+  extern __shared__ float4 ln_smem[];   // [4 warps][NM][scale+1 | shift][D/4]
+  const int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const int row = warp;
-  const int s = row / T;
-  const float4* src = reinterpret_cast<const float4*>(h + (size_t)row * D);
-  float4 v[NV];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = src[i * 32 + lane];
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(sum) * (1.0f / D);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-  }
-  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+  if (task >= S * runs_per_seq) return;
+  const int s = task / runs_per_seq;
+  const int t0 = (task - s * runs_per_seq) * run_len;
+  const int t1 = min(T, t0 + run_len);
+  if (t0 >= t1) return;
 
-  auto emit = [&](const float* mod, int ld_mod, __nv_bfloat16* out) {
-    const float4* sc = reinterpret_cast<const float4*>(mod + (size_t)s * ld_mod);
-    const float4* sh = reinterpret_cast<const float4*>(mod + (size_t)s * ld_mod + D);
-    uint2* dst = reinterpret_cast<uint2*>(out + (size_t)row * D);
+  const float4* src = reinterpret_cast<const float4*>(h + ((size_t)s * T + t0) * D);
+  float4 v[NV], nx[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = src[i * 32 + lane];
+
+  float4* ms = ln_smem + (size_t)(threadIdx.x >> 5) * (NM * 2 * (D / 4));
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    const float* mod = m == 0 ? mod0 : mod1;
+    const int ld = m == 0 ? ld_mod0 : ld_mod1;
+    const float4* psc = reinterpret_cast<const float4*>(mod + (size_t)s * ld);
+    const float4* psh = reinterpret_cast<const float4*>(mod + (size_t)s * ld + D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 a = __ldg(sc + i * 32 + lane);
-      const float4 b = __ldg(sh + i * 32 + lane);
-      uint2 pk;
-      pk.x = pack_bf16x2(v[i].x * rstd * (1.f + a.x) + b.x, v[i].y * rstd * (1.f + a.y) + b.y);
-      pk.y = pack_bf16x2(v[i].z * rstd * (1.f + a.z) + b.z, v[i].w * rstd * (1.f + a.w) + b.w);
-      dst[i * 32 + lane] = pk;
+      float4 a = __ldg(psc + i * 32 + lane);
+      a.x += 1.f; a.y += 1.f; a.z += 1.f; a.w += 1.f;
+      ms[(m * 2) * (D / 4) + i * 32 + lane] = a;
+      ms[(m * 2 + 1) * (D / 4) + i * 32 + lane] = __ldg(psh + i * 32 + lane);
     }
-  };
-  emit(mod0, ld_mod0, out0);
-  if (out1 != nullptr) emit(mod1, ld_mod1, out1);
+  }
+  __syncwarp();
+
+  for (int t = t0; t < t1; ++t) {
+    if (t + 1 < t1) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nx[i] = src[(size_t)(t + 1 - t0) * (D / 4) + i * 32 + lane];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+    const size_t row = (size_t)s * T + t;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      uint2* dst = reinterpret_cast<uint2*>((m == 0 ? out0 : out1) + row * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 a = ms[(m * 2) * (D / 4) + i * 32 + lane];
+        const float4 b = ms[(m * 2 + 1) * (D / 4) + i * 32 + lane];
+        uint2 pk;
+        pk.x = pack_bf16x2(fmaf(v[i].x, a.x, b.x), fmaf(v[i].y, a.y, b.y));
+        pk.y = pack_bf16x2(fmaf(v[i].z, a.z, b.z), fmaf(v[i].w, a.w, b.w));
+        dst[i * 32 + lane] = pk;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = nx[i];
+  }
+}
+
+template <int NV>
+static void launch_ln_t(const float* h, int S, int T, const float* mod0, int ld_mod0, __nv_bfloat16* out0,
+                        const float* mod1, int ld_mod1, __nv_bfloat16* out1, cudaStream_t stream) {
+  // runs of ~24 rows: long enough to amortise the modulation vectors, short enough to fill the SMs (S*T/24 warps)
+  const int runs = (T + 23) / 24;
+  const int run_len = (T + runs - 1) / runs;
+  const int tasks = S * runs;
+  const int blocks = (tasks + 3) / 4;   // 4 warps per block, 8 KB (16 KB dual) of modulation vectors per warp at D=1024
+  const size_t smem1 = (size_t)4 * 2 * NV * 128 * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {   // the dual variant needs 64 KB at D = 1024
+    cudaFuncSetAttribute(ln_modulate_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem1));
+    attr_done = true;
+  }
+  if (out1 != nullptr)
+    ln_modulate_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, mod0, ld_mod0, out0, mod1, ld_mod1, out1);
+  else
+    ln_modulate_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, mod0, ld_mod0, out0, nullptr, 0, nullptr);
 }
 
 int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, int ld_mod0,
@@ -61,13 +116,13 @@ int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, i
                        cudaStream_t stream) {
   MMDM_REQUIRE(D == 128 || D == 256 || D == 512 || D == 1024, "ln_modulate: unsupported latent dim %d", D);
   MMDM_REQUIRE((ld_mod0 % 4) == 0 && (out1 == nullptr || (ld_mod1 % 4) == 0), "ln_modulate: mod pitch %% 4");
-  const int threads = 256;
-  const int blocks = (M * 32 + threads - 1) / threads;
+  MMDM_REQUIRE(T > 0 && M % T == 0, "ln_modulate: M=%d is not a whole number of T=%d row sequences", M, T);
+  const int S = M / T;
   switch (D) {
-    case 128: ln_modulate_kernel<1><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
-    case 256: ln_modulate_kernel<2><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
-    case 512: ln_modulate_kernel<4><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
-    default: ln_modulate_kernel<8><<<blocks, threads, 0, stream>>>(h, M, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1); break;
+    case 128: launch_ln_t<1>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
+    case 256: launch_ln_t<2>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
+    case 512: launch_ln_t<4>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
+    default: launch_ln_t<8>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
   }
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;

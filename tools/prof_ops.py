@@ -41,6 +41,7 @@ runs = {
     "ffn2": (lambda: ops.linear_bf16(mid, w2, mode=EPI_RESID, out=h, bias=bd, resid=h), 2.0 * M * D * F),
     "attn": (lambda: ops.attention(qk[:, :D], qk[:, D:], vt, att, S, T, H, hd, 0), 4.0 * S * H * T * (T + 1) * hd),
     "ln": (lambda: ops.ln_modulate(h, T, mod[:, :2 * D], out0=xn, mod1=mod[:, 2 * D:], out1=xf), 0.0),
+    "ln1": (lambda: ops.ln_modulate(h, T, mod[:, :2 * D], out0=xn), -1.0),
 }
 names = list(runs) if args.what == "all" else [args.what]
 runs["qkv"][0]()  # make qk/vt meaningful for attention
@@ -55,5 +56,6 @@ for n in names:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
-    extra = f"{fl / ms / 1e9:8.1f} TFLOP/s" if fl else f"{(M * D * 4 + 2 * M * D * 2) / ms / 1e6:8.1f} GB/s"
+    extra = (f"{fl / ms / 1e9:8.1f} TFLOP/s" if fl > 0 else
+             f"{(M * D * 4 + (2 if fl == 0 else 1) * M * D * 2) / ms / 1e6:8.1f} GB/s")
     print(f"{n:5s} {ms * 1e3:9.1f} us  {extra}")

@@ -166,6 +166,16 @@ mixstep_kernel(const MixStepParams P) {
   const float s_cfg = P.cfg_scale, s_unc = 1.f - P.cfg_scale;
   const bool two = (P.ncfg == 2);
   constexpr int NIT = (2 * NFEAT + 31) / 32;   // 17 words per lane per row
+  // A lane always handles the same 17 features of a row (f = lane + 32 i): which Mixer weight multiplies them,
+  // whether they are a joint height (floor search) and their per-person index are computed once, not per frame.
+  int meta[NIT];   // bits 0-5: person * 24 + weight index, bit 6: y coordinate of a joint position, bits 8-16: fi
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    const int f = lane + 32 * i;
+    const int p = f >= NFEAT, fi = f - p * NFEAT;
+    const int wi = (NW == 1) ? 0 : weight_index(fi);
+    meta[i] = (p * 24 + wi) | ((fi < OFF_VEL && (fi % 3) == 1) ? 64 : 0) | (fi << 8);
+  }
   for (int fl = warp; fl < nfr; fl += MIX_WARPS) {
     const int t = t_begin + fl;
     float* wv = wwarp + warp * 4 * 24;
@@ -195,10 +205,9 @@ mixstep_kernel(const MixStepParams P) {
     for (int i = 0; i < NIT; ++i) {
       const int f = lane + 32 * i;
       if (f < 2 * NFEAT) {
-        const int p = f >= NFEAT, fi = f - p * NFEAT;
-        const int wi = (NW == 1) ? 0 : weight_index(fi);
-        const float wc = wv[p * 24 + wi];
-        const float wu = two ? wv[(2 + p) * 24 + wi] : 0.f;
+        const int p = f >= NFEAT, fi = meta[i] >> 8;
+        const float wc = wv[meta[i] & 63];
+        const float wu = two ? wv[48 + (meta[i] & 63)] : 0.f;
         const float mc = o2c[i] + wc * (o1c[i] - o2c[i]);
         const float mu = two ? o2u[i] + wu * (o1u[i] - o2u[i]) : 0.f;
         if (P.mix_only == 1 || (P.mix_only == 0 && P.mix_out != nullptr)) {   // out_influenced ("eval" history)
@@ -217,7 +226,7 @@ mixstep_kernel(const MixStepParams P) {
             P.mix_out[rc + f] = g;
           } else {
             crow[f] = g;
-            if (fi < OFF_VEL && (fi % 3) == 1) {
+            if (meta[i] & 64) {
               if (p) ym1 = fminf(ym1, g); else ym0 = fminf(ym0, g);
             }
             if (final_step) P.final_out[rc + f] = g;   // rows of the un-doubled batch coincide with the cond half
@@ -279,7 +288,7 @@ mixstep_kernel(const MixStepParams P) {
     for (int i = 0; i < NIT; ++i) {
       const int f = lane + 32 * i;
       if (f < 2 * NFEAT) {
-        const int fi = f >= NFEAT ? f - NFEAT : f;
+        const int fi = meta[i] >> 8;
         const float pred = (crow[f] - tab[2 * NFEAT + fi]) * tab[3 * NFEAT + fi];
         const float eps = (c_recip * xs2[i] - pred) * c_inv_recipm1;
         P.x2[rx + f] = pred * c_ap + c_eps * eps;
@@ -314,7 +323,7 @@ mixstep_kernel(const MixStepParams P) {
     for (int i = 0; i < NIT; ++i) {
       const int f = lane + 32 * i;
       if (f < 2 * NFEAT) {
-        const int fi = f >= NFEAT ? f - NFEAT : f;
+        const int fi = meta[i] >> 8;
         const float pred = (crow[f] - tab[fi]) * tab[NFEAT + fi];
         const float eps = (c_recip * xs1[i] - pred) * c_inv_recipm1;
         P.x1[rx + f] = pred * c_ap + c_eps * eps;

@@ -48,22 +48,30 @@ __device__ __forceinline__ float copysign_ref(float a, float b) { return ((a < 0
 //   rot6d (interleaved a1=d[0,2,4], a2=d[1,3,5]) -> Gram-Schmidt matrix (rotation_conversions.py:513-535)
 //   -> quaternion (:98-120) -> axis-angle (:482-510) -> *(-1) -> *(-1) -> quaternion (:450-479)
 //   -> matrix (:38-66) -> first two rows, interleaved (:541-571).
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Same formula order as the reference; divisions and square roots use the approx instructions (2 ulp), which keeps
+// the deviation from the reference's own fp32 evaluation at the 1e-6 level (tested at 1e-4) and takes the round
+// trip from ~300 to ~90 instructions per joint - the fused mix kernel was issue-bound on it.
 __device__ __forceinline__ void rot6d_roundtrip(const float* d, float* o) {
   V3 a1 = v3(d[0], d[2], d[4]);
   V3 a2 = v3(d[1], d[3], d[5]);
-  const float n1 = fmaxf(sqrtf(dot3(a1, a1)), 1e-12f);
-  V3 b1 = v3(a1.x / n1, a1.y / n1, a1.z / n1);
+  const float i1 = rcp_approx(fmaxf(sqrt_fast(dot3(a1, a1)), 1e-12f));   // F.normalize eps (rotation_conversions.py:529)
+  V3 b1 = v3(a1.x * i1, a1.y * i1, a1.z * i1);
   const float pr = dot3(b1, a2);
   V3 b2 = v3(a2.x - pr * b1.x, a2.y - pr * b1.y, a2.z - pr * b1.z);
-  const float n2 = fmaxf(sqrtf(dot3(b2, b2)), 1e-12f);
-  b2 = v3(b2.x / n2, b2.y / n2, b2.z / n2);
+  const float i2 = rcp_approx(fmaxf(sqrt_fast(dot3(b2, b2)), 1e-12f));
+  b2 = v3(b2.x * i2, b2.y * i2, b2.z * i2);
   const V3 b3 = cross3(b1, b2);
   // matrix rows b1,b2,b3 -> quaternion
   const float m00 = b1.x, m11 = b2.y, m22 = b3.z;
-  const float qw = 0.5f * sqrt_pos(1.f + m00 + m11 + m22);
-  float qx = 0.5f * sqrt_pos(1.f + m00 - m11 - m22);
-  float qy = 0.5f * sqrt_pos(1.f - m00 + m11 - m22);
-  float qz = 0.5f * sqrt_pos(1.f - m00 - m11 + m22);
+  const float qw = 0.5f * sqrt_fast(fmaxf(1.f + m00 + m11 + m22, 0.f));
+  float qx = 0.5f * sqrt_fast(fmaxf(1.f + m00 - m11 - m22, 0.f));
+  float qy = 0.5f * sqrt_fast(fmaxf(1.f - m00 + m11 - m22, 0.f));
+  float qz = 0.5f * sqrt_fast(fmaxf(1.f - m00 - m11 + m22, 0.f));
   qx = copysign_ref(qx, b3.y - b2.z);
   qy = copysign_ref(qy, b1.z - b3.x);
   qz = copysign_ref(qz, b2.x - b1.y);
@@ -71,7 +79,7 @@ __device__ __forceinline__ void rot6d_roundtrip(const float* d, float* o) {
   // on (qw, qv) up to a factor 1 + O(|q|-1) that the normalising quaternion_to_matrix below removes, so the
   // atan2/sin/cos chain is not evaluated (difference to the reference's fp32 evaluation ~1e-6, tested at 1e-4).
   const float r = qw, i = qx, j = qy, k = qz;
-  const float two_s = 2.f / (r * r + i * i + j * j + k * k);
+  const float two_s = 2.f * rcp_approx(r * r + i * i + j * j + k * k);
   const float r00 = 1.f - two_s * (j * j + k * k), r01 = two_s * (i * j - k * r), r02 = two_s * (i * k + j * r);
   const float r10 = two_s * (i * j + k * r), r11 = 1.f - two_s * (i * i + k * k), r12 = two_s * (j * k - i * r);
   o[0] = r00; o[1] = r10; o[2] = r01; o[3] = r11; o[4] = r02; o[5] = r12;

@@ -107,6 +107,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(args):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu launch list of this
+    same workload (profiles/r01_launches_v3.csv -> profiles/r01_kernel_traffic.json, tools/summarize_launches.py).
+    Only valid for the configuration that was profiled (batch 32 x 300 frames, mode 4)."""
+    path = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    if not (os.path.exists(path) and args.batch == 32 and args.frames == 300 and args.mode == 4):
+        return {}
+    with open(path) as f:
+        return json.load(f)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -308,6 +319,7 @@ def main():
         return
 
     peaks = measured_peaks()
+    traffic = ncu_traffic(args)
     tot_ms = sum(p["ms"] for p in prof)
     gem = [p for p in prof if p["name"].startswith("gemm_")]
     gem_ms = sum(p["ms"] for p in gem)
@@ -316,7 +328,10 @@ def main():
     achieved_tf = gem_fl / (gem_ms * 1e-3) / 1e12 if gem_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (all tcgen05 GEMMs of the step)",
                 "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tflops_sustained"], "traffic": None,
+                "frac": achieved_tf / peaks["tflops_sustained"],
+                "traffic": traffic.get("gemm_class", {}).get("dram_bytes_per_launch"),
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the GEMM launches of one DDIM "
+                                  "step (profiles/r01_launches_v3.csv)" if traffic else None,
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step), of measured",
                 "launches": gem_n, "avg_launch_us": 1e3 * gem_ms / max(gem_n, 1),
                 "flops_per_launch": gem_fl / max(gem_n, 1), "share_of_step": gem_ms / tot_ms if tot_ms else None}
@@ -325,7 +340,8 @@ def main():
     if mixp and mixp[0]["ms"] > 0:
         gbs = mixp[0]["bytes"] / (mixp[0]["ms"] * 1e-3) / 1e9
         roofline_mix = {"bound": "hbm", "kernel": "mixstep_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": gbs / peaks["hbm_gbs"], "traffic": None, "bytes_per_launch": mixp[0]["bytes"] / mixp[0]["launches"],
+                        "frac": gbs / peaks["hbm_gbs"],
+                        "traffic": traffic.get("mixstep_kernel<23>", {}).get("dram_bytes_per_launch"), "bytes_per_launch": mixp[0]["bytes"] / mixp[0]["launches"],
                         "avg_launch_us": 1e3 * mixp[0]["ms"] / mixp[0]["launches"]}
     kernels = sorted(({"name": p["name"], "launches_per_ddim_step": p["launches"] / args.profile_steps,
                        "ms_per_ddim_step": p["ms"] / args.profile_steps, "share": p["ms"] / tot_ms if tot_ms else None,

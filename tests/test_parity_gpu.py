@@ -305,7 +305,7 @@ def test_sampler_rejects_what_the_reference_path_never_uses(golden):
         diff.ddim_sample_loop(cfgm, (2, 24, 524), clip_denoised=False, eta=0.5, **kw)
     with pytest.raises(Exception):
         mix.to(DEV)(torch.zeros(2, 400, 524, device=DEV), torch.zeros(2, dtype=torch.long, device=DEV),
-                    cond=torch.zeros(2, 6144, device=DEV), x2=torch.zeros(2, 400, 524, device=DEV))   # T > 319
+                    cond=torch.zeros(2, 6144, device=DEV), x2=torch.zeros(2, 400, 524, device=DEV))   # T > 303
 
 
 # ---- full-size geometry (BASELINE configs): D=1024, 8 layers, T=300 --------------------------------------------

@@ -39,6 +39,9 @@ int num_sms() {
 // tcgen05.ld 32x32b shape). Everything that does not depend on the column (row validity, sequence / frame
 // index of the row) is computed once per tile in RowCtx; the per-chunk fast path has no per-element guards.
 // ------------------------------------------------------------------------------------------------
+// modes whose fp32 output goes through the shared-memory transpose (full-line loads / stores)
+__host__ __device__ constexpr bool transposed_mode(int mode) { return mode == EPI_RESID || mode == EPI_EMBED_PE; }
+
 struct RowCtx {
   int row;
   bool valid;
@@ -114,7 +117,7 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N,
                                                uint32_t bias_smem) {
   if (!rc.valid || col0 >= N) return;
-  if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || MODE == EPI_RESID || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
+  if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || transposed_mode(MODE) || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
     epilogue_chunk_edge<MODE>(ep, rc, col0, v, N);
     return;
   }
@@ -198,6 +201,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& 
 // global access is a full 128-byte line instead of 32 scattered 16-byte pieces.
 // stg: per-warp staging of 32 x 32 floats, float4 slots XOR-swizzled -> conflict-free both ways.
 // bias4: the bias of this lane's 4 columns (col0 + 4*(lane&7) ...), the same for all 8 rows the lane writes.
+// The same path serves the motion-embedding epilogue (MODE == EPI_EMBED_PE): the addend is the positional-encoding
+// row pe[row % T] instead of the residual row, and the result is optionally written a second time dup_row_offset
+// rows further down (the unconditional CFG half shares the embedding).
+template <int MODE>
 __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_base, int lane, int col0,
                                                        const float* v, int M, uint32_t stg, float4 bias4) {
 #pragma unroll
@@ -211,8 +218,12 @@ __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = m_base + 4 * i + (lane >> 3);
-    r4[i] = (row < M) ? *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldo + col0 + 4 * g)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == EPI_EMBED_PE)
+      r4[i] = (row < M) ? __ldg(reinterpret_cast<const float4*>(ep.pe + (size_t)(row % ep.T) * ep.pe_ld + col0 + 4 * g))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    else
+      r4[i] = (row < M) ? *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldo + col0 + 4 * g)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -224,12 +235,54 @@ __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_
       const float4 o = make_float4(r4[i].x + a.x + bias4.x, r4[i].y + a.y + bias4.y, r4[i].z + a.z + bias4.z,
                                    r4[i].w + a.w + bias4.w);
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = o;
-      if (ep.out_bf16 != nullptr) {
+      if (MODE == EPI_EMBED_PE && ep.dup_row_offset != 0)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off + (size_t)ep.dup_row_offset * ep.ldo) = o;
+      if (MODE == EPI_RESID && ep.out_bf16 != nullptr) {
         uint2 pk;
         pk.x = pack_bf16x2(o.x, o.y);
         pk.y = pack_bf16x2(o.z, o.w);
         *reinterpret_cast<uint2*>(ep.out_bf16 + off) = pk;
       }
+    }
+  }
+  __syncwarp();
+}
+
+// Output-layer epilogue (MODE == EPI_FINAL), same transpose: (acc + bias) * std + mean written to the (B, T,
+// persons * nfeats) layout. Rows of that layout are only 8-byte aligned (nfeats = 262), hence float2 stores; a
+// quarter-warp still covers 128 contiguous bytes of one row instead of 32 lanes writing 32 different rows.
+__device__ __forceinline__ void epilogue_chunk_final_t(const GemmEpi& ep, int m_base, int lane, int col0,
+                                                       const float* v, int M, int N, uint32_t stg) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    sts128(stg + (uint32_t)(lane * 8 + (g ^ (lane & 7))) * 16,
+           make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
+  __syncwarp();
+  const int g = lane & 7;
+  const int c = col0 + 4 * g;
+  float bs[4], sd[4], mn[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const bool ok = c + e < N;
+    bs[e] = (ok && ep.bias) ? __ldg(ep.bias + c + e) : 0.f;
+    sd[e] = (ok && ep.std) ? __ldg(ep.std + c + e) : 1.f;
+    mn[e] = (ok && ep.std) ? __ldg(ep.mean + c + e) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    const int row = m_base + rr;
+    if (row < M && c < N) {
+      const float4 a = lds128(stg + (uint32_t)(rr * 8 + (g ^ (rr & 7))) * 16);
+      const int sq = row / ep.T, t = row - sq * ep.T;
+      float* dst = (ep.persons_per_row == 2)
+                       ? reinterpret_cast<float*>(ep.out) + ((size_t)(sq >> 1) * ep.T + t) * (2 * ep.nfeats) +
+                             (sq & 1) * ep.nfeats + c
+                       : reinterpret_cast<float*>(ep.out) + ((size_t)sq * ep.T + t) * ep.nfeats + c;
+      const float o0 = (a.x + bs[0]) * sd[0] + mn[0], o1 = (a.y + bs[1]) * sd[1] + mn[1];
+      const float o2 = (a.z + bs[2]) * sd[2] + mn[2], o3 = (a.w + bs[3]) * sd[3] + mn[3];
+      if (c + 1 < N) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1); else dst[0] = o0;
+      if (c + 3 < N) *reinterpret_cast<float2*>(dst + 2) = make_float2(o2, o3); else if (c + 2 < N) dst[2] = o2;
     }
   }
   __syncwarp();
@@ -255,7 +308,7 @@ __device__ __forceinline__ EpiBias<BN> bias_fetch(const GemmEpi& ep, int n0, int
     const int col0 = n0 + half * (BN / 2) + i * 32;
     r.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ep.bias != nullptr) {
-      if (MODE == EPI_RESID) {
+      if (transposed_mode(MODE)) {
         if (col0 + 32 <= N && ep.vec_ok) r.b[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + (lane & 7));
       } else if (col0 + lane < N) {
         r.b[i].x = __ldg(ep.bias + col0 + lane);
@@ -291,8 +344,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0,
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
     const int col0 = n0 + (c0 + c) * 32;
-    if (MODE == EPI_RESID && ep.vec_ok && col0 + 32 <= N)
-      epilogue_chunk_resid_t(ep, m0 + q * 32, lane, col0, v, M, stg, bias.b[c]);
+    if (transposed_mode(MODE) && ep.vec_ok && col0 + 32 <= N)
+      epilogue_chunk_resid_t<MODE>(ep, m0 + q * 32, lane, col0, v, M, stg, bias.b[c]);
+    else if (MODE == EPI_FINAL && ep.final_vec_ok && col0 < N)
+      epilogue_chunk_final_t(ep, m0 + q * 32, lane, col0, v, M, N, stg);
     else
       epilogue_chunk<MODE>(ep, rc, col0, v, N, bias_smem + (uint32_t)c * 128);
     if (c + 1 < NCH) tmem_ld_wait();
@@ -417,14 +472,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     EpiBias<BN> bias = {}, bias_next = {};
-    if (MODE != EPI_RESID && (int)blockIdx.x < num_tiles)
+    if (!transposed_mode(MODE) && (int)blockIdx.x < num_tiles)
       bias_next = bias_fetch<BN, MODE>(ep, ((int)blockIdx.x % num_n) * BN, half, lane, N);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * C::BM;
       const int n0 = (tile % num_n) * BN;
-      if (MODE == EPI_RESID) {
+      if (transposed_mode(MODE)) {
         bias = bias_fetch<BN, MODE>(ep, n0, half, lane, N);   // in flight while waiting for the accumulator
-      } else {
+      } else if (MODE != EPI_FINAL) {   // (the output layer reads bias / std / mean per column group itself)
         bias_publish<BN>(bias_next, stg, lane);
         if (tile + (int)gridDim.x < num_tiles)   // next tile's bias: its latency hides behind this tile
           bias_next = bias_fetch<BN, MODE>(ep, ((tile + (int)gridDim.x) % num_n) * BN, half, lane, N);
@@ -592,13 +647,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096;
     EpiBias<BN> bias = {}, bias_next = {};
-    if (MODE != EPI_RESID && pair < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, (pair % num_n) * BN, half, lane, N);
+    if (!transposed_mode(MODE) && pair < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, (pair % num_n) * BN, half, lane, N);
     for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
       const int n0 = (tile % num_n) * BN;
-      if (MODE == EPI_RESID) {
+      if (transposed_mode(MODE)) {
         bias = bias_fetch<BN, MODE>(ep, n0, half, lane, N);
-      } else {
+      } else if (MODE != EPI_FINAL) {
         bias_publish<BN>(bias_next, stg, lane);
         if (tile + npairs < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, ((tile + npairs) % num_n) * BN, half, lane, N);
       }
@@ -767,6 +822,7 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
                (ep.out_bf16 == nullptr || (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0) &&
                (ep.pe == nullptr || ((reinterpret_cast<uintptr_t>(ep.pe) & 15) == 0 && (ep.pe_ld % 4) == 0)))
                   ? 1 : 0;
+  e2.final_vec_ok = (ep.mode == EPI_FINAL && (reinterpret_cast<uintptr_t>(ep.out) & 7) == 0 && (ep.nfeats % 2) == 0) ? 1 : 0;
   switch (ep.mode) {
     case EPI_BF16:
       if (ep.vt_col0 >= 0)

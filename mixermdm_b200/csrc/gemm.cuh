@@ -37,6 +37,7 @@ struct GemmEpi {
   int nfeats = 0;
   int persons_per_row = 2;               // 2: sequences alternate persons (s&1); 1: plain (s*T+t)*nfeats
   int vec_ok = 0;                        // set by launch_gemm: pointers/pitches allow 16-byte vector access
+  int final_vec_ok = 0;                  // set by launch_gemm: EPI_FINAL rows allow 8-byte vector stores
 };
 
 // A: [M, K] bf16 with row pitch lda (elements, lda*2 % 16 == 0); W: [N, K] bf16 pitch ldw.

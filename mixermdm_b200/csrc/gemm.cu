@@ -123,10 +123,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& 
   }
   float b[32];
   load_bias32(bias_smem, b);
-  if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
+  if (MODE == EPI_GELU_BF16) {
+    // packed fp32x2 evaluation: the epilogue was issue-bound on the scalar form
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)rc.row * ep.ldo + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 pk;
+      pk.x = gelu_fast2_bf16(add2(pack2(v[8 * j], v[8 * j + 1]), pack2(b[8 * j], b[8 * j + 1])));
+      pk.y = gelu_fast2_bf16(add2(pack2(v[8 * j + 2], v[8 * j + 3]), pack2(b[8 * j + 2], b[8 * j + 3])));
+      pk.z = gelu_fast2_bf16(add2(pack2(v[8 * j + 4], v[8 * j + 5]), pack2(b[8 * j + 4], b[8 * j + 5])));
+      pk.w = gelu_fast2_bf16(add2(pack2(v[8 * j + 6], v[8 * j + 7]), pack2(b[8 * j + 6], b[8 * j + 7])));
+      dst[j] = pk;
+    }
+  } else if (MODE == EPI_BF16) {
     float o[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = (MODE == EPI_GELU_BF16) ? gelu_fast(v[j] + b[j]) : (v[j] + b[j]);
+    for (int j = 0; j < 32; ++j) o[j] = v[j] + b[j];
     if (MODE == EPI_BF16 && ep.vt_col0 >= 0 && col0 >= ep.vt_col0) {
       // V^T: the 32 columns of a chunk lie inside one head (hd is 64 or 128, chunks are 32-aligned)
       const int nn = col0 - ep.vt_col0;
@@ -301,11 +313,11 @@ struct EpiBias {
   float4 b[BN / 64];
 };
 template <int BN, int MODE>
-__device__ __forceinline__ EpiBias<BN> bias_fetch(const GemmEpi& ep, int n0, int half, int lane, int N) {
-  EpiBias<BN> r;
+__device__ __forceinline__ EpiBias<BN> bias_fetch(const GemmEpi& ep, int n0, int c0, int lane, int N) {
+  EpiBias<BN> r;   // c0: first 32-column chunk of the warp; up to BN/64 chunks are fetched
 #pragma unroll
   for (int i = 0; i < BN / 64; ++i) {
-    const int col0 = n0 + half * (BN / 2) + i * 32;
+    const int col0 = n0 + (c0 + i) * 32;
     r.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ep.bias != nullptr) {
       if (transposed_mode(MODE)) {
@@ -328,10 +340,9 @@ __device__ __forceinline__ void bias_publish(const EpiBias<BN>& b, uint32_t bias
 
 template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0, int M, int N, uint32_t tmem_acc,
-                                              int q, int half, int lane, uint32_t stg, const EpiBias<BN>& bias) {
+                                              int q, int c0, int cnt, int lane, uint32_t stg, const EpiBias<BN>& bias) {
   const uint32_t bias_smem = stg;   // non-residual modes: the staging slice holds the published bias
-  constexpr int NCH = BN / 64;   // chunks of 32 columns per warp
-  const int c0 = half * NCH;
+  constexpr int NCH = BN / 64;   // at most this many chunks of 32 columns per warp: chunks [c0, c0 + cnt)
   const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);
   const uint32_t taddr = tmem_acc + (uint32_t)(c0 * 32) + ((uint32_t)(q * 32) << 16);
   uint32_t r[2][32];
@@ -339,7 +350,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0,
   tmem_ld_wait();
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+    if (c >= cnt) break;
+    if (c + 1 < cnt) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
@@ -350,7 +362,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0,
       epilogue_chunk_final_t(ep, m0 + q * 32, lane, col0, v, M, N, stg);
     else
       epilogue_chunk<MODE>(ep, rc, col0, v, N, bias_smem + (uint32_t)c * 128);
-    if (c + 1 < NCH) tmem_ld_wait();
+    if (c + 1 < cnt) tmem_ld_wait();
   }
 }
 
@@ -473,16 +485,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     EpiBias<BN> bias = {}, bias_next = {};
     if (!transposed_mode(MODE) && (int)blockIdx.x < num_tiles)
-      bias_next = bias_fetch<BN, MODE>(ep, ((int)blockIdx.x % num_n) * BN, half, lane, N);
+      bias_next = bias_fetch<BN, MODE>(ep, ((int)blockIdx.x % num_n) * BN, half * (BN / 64), lane, N);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * C::BM;
       const int n0 = (tile % num_n) * BN;
       if (transposed_mode(MODE)) {
-        bias = bias_fetch<BN, MODE>(ep, n0, half, lane, N);   // in flight while waiting for the accumulator
+        bias = bias_fetch<BN, MODE>(ep, n0, half * (BN / 64), lane, N);   // in flight while waiting for the accumulator
       } else if (MODE != EPI_FINAL) {   // (the output layer reads bias / std / mean per column group itself)
         bias_publish<BN>(bias_next, stg, lane);
         if (tile + (int)gridDim.x < num_tiles)   // next tile's bias: its latency hides behind this tile
-          bias_next = bias_fetch<BN, MODE>(ep, ((tile + (int)gridDim.x) % num_n) * BN, half, lane, N);
+          bias_next = bias_fetch<BN, MODE>(ep, ((tile + (int)gridDim.x) % num_n) * BN, half * (BN / 64), lane, N);
       }
       if (MODE == EPI_RESID && ep.vec_ok) {
         // pull this warp's share of the residual tile towards L2 while the MMAs of the tile are still running
@@ -499,7 +511,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, half, lane, stg, bias);
+      epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, half * (BN / 64), BN / 64, lane,
+                              stg, bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -522,24 +535,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // barriers; both CTAs' TMA loads signal the leader's full barrier, the leader's commits are multicast to both
 // CTAs' empty / accumulator-full barriers. Epilogue as in the single-CTA kernel (each CTA drains its own TMEM).
 // ------------------------------------------------------------------------------------------------
+template <int MODE>
 struct Gemm2Cfg {
   static constexpr int BM = 128;    // rows per CTA (256 per pair)
   static constexpr int BN = 256;
   static constexpr int BK = 64;
   static constexpr int STAGES = 6;
+  // Epilogue warps: 8 (two per TMEM lane quarter, 4 chunks of 32 columns each); the GELU epilogue costs ~20
+  // instructions per element and paced FFN-1 at 55 % tensor-pipe activity, so it gets 12 (3 + 3 + 2 chunks).
+  static constexpr int EPI_WARPS = (MODE == EPI_GELU_BF16) ? 12 : 8;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr size_t STG_BYTES = 8 * 32 * 32 * 4;
+  // per-warp staging: a 32 x 32 fp32 transpose slab for the full-line store modes, else just the bias slice
+  static constexpr uint32_t STG_WARP_BYTES = (transposed_mode(MODE) || MODE == EPI_FINAL) ? 4096 : 512;
+  static constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG_WARP_BYTES;
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
 };
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<MODE>::THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmEpi ep, int M, int N, int K) {
-  using C = Gemm2Cfg;
+  using C = Gemm2Cfg<MODE>;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -570,7 +590,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 16);   // 8 epilogue warps of each CTA arrive on the leader's barrier
+      mbar_init(&tempty_bar[i], 2 * C::EPI_WARPS);   // the epilogue warps of both CTAs arrive on the leader's barrier
     }
     fence_barrier_init();
   }
@@ -641,24 +661,27 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;                       // column part of the tile this warp drains
+    constexpr int NPART = C::EPI_WARPS / 4, NCHUNK = BN / 32;
+    const int c0 = NPART == 2 ? part * 4 : part * 3;        // first chunk ...
+    const int cnt = NPART == 2 ? 4 : (part < 2 ? 3 : NCHUNK - 6);   // ... and chunk count
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
-    const uint32_t stg = stg_base + (uint32_t)(warp - 4) * 4096;
+    const uint32_t stg = stg_base + (uint32_t)(warp - 4) * C::STG_WARP_BYTES;
     EpiBias<BN> bias = {}, bias_next = {};
-    if (!transposed_mode(MODE) && pair < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, (pair % num_n) * BN, half, lane, N);
+    if (!transposed_mode(MODE) && pair < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, (pair % num_n) * BN, c0, lane, N);
     for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
       const int n0 = (tile % num_n) * BN;
       if (transposed_mode(MODE)) {
-        bias = bias_fetch<BN, MODE>(ep, n0, half, lane, N);
+        bias = bias_fetch<BN, MODE>(ep, n0, c0, lane, N);
       } else if (MODE != EPI_FINAL) {
         bias_publish<BN>(bias_next, stg, lane);
-        if (tile + npairs < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, ((tile + npairs) % num_n) * BN, half, lane, N);
+        if (tile + npairs < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, ((tile + npairs) % num_n) * BN, c0, lane, N);
       }
       if (MODE == EPI_RESID && ep.vec_ok) {
-        const int col = n0 + half * (BN / 2);
+        const int col = n0 + c0 * 32;
         if (col < N) {
           const int r = m0 + q * 32 + lane;
           if (r < M) {
@@ -671,7 +694,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, half, lane, stg, bias);
+      epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
@@ -688,7 +711,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 template <int MODE>
 static int launch_tc2(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                       const GemmEpi& ep, cudaStream_t stream) {
-  using C = Gemm2Cfg;
+  using C = Gemm2Cfg<MODE>;
   static bool attr_done = false;
   if (!attr_done) {
     MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -713,7 +736,7 @@ static int launch_tc2(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm_bf16_tn_2cta_kernel<MODE><<<grid, 384, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
+  gemm_bf16_tn_2cta_kernel<MODE><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

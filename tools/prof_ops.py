@@ -38,6 +38,7 @@ runs = {
     "qkv": (lambda: ops.linear_bf16(x, w_qkv, mode=EPI_BF16, out=qk, bias=b3, vt=vt, vt_col0=2 * D, T=T, H=H, hd=hd, Tp=Tp), 2.0 * M * 3 * D * D),
     "proj": (lambda: ops.linear_bf16(x, w_o, mode=EPI_RESID, out=h, bias=b1, resid=h), 2.0 * M * D * D),
     "ffn1": (lambda: ops.linear_bf16(x, w1, mode=EPI_GELU_BF16, out=mid, bias=bf), 2.0 * M * F * D),
+    "ffn1_plain": (lambda: ops.linear_bf16(x, w1, mode=EPI_BF16, out=mid, bias=bf), 2.0 * M * F * D),
     "ffn2": (lambda: ops.linear_bf16(mid, w2, mode=EPI_RESID, out=h, bias=bd, resid=h), 2.0 * M * D * F),
     "attn": (lambda: ops.attention(qk[:, :D], qk[:, D:], vt, att, S, T, H, hd, 0), 4.0 * S * H * T * (T + 1) * hd),
     "ln": (lambda: ops.ln_modulate(h, T, mod[:, :2 * D], out0=xn, mod1=mod[:, 2 * D:], out1=xf), 0.0),

@@ -105,7 +105,9 @@ typedef struct mmdm_mixstep_args {
                                 ((c*B+b)*2+p) (pooled modes 1,3); 1 (modes 1,2) or 23 (modes 3,4) valid columns */
   const float* out1a; const float* out2a;  /* (ncfg*B,T,524) aligned predictions */
   float* x1; float* x2;      /* (B,T,524) state streams, updated in place */
-  float* final_out;          /* (B,T,524) */
+  float* final_out;          /* (B,T,524): the guided prediction of the step. The result at index 0; at every other
+                                index the kernel's own hand-over buffer between its two phases (contents = the raw
+                                guided prediction of that step) */
   float* mix_out;
   const float* mean1; const float* std1; const float* mean2; const float* std2;
   float* hist_i1; float* hist_i2;
@@ -186,7 +188,7 @@ int mmdm_set_state(mmdm_handle* h, const float* x1, const float* x2, int step_in
 int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream);
 /* one DDIM step: CFG-doubled Mixer.forward + process_xstart + DDIM update; decrements the device step index.
  * replaces MixerDiffusion.ddim_sample (gaussian_diffusion.py:1902-1965) */
-int mmdm_step(mmdm_handle* h, float* final_out /* (B,T,524) written when the index is 0, or NULL */, void* stream);
+int mmdm_step(mmdm_handle* h, float* final_out /* (B,T,524) guided prediction of the step (the sample when the index is 0), or NULL */, void* stream);
 /* whole loop from noise; result = pred_xstart2 of the last step (gaussian_diffusion.py:1769-1820).
  * use_graph != 0 replays one captured step graph nsteps times. hist_i1/hist_i2: optional
  * (nsteps, 2B, T, 262) fp32 device buffers receiving the expanded Mixer weights, or NULL.

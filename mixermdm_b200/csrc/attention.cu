@@ -14,7 +14,7 @@
 namespace mmdm {
 
 struct AttnParams {
-  int S, T, H, NK, n1, n2, kv_xor;
+  int S, T, H, NK, n1, n2, kv_xor, rev;
   float scale_log2;
 };
 
@@ -174,7 +174,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
 
   auto item_sh = [&](int k, int& s, int& h) {
-    const int item = (int)blockIdx.x + k * (int)gridDim.x;
+    int item = (int)blockIdx.x + k * (int)gridDim.x;
+    if (p.rev) item = total_items - 1 - item;   // last sequences first (L2 reuse of the projection GEMM's tail)
     s = item / p.H;
     h = item - s * p.H;
   };
@@ -522,7 +523,7 @@ static int num_sms_attn() {
 template <int HD>
 static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk,
                               const __nv_bfloat16* vt, int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H,
-                              int kv_xor, cudaStream_t stream) {
+                              int kv_xor, int rev, cudaStream_t stream) {
   using C = AttnCfg<HD>;
   CUtensorMap tmQ, tmK, tmV, tmO;
   {
@@ -556,6 +557,7 @@ static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat
   p.n1 = p.NK < (int)C::EARLY_KEYS ? p.NK : (int)C::EARLY_KEYS;   // keys [0,224) -> early S part, the rest -> late
   p.n2 = p.NK - p.n1;
   p.kv_xor = kv_xor;
+  p.rev = rev;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   const int items = S * H;
   const int grid = items < num_sms_attn() ? items : num_sms_attn();
@@ -580,15 +582,15 @@ int attention_init() {
 
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
                      int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H, int hd, int kv_xor,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int rev) {
   static int inited = attention_init();
   MMDM_REQUIRE(inited == 0, "attention: kernel attribute setup failed");
   MMDM_REQUIRE(T >= 1 && T <= 303, "attention: T=%d outside the single-tile range [1,303]", T);
   MMDM_REQUIRE(hd == 64 || hd == 128, "attention: head dim %d not in {64,128}", hd);
   MMDM_REQUIRE((ldq % 8) == 0 && (ldk % 8) == 0 && (Tp % 8) == 0 && (ldo % 8) == 0 && Tp >= T,
                "attention: pitches must be multiples of 8 elements");
-  if (hd == 128) return launch_attention_t<128>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, stream);
-  return launch_attention_t<64>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, stream);
+  if (hd == 128) return launch_attention_t<128>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, rev, stream);
+  return launch_attention_t<64>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, rev, stream);
 }
 
 }  // namespace mmdm

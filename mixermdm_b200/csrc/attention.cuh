@@ -8,7 +8,7 @@ namespace mmdm {
 // Keys/values of query sequence s come from sequence (s ^ kv_xor).
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
                      int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H, int hd, int kv_xor,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int rev = 0);
 
 int attention_init();
 

@@ -4,6 +4,7 @@
 // so all three networks see GEMMs with M = 2*Bx*T rows and the two streams of the interaction denoiser are
 // batched along M (they share weights: models/in2in.py:439-440), as are the two persons of the individual
 // denoiser (models/mixermdm.py:685-686) and of the Influence network (:735-736).
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -123,6 +124,11 @@ struct mmdm_handle {
   float *graph_h1 = nullptr, *graph_h2 = nullptr;
   Profiler prof;
   long long launches = 0;
+  // Serpentine traversal: every big launch (LN, GEMM, attention) walks its rows in the direction opposite to the
+  // launch before it, so a consumer starts on the rows its producer wrote last - the part of a 80-160 MB
+  // activation that is still in the 126 MB L2. MMDM_SERPENTINE=0 turns it off (A/B measurements).
+  bool serpentine = true;
+  int rev = 0;
 };
 
 namespace mmdm {
@@ -219,10 +225,17 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
 // ------------------------------------------------------------------------------------------------
 // building blocks
 // ------------------------------------------------------------------------------------------------
+static int next_dir(mmdm_handle* h, bool flip = true) {
+  if (flip) h->rev ^= 1;
+  return h->serpentine ? h->rev : 0;
+}
+
 static int gemm(mmdm_handle* h, const char* tag, const bf16* A, int lda, const void* W, int ldw, int M, int N, int K,
-                const GemmEpi& ep, cudaStream_t st) {
+                const GemmEpi& ep, cudaStream_t st, bool flip = true) {
   Scope sc(h, tag, st, 2.0 * M * N * K);
-  return launch_gemm(A, lda, reinterpret_cast<const bf16*>(W), ldw, M, N, K, ep, st);
+  GemmEpi e = ep;
+  e.rev = next_dir(h, flip);
+  return launch_gemm(A, lda, reinterpret_cast<const bf16*>(W), ldw, M, N, K, e, st);
 }
 
 struct Mods {   // AdaLN outputs of one block: pointers to the (scale|shift) rows of sequence 0 + pitches
@@ -282,13 +295,14 @@ static int attention(mmdm_handle* h, const Net& n, int S, int T, int kv_xor, cud
   Workspace& ws = h->ws;
   const int D = n.w.D;
   Scope sc(h, "attention", st, 4.0 * S * n.w.H * (double)T * (T + 1) * n.hd());
-  return launch_attention(ws.qk, 2 * D, ws.qk + D, 2 * D, ws.vt, h->Tp, ws.att, D, S, T, n.w.H, n.hd(), kv_xor, st);
+  return launch_attention(ws.qk, 2 * D, ws.qk + D, 2 * D, ws.vt, h->Tp, ws.att, D, S, T, n.w.H, n.hd(), kv_xor, st,
+                          next_dir(h));
 }
 
 static int ln(mmdm_handle* h, const float* src, int M, int D, int T, const float* m0, int ld0, bf16* o0,
               const float* m1, int ld1, bf16* o1, cudaStream_t st) {
   Scope sc(h, "ln_modulate", st);
-  return launch_ln_modulate(src, M, D, T, m0, ld0, o0, m1, ld1, o1, st);
+  return launch_ln_modulate(src, M, D, T, m0, ld0, o0, m1, ld1, o1, st, next_dir(h));
 }
 
 // one transformer block on the residual stream hres (M, D), in place.
@@ -329,7 +343,7 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
     GemmEpi ek;
     ek.mode = EPI_BF16; ek.bias = b.ca_kv_b; ek.out = ws.qk + D; ek.ldo = 2 * D;
     ek.vt_col0 = D; ek.vt = ws.vt; ek.T = T; ek.H = H; ek.hd = hd; ek.Tp = h->Tp;
-    MMDM_TRY(gemm(h, "gemm_qkv", ws.xf, D, b.ca_kv_w, D, M, 2 * D, D, ek, st));
+    MMDM_TRY(gemm(h, "gemm_qkv", ws.xf, D, b.ca_kv_w, D, M, 2 * D, D, ek, st, /*flip=*/false));   // same way as the q GEMM
     MMDM_TRY(attention(h, n, S, T, kvsrc == nullptr ? 1 : 0, st));
     er.bias = b.ca_out_b;
     MMDM_TRY(gemm(h, "gemm_proj", ws.att, D, b.ca_out_w, D, M, D, D, er, st));
@@ -487,6 +501,7 @@ struct EvalHist {   // optional per-step outputs of Mixer mode "eval" (mixermdm.
 static int step_body(mmdm_handle* h, float* final_out, float* h1, float* h2, cudaStream_t st,
                      const EvalHist* eh = nullptr) {
   const float* temb[3] = {h->ws.temb_tab[0], h->ws.temb_tab[1], h->ws.temb_tab[2]};
+  h->rev = 0;
   MMDM_TRY(run_mixer_nets(h, h->ws.x1, h->ws.x2, h->B, 1, temb, h->ws.step, st));
   MMDM_TRY(run_head(h, 4 * h->B, h->T, st));
   MixStepParams P = mix_params(h);
@@ -542,6 +557,10 @@ int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_han
   MMDM_TRY(motion_init());
   mmdm_handle* h = new mmdm_handle();
   h->cfg = *cfg;
+  {
+    const char* e = getenv("MMDM_SERPENTINE");
+    h->serpentine = !(e && e[0] == '0');
+  }
   h->timestep_map.assign(cfg->timestep_map, cfg->timestep_map + cfg->nsteps);
   h->cfg.timestep_map = nullptr;
   for (int i = 0; i < 3; ++i) {

@@ -604,7 +604,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += npairs) {
+      for (int it = pair; it < num_tiles; it += npairs) {
+        const int tile = ep.rev ? num_tiles - 1 - it : it;
         const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
         const int n0 = (tile % num_n) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -670,15 +671,20 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     const uint32_t stg = stg_base + (uint32_t)(warp - 4) * C::STG_WARP_BYTES;
     EpiBias<BN> bias = {}, bias_next = {};
-    if (!transposed_mode(MODE) && pair < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, (pair % num_n) * BN, c0, lane, N);
-    for (int tile = pair; tile < num_tiles; tile += npairs) {
+    // ep.rev walks the tiles from the last row block down (see GemmEpi::rev)
+    auto tile_of = [&](int it) { return ep.rev ? num_tiles - 1 - it : it; };
+    if (!transposed_mode(MODE) && pair < num_tiles)
+      bias_next = bias_fetch<BN, MODE>(ep, (tile_of(pair) % num_n) * BN, c0, lane, N);
+    for (int it = pair; it < num_tiles; it += npairs) {
+      const int tile = tile_of(it);
       const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
       const int n0 = (tile % num_n) * BN;
       if (transposed_mode(MODE)) {
         bias = bias_fetch<BN, MODE>(ep, n0, c0, lane, N);
       } else if (MODE != EPI_FINAL) {
         bias_publish<BN>(bias_next, stg, lane);
-        if (tile + npairs < num_tiles) bias_next = bias_fetch<BN, MODE>(ep, ((tile + npairs) % num_n) * BN, c0, lane, N);
+        if (it + npairs < num_tiles)
+          bias_next = bias_fetch<BN, MODE>(ep, (tile_of(it + npairs) % num_n) * BN, c0, lane, N);
       }
       if (MODE == EPI_RESID && ep.vec_ok) {
         const int col = n0 + c0 * 32;

@@ -36,6 +36,9 @@ struct GemmEpi {
   const float* mean = nullptr;
   int nfeats = 0;
   int persons_per_row = 2;               // 2: sequences alternate persons (s&1); 1: plain (s*T+t)*nfeats
+  // Walk the output tiles from the last row block down (CTA-pair kernel only). The engine alternates the direction
+  // from launch to launch so that a kernel starts on the rows its producer wrote last, which are still in L2.
+  int rev = 0;
   int vec_ok = 0;                        // set by launch_gemm: pointers/pitches allow 16-byte vector access
   int final_vec_ok = 0;                  // set by launch_gemm: EPI_FINAL rows allow 8-byte vector stores
 };

@@ -12,6 +12,7 @@
 #include "motion.cuh"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "motion_math.cuh"
 
@@ -102,24 +103,166 @@ int launch_align(const float* out1, const float* out2, float* out1a, float* out2
 
 // ------------------------------------------------------------------------------------------------
 // mixstep_kernel
+//
+// Persistent 4-CTA clusters, one sample at a time per cluster; CTA `rank` owns frames [rank*FR, rank*FR+FR).
+// HBM latency under load is ~2 us, so an SM needs >= 100 KB of reads in flight to stream at its share of the
+// bandwidth (tools/micro/bulk_ring.cu). Shared memory is therefore ONE ring of ~100 row slots (2096 B each) that
+// two producer warps fill with cp.async.bulk, one row per lane, far ahead of the 14 consumer warps:
+//   phase 1 of a sample, per frame: rows out1a, out2a of the cond and of the uncond half  -> mix, guidance,
+//           floor search; the guided prediction g goes to global memory (P.final_out doubles as that scratch:
+//           it is only a result at the last step) where it stays in L2,
+//   phase 2, per frame: rows x1, x2 and g -> process_xstart (centring in place in the slot) + DDIM update.
+// The row stream is software-pipelined across samples - P1(0), P1(1), P2(0), P1(2), P2(1), ... - so the cluster
+// exchange centring needs (min-y over all frames, frame-0 root and hips, through DSMEM and remote mbarrier
+// arrives) and the visibility of g have a whole phase to complete and the ring never drains at a phase boundary.
+// Streaming reads carry an L2 evict_first policy so that they do not push g out of L2.
 // ------------------------------------------------------------------------------------------------
-constexpr int MIX_THREADS = 512;    // 16 warps per CTA (one CTA per SM): latency hiding matters more than per-lane batch depth
-constexpr int MIX_WARPS = MIX_THREADS / 32;
-constexpr int MIX_CLUSTER = 4;     // 4 SMs per sample: ~36 clusters resident (8-CTA clusters only reach 15)
-constexpr int HD_MIX = 512;  // Mixer latent dim the head reads
+constexpr int MIX_CONSUMERS = 14;
+constexpr int MIX_PRODUCERS = 2;
+constexpr int MIX_THREADS = (MIX_CONSUMERS + MIX_PRODUCERS) * 32;
+constexpr int MIX_CLUSTER = 4;                         // 4 SMs per sample: 33 clusters resident (8-CTA clusters: 15)
+constexpr int ROWF = 2 * NFEAT;                        // 524 floats per (sample, frame) row
+constexpr int ROWB = ROWF * 4;                         // 2096 bytes
+constexpr int ROW4 = ROWF / 4;                         // 131 float4
+constexpr int NIT4 = (ROW4 + 31) / 32;                 // 5 float4 per lane per row
+constexpr int MIX_MAX_SLOTS = 104;
+constexpr int MIX_SMEM_MAX = 227 * 1024;
 
 struct MixExport {        // per-CTA data other CTAs of the cluster read through DSMEM
   float ymin[2];
   float f0[2][9];         // frame-0 joints 0,1,2 (xyz) per person (valid on cluster rank 0)
 };
 
-static size_t mix_smem_bytes(int frames_per_cta) {
-  size_t b = (size_t)frames_per_cta * 2 * NFEAT * 4;         // guided prediction of my frames
-  b += (size_t)MIX_WARPS * 4 * 24 * 4;                       // per-warp weights [4][24]
-  b += (size_t)MIX_WARPS * 2 * 4;                            // per-warp y-min
-  b += sizeof(MixExport);
-  b += 4 * NFEAT * 4;                                        // 1/std and mean tables of both normalisers
-  return b + 64;
+struct MixLayout {
+  int tab_off, wv_off, ymin_off, ex_off, cx_off, bar_off, ctr_off, ring_off, total, nslots;
+};
+__host__ __device__ inline MixLayout mix_layout() {
+  MixLayout L;
+  int o = 0;
+  L.tab_off = o;   o += 4 * ROWB;                       // DDIM / normaliser tables TA1 | TB1 | TA2 | TB2, row layout
+  L.wv_off = o;    o += MIX_CONSUMERS * 96 * 4;         // per-warp Mixer weights of the current frame [4][24]
+  L.ymin_off = o;  o += 2 * MIX_CONSUMERS * 2 * 4;      // [sample parity][warp][person]
+  L.ex_off = o;    o += 2 * (int)sizeof(MixExport);     // [sample parity]
+  L.cx_off = o;    o += 2 * 2 * 8 * 4;                  // centring transforms [sample parity][person]
+  o = (o + 15) / 16 * 16;
+  L.bar_off = o;   o += (2 * MIX_MAX_SLOTS + 1) * 8;    // full[] | empty[] | mid
+  L.ctr_off = o;   o += 16 + MIX_MAX_SLOTS * 4;         // p1_done, claims[2], slot_lap[]
+  o = (o + 15) / 16 * 16;
+  L.ring_off = o;
+  int n = (MIX_SMEM_MAX - o) / ROWB;
+  n = n > MIX_MAX_SLOTS ? MIX_MAX_SLOTS : n;
+  L.nslots = n & ~1;                                    // two halves, one per producer warp
+  L.total = o + L.nslots * ROWB;
+  return L;
+}
+static_assert(sizeof(MixExport) % 16 == 0, "MixExport is laid out in 16-byte units");
+
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(MIX_CONSUMERS * 32) : "memory");
+}
+__device__ __forceinline__ float4 lds128g(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// cluster-scope mbarrier signalling (remote arrive / acquiring wait)
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 6000000000LL) {
+      printf("mmdm mixstep: cluster barrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+// Monotonic counters, plain volatile shared-memory words (a release store compiles to MEMBAR.ALL.CTA):
+//   slot_lap[s]: how often the producer has acquired slot s. An mbarrier parity wait is only meaningful within one
+//              phase of the barrier's current one and the consumers look further ahead than that, so a warp first
+//              waits until the producer has acquired the slot for its row - it has then seen the slot's previous
+//              use released, the slot's full barrier is in that row's phase - and only then on the barrier.
+//   p1_done  : samples whose phase 1 this CTA has finished (their g rows may be fetched).
+__device__ __forceinline__ void st_volatile_smem(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_smem(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until(const int* ctr, int want, const char* what) {
+  if (ld_volatile_smem(ctr) >= want) return;
+  const long long t0 = clock64();
+  while (ld_volatile_smem(ctr) < want) {
+    __nanosleep(32);
+    if (clock64() - t0 > 6000000000LL) {
+      printf("mmdm mixstep: stalled waiting for %s >= %d (block %d thread %d)\n", what, want, (int)blockIdx.x,
+             (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// mbarrier wait whose polling loop costs three instructions per round (the waiting warps share issue slots with the
+// working ones); the watchdog clock is only read every 4096 rounds
+__device__ __forceinline__ void mix_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((it & 4095u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 6000000000LL) {
+        printf("mmdm mixstep: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
+// ring position of row c of the CTA's row stream: groups of 32 rows alternate between the two producer warps, each
+// of which owns one half of the ring
+struct RowPos { int slot, lap, prod, group; };
+// (half_rcp = ceil(2^32 / half): exact quotient for the < 2^20 rows a CTA streams)
+__device__ __forceinline__ RowPos locate_row(int c, int half, uint32_t half_rcp) {
+  RowPos r;
+  const int g = c >> 5;
+  r.prod = g & 1;
+  r.group = g >> 1;
+  const int lc = r.group * 32 + (c & 31);
+  r.lap = (int)__umulhi((uint32_t)lc, half_rcp);
+  r.slot = r.prod * half + (lc - r.lap * half);
+  return r;
+}
+
+// Optional timeline of block 0 (tools/mix_trace.py): [warp][event][4] = tag, three clock64 stamps. Null in production.
+__device__ long long* g_mix_trace = nullptr;
+constexpr int MIX_TRACE_EVENTS = 512;
+__device__ __forceinline__ void mix_trace(long long* tr, int warp, int& n, long long tag, long long t0, long long t1,
+                                          long long t2) {
+  if (tr != nullptr && n < MIX_TRACE_EVENTS) {
+    long long* e = tr + ((size_t)warp * MIX_TRACE_EVENTS + n) * 4;
+    e[0] = tag; e[1] = t0; e[2] = t1; e[3] = t2;
+    ++n;
+  }
 }
 
 template <int NW>
@@ -127,213 +270,408 @@ __global__ void __launch_bounds__(MIX_THREADS, 1)
 mixstep_kernel(const MixStepParams P) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int b = blockIdx.x / MIX_CLUSTER;
+  const int cluster_id = blockIdx.x / MIX_CLUSTER, nclusters = gridDim.x / MIX_CLUSTER;
   const int T = P.T, B = P.B;
   const int FR = (T + MIX_CLUSTER - 1) / MIX_CLUSTER;
   const int t_begin = rank * FR;
   const int nfr = max(0, min(FR, T - t_begin));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool pooled = (P.mode == 1 || P.mode == 3);
+  const int ncfg = P.ncfg;
+  long long* const tr = (blockIdx.x == 0 && lane == 0) ? g_mix_trace : nullptr;
+  int ntr = 0;
 
   extern __shared__ __align__(16) uint8_t smem[];
-  float* cfg = reinterpret_cast<float*>(smem);
-  float* wwarp = cfg + (size_t)FR * 2 * NFEAT;               // [MIX_WARPS][4][24]
-  float* ymin_w = wwarp + MIX_WARPS * 4 * 24;                // [MIX_WARPS][2]
-  MixExport* ex = reinterpret_cast<MixExport*>(ymin_w + MIX_WARPS * 2);
-  float* tab = reinterpret_cast<float*>(ex + 1);             // [mean1 | rstd1 | mean2 | rstd2] x 262
+  const MixLayout L = mix_layout();
+  float* tab = reinterpret_cast<float*>(smem + L.tab_off);
+  float* ymin_w = reinterpret_cast<float*>(smem + L.ymin_off);
+  MixExport* ex = reinterpret_cast<MixExport*>(smem + L.ex_off);
+  float* cxs = reinterpret_cast<float*>(smem + L.cx_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty = full + MIX_MAX_SLOTS;
+  uint64_t* mid_bar = empty + MIX_MAX_SLOTS;
+  int* p1_done = reinterpret_cast<int*>(smem + L.ctr_off);
+  int* claims = p1_done + 1;      // frame tickets handed out so far, per phase
+  int* slot_lap = p1_done + 4;    // per slot: number of times the producer has acquired it
+  uint8_t* ring = smem + L.ring_off;
+  const int NS = L.nslots, half = NS / 2;
+  const uint32_t half_rcp = (uint32_t)((0x100000000ULL + half - 1) / half);
 
   const int step = P.mix_only ? 0 : *P.step_ptr;
   const bool final_step = (step == 0) && !P.mix_only;
-  if (!P.mix_only) {
-    for (int i = threadIdx.x; i < NFEAT; i += MIX_THREADS) {
-      tab[i] = P.mean1[i];
-      tab[NFEAT + i] = 1.0f / P.std1[i];
-      tab[2 * NFEAT + i] = P.mean2[i];
-      tab[3 * NFEAT + i] = 1.0f / P.std2[i];
+  const bool phase2 = !final_step && !P.mix_only;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
     }
+    mbar_init(mid_bar, MIX_CLUSTER);
+    for (int i = 0; i < NS; ++i) slot_lap[i] = 0;
+    *p1_done = 0;
+    claims[0] = 0;
+    claims[1] = 0;
+    fence_barrier_init();
   }
-  // row of the Mixer weights for (cfg half c, person p, frame t): sequence ((c*B + b)*2 + p), per token unless pooled
-  auto wrow = [&](int c, int p, int t) {
-    const size_t seq = (size_t)(c * B + b) * 2 + p;
-    return P.weights + (pooled ? seq : seq * T + t) * 24;
-  };
-  __syncthreads();
+  cluster_sync_all();   // every CTA's barriers exist before the first remote arrive
 
-  // ---- phase 1: head + mix + guidance for my frames ---------------------------------------------
-  // One warp per frame. All global loads of a stage are issued before the first one is consumed (the kernel is
-  // HBM-latency bound otherwise): 4 x 17 coalesced words per lane for the aligned predictions.
-  float ym0 = INFINITY, ym1 = INFINITY;
-  const float s_cfg = P.cfg_scale, s_unc = 1.f - P.cfg_scale;
-  const bool two = (P.ncfg == 2);
-  constexpr int NIT = (2 * NFEAT + 31) / 32;   // 17 words per lane per row
-  // A lane always handles the same 17 features of a row (f = lane + 32 i): which Mixer weight multiplies them,
-  // whether they are a joint height (floor search) and their per-person index are computed once, not per frame.
-  int meta[NIT];   // bits 0-5: person * 24 + weight index, bit 6: y coordinate of a joint position, bits 8-16: fi
-#pragma unroll
-  for (int i = 0; i < NIT; ++i) {
-    const int f = lane + 32 * i;
-    const int p = f >= NFEAT, fi = f - p * NFEAT;
-    const int wi = (NW == 1) ? 0 : weight_index(fi);
-    meta[i] = (p * 24 + wi) | ((fi < OFF_VEL && (fi % 3) == 1) ? 64 : 0) | (fi << 8);
-  }
-  for (int fl = warp; fl < nfr; fl += MIX_WARPS) {
-    const int t = t_begin + fl;
-    float* wv = wwarp + warp * 4 * 24;
-    if (lane < 24) {
-#pragma unroll
-      for (int cp = 0; cp < 4; ++cp)
-        if (cp < 2 * P.ncfg) wv[cp * 24 + lane] = (lane < NW) ? __ldg(wrow(cp >> 1, cp & 1, t) + lane) : 0.f;
-    }
-    __syncwarp();
-    if (P.has_force)
-      for (int i = lane; i < 4 * 24; i += 32) wv[i] = P.force_val;
-    __syncwarp();
-    const size_t rc = ((size_t)b * T + t) * (2 * NFEAT);            // cond half row
-    const size_t ru = ((size_t)(B + b) * T + t) * (2 * NFEAT);      // uncond half row
-    float* crow = cfg + (size_t)fl * 2 * NFEAT;
-    float o1c[NIT], o2c[NIT], o1u[NIT], o2u[NIT];
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int f = lane + 32 * i;
-      const bool ok = f < 2 * NFEAT;
-      o1c[i] = ok ? __ldg(P.out1a + rc + f) : 0.f;
-      o2c[i] = ok ? __ldg(P.out2a + rc + f) : 0.f;
-      o1u[i] = (ok && two) ? __ldg(P.out1a + ru + f) : 0.f;
-      o2u[i] = (ok && two) ? __ldg(P.out2a + ru + f) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int f = lane + 32 * i;
-      if (f < 2 * NFEAT) {
-        const int p = f >= NFEAT, fi = meta[i] >> 8;
-        const float wc = wv[meta[i] & 63];
-        const float wu = two ? wv[48 + (meta[i] & 63)] : 0.f;
-        const float mc = o2c[i] + wc * (o1c[i] - o2c[i]);
-        const float mu = two ? o2u[i] + wu * (o1u[i] - o2u[i]) : 0.f;
-        if (P.mix_only == 1 || (P.mix_only == 0 && P.mix_out != nullptr)) {   // out_influenced ("eval" history)
-          P.mix_out[rc + f] = mc;
-          if (two) P.mix_out[ru + f] = mu;
+  // Row stream of this CTA. S samples; r1 rows per sample in phase 1 (per frame: out1a, out2a of each cfg half),
+  // r2 in phase 2 (per frame: x1, x2, g). Order: P1(0), then for k = 1..S: [P1(k) if k < S], P2(k-1).
+  const int S = cluster_id < B ? (B - cluster_id + nclusters - 1) / nclusters : 0;
+  const int R1 = 2 * ncfg, R2 = 3;
+  const int r1 = nfr * R1, r2 = phase2 ? nfr * R2 : 0;
+  const int total_rows = S * (r1 + r2);
+  auto base_p1 = [&](int k) { return k * r1 + (k > 0 ? k - 1 : 0) * r2; };
+  auto base_p2 = [&](int k) { return min(k + 1, S) * r1 + (k - 1) * r2; };   // P2(k-1), issued in stage k
+
+  if (warp >= MIX_CONSUMERS) {
+    // ---- producer warps: one row per lane, 32 rows per group, groups alternate between the two warps --------
+    const int pw = warp - MIX_CONSUMERS;
+    uint64_t pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    for (int g = pw; g * 32 < total_rows; g += MIX_PRODUCERS) {
+      const int c = g * 32 + lane;
+      const bool valid = c < total_rows;
+      const long long tp0 = tr ? clock64() : 0;
+      const float* src = nullptr;
+      int need_p1 = 0;   // > 0: the row is g of sample need_p1 - 1, written by this CTA's consumers in that sample's phase 1
+      RowPos rp = {0, 0, 0, 0};
+      if (valid) {
+        // decode c -> (sample, phase, frame, row of the frame)
+        int n, idx;
+        bool p1;
+        if (c < r1) {
+          n = 0; idx = c; p1 = true;
+        } else {
+          const int cp = c - r1, k = 1 + cp / (r1 + r2), rem = cp - (k - 1) * (r1 + r2);
+          if (k < S && rem < r1) { n = k; idx = rem; p1 = true; }
+          else { n = k - 1; idx = k < S ? rem - r1 : rem; p1 = false; }
         }
-        if (P.hist_i1 != nullptr) {
-          float* hbase = (p ? P.hist_i2 : P.hist_i1) +
-                         (size_t)(P.mix_only ? 0 : (P.nsteps - 1 - step)) * ((size_t)P.ncfg * B * T * NFEAT);
-          hbase[((size_t)b * T + t) * NFEAT + fi] = wc;
-          if (two) hbase[((size_t)(B + b) * T + t) * NFEAT + fi] = wu;
+        const int b = cluster_id + n * nclusters;
+        if (p1) {
+          const int fl = idx / R1, r = idx - fl * R1;
+          src = ((r & 1) ? P.out2a : P.out1a) + ((size_t)((r >> 1) * B + b) * T + t_begin + fl) * ROWF;
+        } else {
+          const int fl = idx / R2, r = idx - fl * R2;
+          src = (r == 0 ? P.x1 : r == 1 ? P.x2 : P.final_out) + ((size_t)b * T + t_begin + fl) * ROWF;
+          if (r == 2) need_p1 = n + 1;
         }
-        if (P.mix_only != 1) {
-          const float g = s_cfg * mc + s_unc * mu;
-          if (P.mix_only == 2) {
-            P.mix_out[rc + f] = g;
-          } else {
-            crow[f] = g;
-            if (meta[i] & 64) {
-              if (p) ym1 = fminf(ym1, g); else ym0 = fminf(ym0, g);
+        // every lane runs its own slot: wait until it is free, arm its barrier, tell the consumers, copy
+        rp = locate_row(c, half, half_rcp);
+        if (rp.lap > 0) mix_wait(&empty[rp.slot], (uint32_t)(rp.lap - 1) & 1u);
+        mbar_arrive_expect_tx(&full[rp.slot], ROWB);
+        st_volatile_smem(slot_lap + rp.slot, rp.lap + 1);
+        if (need_p1 > 0) {
+          spin_until(p1_done, need_p1, "p1_done");
+          fence_proxy_async_all();
+        }
+        bulk_g2s_hint(smem_u32(ring + (size_t)rp.slot * ROWB), src, ROWB, smem_u32(&full[rp.slot]), pol_stream);
+      }
+      const long long tp1 = tr ? clock64() : 0;
+      __syncwarp();
+      mix_trace(tr, warp, ntr, (3LL << 32) | g, tp0, tp1, tr ? clock64() : 0);
+    }
+  } else {
+    // ---- consumer warps --------------------------------------------------------------------------
+    // Frames are handed out dynamically (one shared-memory ticket counter per phase) so that the ring is consumed
+    // in the order it is filled - a warp held up by the cluster exchange or a late row does not sit on slots the
+    // others are waiting behind. Every warp holds the ticket of its NEXT frame while it works on the current one:
+    // the Mixer weights of that frame are fetched a whole frame ahead.
+    const bool two = (ncfg == 2);
+    const f32x2 s_cfg2 = pack2(P.cfg_scale, P.cfg_scale), s_unc2 = pack2(1.f - P.cfg_scale, 1.f - P.cfg_scale);
+    const f32x2 neg1 = pack2(-1.f, -1.f);
+    float* wv = reinterpret_cast<float*>(smem + L.wv_off) + warp * 96;
+    // A lane always handles the same 20 features of a row (float4 j = lane + 32 i): the byte offset of the Mixer
+    // weight that multiplies each of them and whether it is a joint height (floor search) are computed once.
+    // Heights only occur in j < 17 (person 0, i = 0) and 65 < j < 82 (person 1, i = 2).
+    int woff[NIT4 * 4];
+    uint32_t yflags = 0;   // bit e: element e of iteration 0, bit 4 + e: element e of iteration 2
+#pragma unroll
+    for (int i = 0; i < NIT4 * 4; ++i) {
+      const int f = (lane + 32 * (i >> 2)) * 4 + (i & 3);
+      const int p = f >= NFEAT, fi = f - p * NFEAT;
+      const int wi = (NW == 1) ? 0 : weight_index(fi);
+      woff[i] = (p * 24 + wi) * 4;
+      if (fi < OFF_VEL && (fi % 3) == 1 && f < ROWF) {
+        if ((i >> 2) == 0) yflags |= 1u << (i & 3);
+        if ((i >> 2) == 2) yflags |= 1u << (4 + (i & 3));
+      }
+    }
+    // Mixer weights of frame t for (cfg half, person) = 4 rows of 24: three values per lane
+    auto load_w = [&](int b, int t, float* w3) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int idx = lane + 32 * k, cp = idx / 24, kk = idx - cp * 24;
+        const size_t seq = (size_t)((cp >> 1) * B + b) * 2 + (cp & 1);
+        float v = 0.f;
+        if (P.has_force) v = P.force_val;
+        else if (cp < 2 * ncfg && kk < NW) v = __ldg(P.weights + (pooled ? seq : seq * T + t) * 24 + kk);
+        w3[k] = v;
+      }
+    };
+    // wait for row c of the stream; returns its slot
+    auto acquire_row = [&](int c) -> const float* {
+      const RowPos rp = locate_row(c, half, half_rcp);
+      if (lane == 0) spin_until(slot_lap + rp.slot, rp.lap + 1, "slot_lap");
+      __syncwarp();
+      mix_wait(&full[rp.slot], (uint32_t)rp.lap & 1u);
+      return reinterpret_cast<const float*>(ring + (size_t)rp.slot * ROWB);
+    };
+    auto release_row = [&](int c) {   // lane 0 only
+      const RowPos rp = locate_row(c, half, half_rcp);
+      mbar_arrive(&empty[rp.slot]);
+    };
+    auto claim = [&](int which) -> int {   // next ticket of phase `which`: frame q % nfr of sample q / nfr
+      int q = 0;
+      if (lane == 0) q = atomicAdd(claims + which, 1);
+      return __shfl_sync(0xffffffffu, q, 0);
+    };
+    // DDIM update with the normalisation folded in: x' = A pred + Bc x, pred = (g - mean) / std
+    //   (gaussian_diffusion.py:1936-1965 with eta = 0: x' = pred sqrt(ab_prev) + sqrt(1 - ab_prev) eps,
+    //    eps = (sqrt(1/ab) x - pred) / sqrt(1/ab - 1))  ->  x' = TA g + TB + Bc x with per-feature tables TA, TB
+    f32x2 bc2 = pack2(0.f, 0.f);
+    if (phase2) {
+      const double c_recip = P.coef[step * 4 + 0], c_recipm1 = P.coef[step * 4 + 1];
+      const double c_ap = P.coef[step * 4 + 2], c_eps = P.coef[step * 4 + 3];
+      const float A = (float)(c_ap - c_eps / c_recipm1), Bc = (float)(c_eps / c_recipm1 * c_recip);
+      bc2 = pack2(Bc, Bc);
+      for (int i = threadIdx.x; i < ROWF; i += MIX_CONSUMERS * 32) {
+        const int fi = i >= NFEAT ? i - NFEAT : i;
+        const float r1s = 1.0f / P.std1[fi], r2s = 1.0f / P.std2[fi];
+        tab[i] = A * r1s;                              // TA, stream 1 (individual-model normaliser)
+        tab[ROWF + i] = -A * P.mean1[fi] * r1s;        // TB
+        tab[2 * ROWF + i] = A * r2s;                   // TA, stream 2 (interaction-model normaliser)
+        tab[3 * ROWF + i] = -A * P.mean2[fi] * r2s;    // TB
+      }
+      consumer_sync();
+    }
+    const int tickets = S * nfr;
+    int next1 = nfr > 0 ? claim(0) : tickets, next2 = (nfr > 0 && phase2) ? claim(1) : tickets;
+    float w3[3] = {0.f, 0.f, 0.f};
+    if (next1 < tickets) load_w(cluster_id + (next1 / nfr) * nclusters, t_begin + next1 % nfr, w3);
+
+    for (int k = 0; k <= S; ++k) {
+      if (k < S) {
+        // ---- phase 1 of sample k: mix + guidance for my frames -------------------------------------
+        const int b = cluster_id + k * nclusters;
+        const int cb = base_p1(k);
+        float ym0 = INFINITY, ym1 = INFINITY;
+        while (next1 < (k + 1) * nfr) {
+          const int fl = next1 - k * nfr;
+          const int t = t_begin + fl;
+          __syncwarp();   // the previous frame's readers of wv are done
+#pragma unroll
+          for (int q = 0; q < 3; ++q) wv[lane + 32 * q] = w3[q];
+          next1 = claim(0);
+          if (next1 < tickets) load_w(cluster_id + (next1 / nfr) * nclusters, t_begin + next1 % nfr, w3);
+          const int c0 = cb + fl * R1;
+          const long long tc0 = tr ? clock64() : 0;
+          const float* o1c = acquire_row(c0);       // (the __syncwarp inside also orders the wv stores)
+          const float* o2c = acquire_row(c0 + 1);
+          const float* o1u = two ? acquire_row(c0 + 2) : o1c;
+          const float* o2u = two ? acquire_row(c0 + 3) : o2c;
+          const size_t rc = ((size_t)b * T + t) * ROWF;            // cond half row
+          const size_t ru = ((size_t)(B + b) * T + t) * ROWF;      // uncond half row
+          const uint32_t wva = smem_u32(wv);
+          const long long tc1 = tr ? clock64() : 0;
+#pragma unroll
+          for (int i = 0; i < NIT4; ++i) {
+            const int j = lane + 32 * i;
+            if (j < ROW4) {
+              const float4 a4 = lds128g(o1c + 4 * j), b4 = lds128g(o2c + 4 * j);
+              float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = c4;
+              if (two) { c4 = lds128g(o1u + 4 * j); d4 = lds128g(o2u + 4 * j); }
+              float g[4], mcv[4], muv[4], wcv[4], wuv[4];
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {   // two features per packed fp32x2 instruction
+                const int e = 2 * h2;
+                wcv[e] = __uint_as_float(lds32(wva + woff[i * 4 + e]));
+                wcv[e + 1] = __uint_as_float(lds32(wva + woff[i * 4 + e + 1]));
+                const f32x2 av = h2 ? pack2(a4.z, a4.w) : pack2(a4.x, a4.y);
+                const f32x2 bv = h2 ? pack2(b4.z, b4.w) : pack2(b4.x, b4.y);
+                const f32x2 mc = fma2(pack2(wcv[e], wcv[e + 1]), fma2(bv, neg1, av), bv);   // b + w (a - b)
+                f32x2 gg = mul2(s_cfg2, mc);
+                unpack2(mc, mcv[e], mcv[e + 1]);
+                muv[e] = muv[e + 1] = wuv[e] = wuv[e + 1] = 0.f;
+                if (two) {
+                  wuv[e] = __uint_as_float(lds32(wva + 192 + woff[i * 4 + e]));
+                  wuv[e + 1] = __uint_as_float(lds32(wva + 192 + woff[i * 4 + e + 1]));
+                  const f32x2 cv = h2 ? pack2(c4.z, c4.w) : pack2(c4.x, c4.y);
+                  const f32x2 dv = h2 ? pack2(d4.z, d4.w) : pack2(d4.x, d4.y);
+                  const f32x2 mu = fma2(pack2(wuv[e], wuv[e + 1]), fma2(dv, neg1, cv), dv);
+                  gg = fma2(s_unc2, mu, gg);
+                  unpack2(mu, muv[e], muv[e + 1]);
+                }
+                unpack2(gg, g[e], g[e + 1]);
+              }
+              if (i == 0 || i == 2) {   // joint heights of person 0 / person 1
+                const uint32_t yf = i == 0 ? yflags : yflags >> 4;
+                float& ym = i == 0 ? ym0 : ym1;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (yf & (1u << e)) ym = fminf(ym, g[e]);
+              }
+              if (P.hist_i1 != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int f = 4 * j + e, p = f >= NFEAT, fi = f - p * NFEAT;
+                  float* hbase = (p ? P.hist_i2 : P.hist_i1) +
+                                 (size_t)(P.mix_only ? 0 : (P.nsteps - 1 - step)) * ((size_t)ncfg * B * T * NFEAT);
+                  hbase[((size_t)b * T + t) * NFEAT + fi] = wcv[e];
+                  if (two) hbase[((size_t)(B + b) * T + t) * NFEAT + fi] = wuv[e];
+                }
+              }
+              if (P.mix_only == 1 || (P.mix_only == 0 && P.mix_out != nullptr)) {   // out_influenced ("eval" history)
+                *reinterpret_cast<float4*>(P.mix_out + rc + 4 * j) = make_float4(mcv[0], mcv[1], mcv[2], mcv[3]);
+                if (two) *reinterpret_cast<float4*>(P.mix_out + ru + 4 * j) = make_float4(muv[0], muv[1], muv[2], muv[3]);
+              }
+              if (P.mix_only != 1) {
+                // the guided prediction: Mixer.forward's CFG output, the sampler's result at the last step (rows of
+                // the un-doubled batch coincide with the cond half), phase 2's input at every other step
+                float* gdst = (P.mix_only == 2 ? P.mix_out : P.final_out) + rc;
+                *reinterpret_cast<float4*>(gdst + 4 * j) = make_float4(g[0], g[1], g[2], g[3]);
+              }
             }
-            if (final_step) P.final_out[rc + f] = g;   // rows of the un-doubled batch coincide with the cond half
+          }
+          __syncwarp();
+          if (lane == 0) {
+            for (int r = 0; r < R1; ++r) release_row(c0 + r);
+          }
+          mix_trace(tr, warp, ntr, (1LL << 32) | (k * nfr + fl), tc0, tc1, tr ? clock64() : 0);
+        }
+        if (phase2) {
+          ym0 = warp_min(ym0);
+          ym1 = warp_min(ym1);
+          float* yw = ymin_w + (k & 1) * (MIX_CONSUMERS * 2);
+          if (lane == 0) { yw[warp * 2] = ym0; yw[warp * 2 + 1] = ym1; }
+          fence_proxy_async_all();   // my g stores are ordered before the producers' bulk reads of them
+          const long long ts0 = tr ? clock64() : 0;
+          consumer_sync();
+          mix_trace(tr, warp, ntr, (4LL << 32) | k, ts0, tr ? clock64() : 0, 0);
+          if (warp == 0) {
+            MixExport* exk = ex + (k & 1);
+            if (lane < 2) {
+              float m = INFINITY;
+              for (int w = 0; w < MIX_CONSUMERS; ++w) m = fminf(m, yw[w * 2 + lane]);
+              exk->ymin[lane] = m;
+            }
+            if (rank == 0 && lane < 18) {   // frame 0 of the sample is mine: joints 0, 1, 2 of both persons
+              const int p = lane / 9, e = lane - p * 9;
+              exk->f0[p][e] = __ldcg(P.final_out + (size_t)b * T * ROWF + p * NFEAT + e);
+            }
+            if (lane == 0) st_volatile_smem(p1_done, k + 1);
+            __syncwarp();
+            if (lane < MIX_CLUSTER) mbar_arrive_remote_release(mapa_u32(smem_u32(mid_bar), (uint32_t)lane));
+            mbar_wait_cluster(mid_bar, (uint32_t)k & 1u);
+            if (lane < 2) {
+              const int p = lane;
+              const MixExport* e0 = cluster.map_shared_rank(exk, 0);
+              float m = INFINITY;
+              for (int r = 0; r < MIX_CLUSTER; ++r) m = fminf(m, cluster.map_shared_rank(exk, r)->ymin[p]);
+              const float* f0 = e0->f0[p];
+              // FACE_JOINT_INDX[:2] = (r_hip=2, l_hip=1)  (utils/paramUtil.py:89)
+              const CenterXf c = make_center(v3(f0[0], f0[1] - m, f0[2]), v3(f0[6], f0[7], f0[8]), v3(f0[3], f0[4], f0[5]), m);
+              float* o = cxs + ((k & 1) * 2 + p) * 8;
+              o[0] = c.q.w; o[1] = c.q.x; o[2] = c.q.y; o[3] = c.q.z; o[4] = c.floor_y; o[5] = c.sx; o[6] = c.sz;
+            }
+            __syncwarp();
           }
         }
       }
-    }
-    __syncwarp();
-  }
-  if (final_step || P.mix_only) {   // t == 0: nothing is centred or normalised, the guided prediction is the result
-    cluster.sync();
-    return;
-  }
-  ym0 = warp_min(ym0);
-  ym1 = warp_min(ym1);
-  if (lane == 0) { ymin_w[warp * 2] = ym0; ymin_w[warp * 2 + 1] = ym1; }
-  __syncthreads();
-  if (threadIdx.x < 2) {
-    float m = INFINITY;
-    for (int w = 0; w < MIX_WARPS; ++w) m = fminf(m, ymin_w[w * 2 + threadIdx.x]);
-    ex->ymin[threadIdx.x] = m;
-  }
-  if (rank == 0 && threadIdx.x < 18) {
-    const int p = threadIdx.x / 9, e = threadIdx.x % 9;
-    ex->f0[p][e] = cfg[p * NFEAT + e];
-  }
-  cluster.sync();
-  CenterXf cx[2];
-  {
-    const MixExport* e0 = cluster.map_shared_rank(ex, 0);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      float m = INFINITY;
-      for (int r = 0; r < MIX_CLUSTER; ++r) m = fminf(m, cluster.map_shared_rank(ex, r)->ymin[p]);
-      const float* f0 = e0->f0[p];
-      // FACE_JOINT_INDX[:2] = (r_hip=2, l_hip=1)  (utils/paramUtil.py:89)
-      cx[p] = make_center(v3(f0[0], f0[1] - m, f0[2]), v3(f0[6], f0[7], f0[8]), v3(f0[3], f0[4], f0[5]), m);
-    }
-  }
-
-  // ---- phase 2: process_xstart + DDIM on both state streams -----------------------------------------
-  const float c_recip = P.coef[step * 4 + 0], c_inv_recipm1 = 1.0f / P.coef[step * 4 + 1];
-  const float c_ap = P.coef[step * 4 + 2], c_eps = P.coef[step * 4 + 3];
-  for (int fl = warp; fl < nfr; fl += MIX_WARPS) {
-    const int t = t_begin + fl;
-    float* crow = cfg + (size_t)fl * 2 * NFEAT;
-    const size_t rx = ((size_t)b * T + t) * (2 * NFEAT);
-    // both state rows are requested up front; they arrive while the centring / rotation math below runs
-    float xs1[NIT], xs2[NIT];
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int f = lane + 32 * i;
-      const bool ok = f < 2 * NFEAT;
-      xs2[i] = ok ? P.x2[rx + f] : 0.f;
-      xs1[i] = ok ? P.x1[rx + f] : 0.f;
-    }
-    // stream 2 (interaction space): normalise the raw guided prediction
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int f = lane + 32 * i;
-      if (f < 2 * NFEAT) {
-        const int fi = meta[i] >> 8;
-        const float pred = (crow[f] - tab[2 * NFEAT + fi]) * tab[3 * NFEAT + fi];
-        const float eps = (c_recip * xs2[i] - pred) * c_inv_recipm1;
-        P.x2[rx + f] = pred * c_ap + c_eps * eps;
-      }
-    }
-    __syncwarp();
-    // stream 1 (individual space): ih_to_smpl -> center_motion -> smpl_to_ih per person, then normalise
-    if (P.center) {
-      if (lane < NJ) {
+      if (k >= 1 && phase2) {
+        // ---- phase 2 of sample k-1: process_xstart + DDIM on both state streams ----------------------
+        const int n = k - 1;
+        const int b = cluster_id + n * nclusters;
+        const int cb = base_p2(k);
+        const long long ts1 = tr ? clock64() : 0;
+        consumer_sync();   // warp 0 has published the sample's centring transforms
+        mix_trace(tr, warp, ntr, (5LL << 32) | n, ts1, tr ? clock64() : 0, 0);
+        CenterXf cx[2];
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-          float* pp = crow + p * NFEAT + lane * 3;
-          const V3 q = center_pos(cx[p], v3(pp[0], pp[1], pp[2]));
-          pp[0] = q.x; pp[1] = q.y; pp[2] = q.z;
-          float* vp = crow + p * NFEAT + OFF_VEL + lane * 3;
-          const V3 v = qrot(cx[p].q, v3(vp[0], vp[1], vp[2]));
-          vp[0] = v.x; vp[1] = v.y; vp[2] = v.z;
+          const float* o = cxs + ((n & 1) * 2 + p) * 8;
+          cx[p].q.w = o[0]; cx[p].q.x = o[1]; cx[p].q.y = o[2]; cx[p].q.z = o[3];
+          cx[p].floor_y = o[4]; cx[p].sx = o[5]; cx[p].sz = o[6];
         }
-      }
-      for (int idx = lane; idx < 2 * NROT; idx += 32) {
-        const int p = idx / NROT, j = idx - p * NROT;
-        float* rp = crow + p * NFEAT + OFF_ROT + j * 6;
-        float o[6];
-        rot6d_roundtrip(rp, o);
+        while (next2 < (n + 1) * nfr) {
+          const int fl = next2 - n * nfr;
+          next2 = claim(1);
+          const int t = t_begin + fl;
+          const int c0 = cb + fl * R2;
+          const size_t rx = ((size_t)b * T + t) * ROWF;
+          const long long tc0 = tr ? clock64() : 0;
+          const float* xr1 = acquire_row(c0);
+          const float* xr2 = acquire_row(c0 + 1);
+          float* crow = const_cast<float*>(acquire_row(c0 + 2));
+          const long long tc1 = tr ? clock64() : 0;
+          // stream 2 (interaction space): the raw guided prediction, normalised inside the tables
 #pragma unroll
-        for (int e = 0; e < 6; ++e) rp[e] = o[e];
-      }
-      if (lane < 8) crow[(lane >> 2) * NFEAT + OFF_FC + (lane & 3)] = 0.f;
-      __syncwarp();
-    }
+          for (int i = 0; i < NIT4; ++i) {
+            const int j = lane + 32 * i;
+            if (j < ROW4) {
+              const float4 x4 = lds128g(xr2 + 4 * j), g4 = lds128g(crow + 4 * j);
+              const float4 ta = lds128g(tab + 2 * ROWF + 4 * j), tb = lds128g(tab + 3 * ROWF + 4 * j);
+              float o[4];
+              unpack2(fma2(pack2(ta.x, ta.y), pack2(g4.x, g4.y), fma2(bc2, pack2(x4.x, x4.y), pack2(tb.x, tb.y))), o[0], o[1]);
+              unpack2(fma2(pack2(ta.z, ta.w), pack2(g4.z, g4.w), fma2(bc2, pack2(x4.z, x4.w), pack2(tb.z, tb.w))), o[2], o[3]);
+              *reinterpret_cast<float4*>(P.x2 + rx + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          __syncwarp();
+          // stream 1 (individual space): ih_to_smpl -> center_motion -> smpl_to_ih per person, then normalise
+          if (P.center) {
+            if (lane < NJ) {
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int f = lane + 32 * i;
-      if (f < 2 * NFEAT) {
-        const int fi = meta[i] >> 8;
-        const float pred = (crow[f] - tab[fi]) * tab[NFEAT + fi];
-        const float eps = (c_recip * xs1[i] - pred) * c_inv_recipm1;
-        P.x1[rx + f] = pred * c_ap + c_eps * eps;
+              for (int p = 0; p < 2; ++p) {
+                float* pp = crow + p * NFEAT + lane * 3;
+                const V3 q = center_pos(cx[p], v3(pp[0], pp[1], pp[2]));
+                pp[0] = q.x; pp[1] = q.y; pp[2] = q.z;
+                float* vp = crow + p * NFEAT + OFF_VEL + lane * 3;
+                const V3 v = qrot(cx[p].q, v3(vp[0], vp[1], vp[2]));
+                vp[0] = v.x; vp[1] = v.y; vp[2] = v.z;
+              }
+            }
+            for (int idx = lane; idx < 2 * NROT; idx += 32) {
+              const int p = idx / NROT, j = idx - p * NROT;
+              float* rp = crow + p * NFEAT + OFF_ROT + j * 6;
+              float o[6];
+              rot6d_roundtrip(rp, o);
+#pragma unroll
+              for (int e = 0; e < 6; ++e) rp[e] = o[e];
+            }
+            if (lane < 8) crow[(lane >> 2) * NFEAT + OFF_FC + (lane & 3)] = 0.f;
+            __syncwarp();
+          }
+#pragma unroll
+          for (int i = 0; i < NIT4; ++i) {
+            const int j = lane + 32 * i;
+            if (j < ROW4) {
+              const float4 x4 = lds128g(xr1 + 4 * j), g4 = lds128g(crow + 4 * j);
+              const float4 ta = lds128g(tab + 4 * j), tb = lds128g(tab + ROWF + 4 * j);
+              float o[4];
+              unpack2(fma2(pack2(ta.x, ta.y), pack2(g4.x, g4.y), fma2(bc2, pack2(x4.x, x4.y), pack2(tb.x, tb.y))), o[0], o[1]);
+              unpack2(fma2(pack2(ta.z, ta.w), pack2(g4.z, g4.w), fma2(bc2, pack2(x4.z, x4.w), pack2(tb.z, tb.w))), o[2], o[3]);
+              *reinterpret_cast<float4*>(P.x1 + rx + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          fence_proxy_async_smem();   // the centring wrote into the slot: order it before the next bulk copy into it
+          __syncwarp();
+          if (lane == 0) {
+            for (int r = 0; r < R2; ++r) release_row(c0 + r);
+          }
+          mix_trace(tr, warp, ntr, (2LL << 32) | (n * nfr + fl), tc0, tc1, tr ? clock64() : 0);
+        }
       }
     }
   }
-  cluster.sync();   // keep my shared memory alive until every CTA of the cluster has read the exports
+  cluster_sync_all();   // no CTA retires while another one may still read its exports or signal its barriers
 }
 
-constexpr int MIX_SMEM_MAX = 227 * 1024;
+static int g_mix_clusters[2] = {0, 0};   // resident clusters per instantiation (0 = not queried yet)
+
+extern "C" int mmdm_debug_mix_trace(long long* dev_ptr) {
+  return cudaMemcpyToSymbol(g_mix_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -2;
+}
+
 int motion_init() {
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(mixstep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX));
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(mixstep_kernel<23>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX));
@@ -344,16 +682,19 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
   static int inited = motion_init();
   MMDM_REQUIRE(inited == 0, "mixstep: kernel attribute setup failed");
   MMDM_REQUIRE(P.mode >= 1 && P.mode <= 4, "Mixing mode not recognized (%d)", P.mode);
-  MMDM_REQUIRE(P.T >= 1 && P.T <= 320 && P.B >= 1, "mixstep: bad shape B=%d T=%d", P.B, P.T);
+  MMDM_REQUIRE(P.T >= 1 && P.B >= 1 && (long long)P.B * P.T * 12 < (1LL << 31), "mixstep: bad shape B=%d T=%d", P.B, P.T);
+  MMDM_REQUIRE(P.ncfg == 1 || P.ncfg == 2, "mixstep: ncfg must be 1 or 2 (got %d)", P.ncfg);
   MMDM_REQUIRE(P.weights != nullptr, "mixstep: Mixer weights missing");
+  MMDM_REQUIRE(((reinterpret_cast<uintptr_t>(P.out1a) | reinterpret_cast<uintptr_t>(P.out2a) |
+                 reinterpret_cast<uintptr_t>(P.weights) | reinterpret_cast<uintptr_t>(P.x1) |
+                 reinterpret_cast<uintptr_t>(P.x2) | reinterpret_cast<uintptr_t>(P.mix_out) |
+                 reinterpret_cast<uintptr_t>(P.final_out)) & 15) == 0,
+               "mixstep: buffers must be 16-byte aligned");
   const int NW = (P.mode <= 2) ? 1 : 23;
-  const int FR = (P.T + MIX_CLUSTER - 1) / MIX_CLUSTER;
-  const size_t smem = mix_smem_bytes(FR);
-  MMDM_REQUIRE(smem <= (size_t)MIX_SMEM_MAX, "mixstep: shared memory budget exceeded (%zu)", smem);
+  const MixLayout L = mix_layout();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(P.B * MIX_CLUSTER));
   cfg.blockDim = dim3(MIX_THREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = (size_t)L.total;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -362,6 +703,19 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  int& resident = g_mix_clusters[NW == 1 ? 0 : 1];
+  if (resident == 0) {   // how many clusters the device holds at once (the kernel is persistent over the samples)
+    cfg.gridDim = dim3((unsigned)(MIX_CLUSTER * 64));
+    cfg.dynamicSmemBytes = MIX_SMEM_MAX;
+    int n = 0;
+    cudaError_t e = NW == 1 ? cudaOccupancyMaxActiveClusters(&n, mixstep_kernel<1>, &cfg)
+                            : cudaOccupancyMaxActiveClusters(&n, mixstep_kernel<23>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    resident = n > 0 ? n : -1;
+    cfg.dynamicSmemBytes = (size_t)L.total;
+  }
+  const int nclusters = resident > 0 && resident < P.B ? resident : P.B;
+  cfg.gridDim = dim3((unsigned)(nclusters * MIX_CLUSTER));
   if (NW == 1) MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<1>, P));
   else MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<23>, P));
   return 0;

@@ -26,7 +26,8 @@ struct MixStepParams {
   const float* out2a;
   float* x1;                         // (B,T,524) state, individual space (updated in place)
   float* x2;                         // (B,T,524) state, interaction space
-  float* final_out;                  // (B,T,524) written at the last step (step index 0)
+  float* final_out;                  // (B,T,524) guided prediction: the result at step index 0, otherwise the
+                                     // kernel's phase-1 -> phase-2 hand-over buffer (stays in L2)
   const float* mean1; const float* std1;   // individual-model normaliser (HumanML3D stats)
   const float* mean2; const float* std2;   // interaction-model normaliser (InterHuman stats)
   float* hist_i1;                    // optional (nsteps, 2B, T, 262) expanded weights, or null

@@ -16,15 +16,16 @@ namespace mmdm {
 // bf16 write per element) instead of stalling on a load -> reduce -> load(modulation) -> store chain per row.
 template <int NV, bool DUAL>
 __global__ void __launch_bounds__(128)
-ln_modulate_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq, int run_len,
+ln_modulate_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq, int run_len, int rev,
                    const float* __restrict__ mod0, int ld_mod0, __nv_bfloat16* __restrict__ out0,
                    const float* __restrict__ mod1, int ld_mod1, __nv_bfloat16* __restrict__ out1) {
   constexpr int D = NV * 128;
   constexpr int NM = DUAL ? 2 : 1;
   extern __shared__ float4 ln_smem[];   // [4 warps][NM][scale+1 | shift][D/4]
-  const int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (task >= S * runs_per_seq) return;
+  if (rev) task = S * runs_per_seq - 1 - task;   // last rows first: they are the ones the producer left in L2
   const int s = task / runs_per_seq;
   const int t0 = (task - s * runs_per_seq) * run_len;
   const int t1 = min(T, t0 + run_len);
@@ -93,7 +94,7 @@ ln_modulate_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq, 
 
 template <int NV>
 static void launch_ln_t(const float* h, int S, int T, const float* mod0, int ld_mod0, __nv_bfloat16* out0,
-                        const float* mod1, int ld_mod1, __nv_bfloat16* out1, cudaStream_t stream) {
+                        const float* mod1, int ld_mod1, __nv_bfloat16* out1, int rev, cudaStream_t stream) {
   // runs of ~24 rows: long enough to amortise the modulation vectors, short enough to fill the SMs (S*T/24 warps)
   const int runs = (T + 23) / 24;
   const int run_len = (T + runs - 1) / runs;
@@ -106,23 +107,23 @@ static void launch_ln_t(const float* h, int S, int T, const float* mod0, int ld_
     attr_done = true;
   }
   if (out1 != nullptr)
-    ln_modulate_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, mod0, ld_mod0, out0, mod1, ld_mod1, out1);
+    ln_modulate_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, rev, mod0, ld_mod0, out0, mod1, ld_mod1, out1);
   else
-    ln_modulate_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, mod0, ld_mod0, out0, nullptr, 0, nullptr);
+    ln_modulate_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, rev, mod0, ld_mod0, out0, nullptr, 0, nullptr);
 }
 
 int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, int ld_mod0,
                        __nv_bfloat16* out0, const float* mod1, int ld_mod1, __nv_bfloat16* out1,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int rev) {
   MMDM_REQUIRE(D == 128 || D == 256 || D == 512 || D == 1024, "ln_modulate: unsupported latent dim %d", D);
   MMDM_REQUIRE((ld_mod0 % 4) == 0 && (out1 == nullptr || (ld_mod1 % 4) == 0), "ln_modulate: mod pitch %% 4");
   MMDM_REQUIRE(T > 0 && M % T == 0, "ln_modulate: M=%d is not a whole number of T=%d row sequences", M, T);
   const int S = M / T;
   switch (D) {
-    case 128: launch_ln_t<1>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
-    case 256: launch_ln_t<2>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
-    case 512: launch_ln_t<4>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
-    default: launch_ln_t<8>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, stream); break;
+    case 128: launch_ln_t<1>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, rev, stream); break;
+    case 256: launch_ln_t<2>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, rev, stream); break;
+    case 512: launch_ln_t<4>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, rev, stream); break;
+    default: launch_ln_t<8>(h, S, T, mod0, ld_mod0, out0, mod1, ld_mod1, out1, rev, stream); break;
   }
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -4,9 +4,10 @@
 namespace mmdm {
 
 // out0 = bf16(LN(h) * (1 + mod0[s, 0:D]) + mod0[s, D:2D]), s = row / T; optional second modulation.
+// rev != 0: rows are visited from the last one down (L2 reuse of the producer's tail, see GemmEpi::rev).
 int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, int ld_mod0,
                        __nv_bfloat16* out0, const float* mod1, int ld_mod1, __nv_bfloat16* out1,
-                       cudaStream_t stream);
+                       cudaStream_t stream, int rev = 0);
 
 // E[s,:] = bf16(SiLU(temb[trow,:] + text[text_row[s],:]))
 // trow = step_ptr ? *step_ptr : temb_idx[s]

@@ -182,14 +182,19 @@ def test_align_kernel_vs_oracle():
     assert relerr(ei[:, :262], rows) < 4e-3 and ei[:, 262:].float().abs().max() == 0
 
 
+# (4, 45): ragged split of the frames over the 4 CTAs of a cluster (12/12/12/9). (40, 300): BASELINE frame count and
+# more samples than clusters fit on the device, so the persistent loop and the ring wrap across samples are covered.
+@pytest.mark.parametrize("shape", [(4, 45), (40, 300), (3, 2)])
 @pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("final", [False, True])
-def test_mix_cfg_ddim_kernel_vs_oracle(mode, final):
+def test_mix_cfg_ddim_kernel_vs_oracle(mode, final, shape):
     from mixermdm_b200 import _lib
     from mixermdm_b200.engine import MixstepArgs
     lib = _lib.load()
     g = np.random.default_rng(100 + mode)
-    B, T = 4, 45
+    B, T = shape
+    if B == 3:
+        B = 2   # (B == 3 is the reference's torch.cross landmine, SURVEY 8a note 7); T = 2: CTAs without frames
     nw = 1 if mode in (1, 2) else 23
     f32 = lambda *s: torch.from_numpy(g.normal(size=s).astype(np.float32))  # noqa: E731
     hfin = f32(2 * B * 2 * T, 512).to(torch.bfloat16)

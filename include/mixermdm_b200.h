@@ -210,6 +210,13 @@ int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const i
 int mmdm_denoiser_forward(mmdm_handle* h, int which, const float* x, const int64_t* timesteps,
                           const float* cond, float* out, int Bx, void* stream);
 
+/* Post-processing of a generated motion (reference: scripts/infer/mixermdm.py:127-132, the step after the sampler):
+ * scipy.ndimage.gaussian_filter1d(motion, sigma, axis = time, mode = 'nearest') on (B,T,F) fp32 device buffers
+ * (F = 524 covers the script's (T,2,262) view). weights: the 2*radius+1 normalised Gaussian taps, HOST memory
+ * (radius = int(4 sigma + 0.5) = 4 for the script's sigma = 1; radius <= 8); out must not alias x. */
+int mmdm_smooth_motion(const float* x, float* out, int B, int T, int F, const float* weights, int radius,
+                       void* stream);
+
 /* per-kernel-class device timing (CUDA events on the launch stream, no graph): enable, run steps, read. */
 int mmdm_profile_enable(mmdm_handle* h, int on);
 /* writes up to max_entries records; returns the number written */

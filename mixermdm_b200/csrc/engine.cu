@@ -793,6 +793,11 @@ int mmdm_mix_cfg_ddim(const mmdm_mixstep_args* a, void* stream) {
   return launch_mixstep(P, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mmdm_smooth_motion(const float* x, float* out, int B, int T, int F, const float* weights, int radius, void* stream) {
+  MMDM_REQUIRE(x && out && weights, "mmdm_smooth_motion: null argument");
+  return launch_smooth_time(x, out, B, T, F, weights, radius, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int mmdm_profile_enable(mmdm_handle* h, int on) {
   MMDM_REQUIRE(h, "mmdm_profile_enable: null handle");
   h->prof.flush();

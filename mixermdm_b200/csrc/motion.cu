@@ -1,14 +1,14 @@
 // Motion-space kernels of the Mixer step (HBM-bound, fp32):
 //   align_kernel   : ih_to_smpl -> align_motions -> smpl_to_ih on the four de-normalised predictions and
 //                    bf16 packing of the Mixer's motion_embed operand (models/mixermdm.py:702-726).
-//   mixstep_kernel : Influence head (Linear 512->{1,23} + sigmoid, models/utils/influence.py:120-125) fused with
-//                    the weight expansion + mix (models/mixermdm.py:739-801), classifier-free guidance
+//   mixstep_kernel : expansion of the Influence head's weights (models/utils/influence.py:120-125, sigmoid(head) comes
+//                    from the head GEMM's epilogue) + mix (models/mixermdm.py:739-801), classifier-free guidance
 //                    (models/utils/cfg_sampler.py:52-55), process_xstart (centre + both normalisers,
-//                    models/utils/gaussian_diffusion.py:2031-2062) and the DDIM update (:1936-1965) in one pass.
-//                    One 4-CTA thread-block CLUSTER per sample: every CTA keeps its frames of the guided prediction in
-//                    shared memory, the per-sample reductions centring needs (min-y over all frames, frame-0
-//                    root and hips) are exchanged through distributed shared memory, so the prediction never
-//                    makes a round trip through HBM.
+//                    models/utils/gaussian_diffusion.py:2031-2062) and the DDIM update (:1936-1965) in one launch.
+//                    Persistent 4-CTA clusters, one sample at a time; all HBM reads stream through a shared-memory
+//                    ring filled by cp.async.bulk; the per-sample reductions centring needs (min-y over all frames,
+//                    frame-0 root and hips) are exchanged through distributed shared memory; the guided prediction
+//                    is handed from the mix phase to the update phase through L2, never through HBM.
 #include "motion.cuh"
 
 #include <cooperative_groups.h>
@@ -106,13 +106,15 @@ int launch_align(const float* out1, const float* out2, float* out1a, float* out2
 //
 // Persistent 4-CTA clusters, one sample at a time per cluster; CTA `rank` owns frames [rank*FR, rank*FR+FR).
 // HBM latency under load is ~2 us, so an SM needs >= 100 KB of reads in flight to stream at its share of the
-// bandwidth (tools/micro/bulk_ring.cu). Shared memory is therefore ONE ring of ~100 row slots (2096 B each) that
-// two producer warps fill with cp.async.bulk, one row per lane, far ahead of the 14 consumer warps:
+// bandwidth (tools/micro/bulk_ring.cu). Shared memory is therefore ONE ring of 25 frame slots (4 rows of 2096 B,
+// one full / one empty mbarrier per slot) that two producer warps fill with cp.async.bulk - one row per lane -
+// far ahead of the 14 consumer warps, which take frames from a ticket counter in the order the ring is filled:
 //   phase 1 of a sample, per frame: rows out1a, out2a of the cond and of the uncond half  -> mix, guidance,
 //           floor search; the guided prediction g goes to global memory (P.final_out doubles as that scratch:
 //           it is only a result at the last step) where it stays in L2,
-//   phase 2, per frame: rows x1, x2 and g -> process_xstart (centring in place in the slot) + DDIM update.
-// The row stream is software-pipelined across samples - P1(0), P1(1), P2(0), P1(2), P2(1), ... - so the cluster
+//   phase 2, per frame: rows x1, x2 and g -> process_xstart (centring in place in the slot) + DDIM update
+//           (normalisers and DDIM coefficients folded into two per-feature tables: two FMAs per value).
+// The frame stream is software-pipelined across samples - P1(0), P1(1), P2(0), P1(2), P2(1), ... - so the cluster
 // exchange centring needs (min-y over all frames, frame-0 root and hips, through DSMEM and remote mbarrier
 // arrives) and the visibility of g have a whole phase to complete and the ring never drains at a phase boundary.
 // Streaming reads carry an L2 evict_first policy so that they do not push g out of L2.
@@ -125,7 +127,9 @@ constexpr int ROWF = 2 * NFEAT;                        // 524 floats per (sample
 constexpr int ROWB = ROWF * 4;                         // 2096 bytes
 constexpr int ROW4 = ROWF / 4;                         // 131 float4
 constexpr int NIT4 = (ROW4 + 31) / 32;                 // 5 float4 per lane per row
-constexpr int MIX_MAX_SLOTS = 104;
+constexpr int SLOT_ROWS = 4;                           // a ring slot holds the rows of one frame of one phase
+constexpr int SLOTB = SLOT_ROWS * ROWB;                // 8384 bytes
+constexpr int MIX_MAX_SLOTS = 26;
 constexpr int MIX_SMEM_MAX = 227 * 1024;
 
 struct MixExport {        // per-CTA data other CTAs of the cluster read through DSMEM
@@ -149,13 +153,13 @@ __host__ __device__ inline MixLayout mix_layout() {
   L.ctr_off = o;   o += 16 + MIX_MAX_SLOTS * 4;         // p1_done, claims[2], slot_lap[]
   o = (o + 15) / 16 * 16;
   L.ring_off = o;
-  int n = (MIX_SMEM_MAX - o) / ROWB;
-  n = n > MIX_MAX_SLOTS ? MIX_MAX_SLOTS : n;
-  L.nslots = n & ~1;                                    // two halves, one per producer warp
-  L.total = o + L.nslots * ROWB;
+  int n = (MIX_SMEM_MAX - o) / SLOTB;
+  L.nslots = n > MIX_MAX_SLOTS ? MIX_MAX_SLOTS : n;
+  L.total = o + L.nslots * SLOTB;
   return L;
 }
 static_assert(sizeof(MixExport) % 16 == 0, "MixExport is laid out in 16-byte units");
+static_assert(2 * MIX_CONSUMERS * 32 >= ROWF, "two table entries per consumer thread cover a row");
 
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
   asm volatile(
@@ -220,36 +224,37 @@ __device__ __forceinline__ void spin_until(const int* ctr, int want, const char*
   }
 }
 
-// mbarrier wait whose polling loop costs three instructions per round (the waiting warps share issue slots with the
-// working ones); the watchdog clock is only read every 4096 rounds
+// mbarrier wait for the ring. try_wait carries a suspend-time hint: the hardware parks the thread until the phase
+// completes (or the hint expires) instead of having it poll - waiting warps share issue slots with working ones,
+// and in this kernel somebody is always waiting (the producers on free slots, by design).
 __device__ __forceinline__ void mix_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = 0;
-  for (uint32_t it = 1;; ++it) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((it & 4095u) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 6000000000LL) {
-        printf("mmdm mixstep: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-        __trap();
-      }
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(200000u)
+        : "memory");
+    if (ok) return;
+    if (it > 20000u) {   // ~4 s of 200 us naps
+      printf("mmdm mixstep: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
     }
   }
 }
 
-// ring position of row c of the CTA's row stream: groups of 32 rows alternate between the two producer warps, each
-// of which owns one half of the ring
-struct RowPos { int slot, lap, prod, group; };
-// (half_rcp = ceil(2^32 / half): exact quotient for the < 2^20 rows a CTA streams)
-__device__ __forceinline__ RowPos locate_row(int c, int half, uint32_t half_rcp) {
+// Ring position of item c of the CTA's stream: slot c % NS, use number ("lap") c / NS.
+// (ns_rcp = ceil(2^32 / NS): exact quotient for the < 2^20 items a CTA streams)
+struct RowPos { int slot, lap; };
+__device__ __forceinline__ RowPos locate_row(int c, int NS, uint32_t ns_rcp) {
   RowPos r;
-  const int g = c >> 5;
-  r.prod = g & 1;
-  r.group = g >> 1;
-  const int lc = r.group * 32 + (c & 31);
-  r.lap = (int)__umulhi((uint32_t)lc, half_rcp);
-  r.slot = r.prod * half + (lc - r.lap * half);
+  r.lap = (int)__umulhi((uint32_t)c, ns_rcp);
+  r.slot = c - r.lap * NS;
   return r;
 }
 
@@ -294,8 +299,8 @@ mixstep_kernel(const MixStepParams P) {
   int* claims = p1_done + 1;      // frame tickets handed out so far, per phase
   int* slot_lap = p1_done + 4;    // per slot: number of times the producer has acquired it
   uint8_t* ring = smem + L.ring_off;
-  const int NS = L.nslots, half = NS / 2;
-  const uint32_t half_rcp = (uint32_t)((0x100000000ULL + half - 1) / half);
+  const int NS = L.nslots;
+  const uint32_t ns_rcp = (uint32_t)((0x100000000ULL + NS - 1) / NS);
 
   const int step = P.mix_only ? 0 : *P.step_ptr;
   const bool final_step = (step == 0) && !P.mix_only;
@@ -314,57 +319,63 @@ mixstep_kernel(const MixStepParams P) {
   }
   cluster_sync_all();   // every CTA's barriers exist before the first remote arrive
 
-  // Row stream of this CTA. S samples; r1 rows per sample in phase 1 (per frame: out1a, out2a of each cfg half),
-  // r2 in phase 2 (per frame: x1, x2, g). Order: P1(0), then for k = 1..S: [P1(k) if k < S], P2(k-1).
+  // Item stream of this CTA: one item = the rows of one frame in one phase (phase 1: out1a, out2a of each cfg half;
+  // phase 2: x1, x2, g). S samples. Order: P1(0), then for k = 1..S: [P1(k) if k < S], P2(k-1).
   const int S = cluster_id < B ? (B - cluster_id + nclusters - 1) / nclusters : 0;
   const int R1 = 2 * ncfg, R2 = 3;
-  const int r1 = nfr * R1, r2 = phase2 ? nfr * R2 : 0;
-  const int total_rows = S * (r1 + r2);
+  const int r1 = nfr, r2 = phase2 ? nfr : 0;   // items per sample and phase
+  const int total_items = S * (r1 + r2);
   auto base_p1 = [&](int k) { return k * r1 + (k > 0 ? k - 1 : 0) * r2; };
   auto base_p2 = [&](int k) { return min(k + 1, S) * r1 + (k - 1) * r2; };   // P2(k-1), issued in stage k
 
   if (warp >= MIX_CONSUMERS) {
-    // ---- producer warps: one row per lane, 32 rows per group, groups alternate between the two warps --------
+    // ---- producer warps: lane = (item of the group, row of the item); groups of 8 items alternate between the
+    // two warps. The lane of an item's first row waits for the slot, arms its barrier with the bytes of all rows and
+    // publishes the acquisition; the lanes of the other rows then send their copies.
     const int pw = warp - MIX_CONSUMERS;
     uint64_t pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    for (int g = pw; g * 32 < total_rows; g += MIX_PRODUCERS) {
-      const int c = g * 32 + lane;
-      const bool valid = c < total_rows;
+    const int li = lane >> 2, r = lane & 3;
+    for (int g = pw; g * 8 < total_items; g += MIX_PRODUCERS) {
+      const int c = g * 8 + li;
       const long long tp0 = tr ? clock64() : 0;
-      const float* src = nullptr;
-      int need_p1 = 0;   // > 0: the row is g of sample need_p1 - 1, written by this CTA's consumers in that sample's phase 1
-      RowPos rp = {0, 0, 0, 0};
-      if (valid) {
-        // decode c -> (sample, phase, frame, row of the frame)
-        int n, idx;
+      if (c < total_items) {
+        // decode c -> (sample, phase, frame)
+        int n, fl;
         bool p1;
         if (c < r1) {
-          n = 0; idx = c; p1 = true;
+          n = 0; fl = c; p1 = true;
         } else {
           const int cp = c - r1, k = 1 + cp / (r1 + r2), rem = cp - (k - 1) * (r1 + r2);
-          if (k < S && rem < r1) { n = k; idx = rem; p1 = true; }
-          else { n = k - 1; idx = k < S ? rem - r1 : rem; p1 = false; }
+          if (k < S && rem < r1) { n = k; fl = rem; p1 = true; }
+          else { n = k - 1; fl = k < S ? rem - r1 : rem; p1 = false; }
         }
-        const int b = cluster_id + n * nclusters;
-        if (p1) {
-          const int fl = idx / R1, r = idx - fl * R1;
-          src = ((r & 1) ? P.out2a : P.out1a) + ((size_t)((r >> 1) * B + b) * T + t_begin + fl) * ROWF;
-        } else {
-          const int fl = idx / R2, r = idx - fl * R2;
-          src = (r == 0 ? P.x1 : r == 1 ? P.x2 : P.final_out) + ((size_t)b * T + t_begin + fl) * ROWF;
-          if (r == 2) need_p1 = n + 1;
+        const int rows = p1 ? R1 : R2;
+        if (r < rows) {
+          const int b = cluster_id + n * nclusters;
+          const float* src;
+          if (p1) src = ((r & 1) ? P.out2a : P.out1a) + ((size_t)((r >> 1) * B + b) * T + t_begin + fl) * ROWF;
+          else src = (r == 0 ? P.x1 : r == 1 ? P.x2 : P.final_out) + ((size_t)b * T + t_begin + fl) * ROWF;
+          const RowPos rp = locate_row(c, NS, ns_rcp);
+          if (r == 0) {
+            if (rp.lap > 0) {
+              // the slot's previous use may belong to the other producer warp: once that one has acquired it, the
+              // empty barrier is in the phase this wait means (a parity wait must not be a whole phase early)
+              spin_until(slot_lap + rp.slot, rp.lap, "slot_lap (producer)");
+              mix_wait(&empty[rp.slot], (uint32_t)(rp.lap - 1) & 1u);
+            }
+            mbar_arrive_expect_tx(&full[rp.slot], (uint32_t)rows * ROWB);
+            st_volatile_smem(slot_lap + rp.slot, rp.lap + 1);
+          } else {
+            spin_until(slot_lap + rp.slot, rp.lap + 1, "slot_lap (row lane)");
+          }
+          if (!p1 && r == 2) {   // g of this frame was written by this CTA's consumers in phase 1 of sample n
+            spin_until(p1_done, n + 1, "p1_done");
+            fence_proxy_async_all();
+          }
+          bulk_g2s_hint(smem_u32(ring + (size_t)rp.slot * SLOTB + r * ROWB), src, ROWB, smem_u32(&full[rp.slot]),
+                        pol_stream);
         }
-        // every lane runs its own slot: wait until it is free, arm its barrier, tell the consumers, copy
-        rp = locate_row(c, half, half_rcp);
-        if (rp.lap > 0) mix_wait(&empty[rp.slot], (uint32_t)(rp.lap - 1) & 1u);
-        mbar_arrive_expect_tx(&full[rp.slot], ROWB);
-        st_volatile_smem(slot_lap + rp.slot, rp.lap + 1);
-        if (need_p1 > 0) {
-          spin_until(p1_done, need_p1, "p1_done");
-          fence_proxy_async_all();
-        }
-        bulk_g2s_hint(smem_u32(ring + (size_t)rp.slot * ROWB), src, ROWB, smem_u32(&full[rp.slot]), pol_stream);
       }
       const long long tp1 = tr ? clock64() : 0;
       __syncwarp();
@@ -380,7 +391,7 @@ mixstep_kernel(const MixStepParams P) {
     const f32x2 s_cfg2 = pack2(P.cfg_scale, P.cfg_scale), s_unc2 = pack2(1.f - P.cfg_scale, 1.f - P.cfg_scale);
     const f32x2 neg1 = pack2(-1.f, -1.f);
     float* wv = reinterpret_cast<float*>(smem + L.wv_off) + warp * 96;
-    // A lane always handles the same 20 features of a row (float4 j = lane + 32 i): the byte offset of the Mixer
+    // A lane always handles the same 20 features of a row (float4 j = lane + 32 i): the index of the Mixer
     // weight that multiplies each of them and whether it is a joint height (floor search) are computed once.
     // Heights only occur in j < 17 (person 0, i = 0) and 65 < j < 82 (person 1, i = 2).
     int woff[NIT4 * 4];
@@ -390,64 +401,89 @@ mixstep_kernel(const MixStepParams P) {
       const int f = (lane + 32 * (i >> 2)) * 4 + (i & 3);
       const int p = f >= NFEAT, fi = f - p * NFEAT;
       const int wi = (NW == 1) ? 0 : weight_index(fi);
-      woff[i] = (p * 24 + wi) * 4;
+      woff[i] = p * 24 + wi;
       if (fi < OFF_VEL && (fi % 3) == 1 && f < ROWF) {
         if ((i >> 2) == 0) yflags |= 1u << (i & 3);
         if ((i >> 2) == 2) yflags |= 1u << (4 + (i & 3));
       }
     }
-    // Mixer weights of frame t for (cfg half, person) = 4 rows of 24: three values per lane
+    // Mixer weights of frame t for (cfg half, person) = 4 rows of 24: three values per lane. Which row / column a
+    // lane fetches never changes: element index of (sequence 0 of the cfg half and person, column) and validity.
+    int wsrc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int idx = lane + 32 * k, cp = idx / 24, kk = idx - cp * 24;
+      wsrc[k] = (cp < 2 * ncfg && kk < NW) ? ((cp >> 1) * B * 2 + (cp & 1)) : -1;
+    }
+    const int wkk0 = lane % 24, wkk1 = (lane + 32) % 24, wkk2 = (lane + 64) % 24;
     auto load_w = [&](int b, int t, float* w3) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const int idx = lane + 32 * k, cp = idx / 24, kk = idx - cp * 24;
-        const size_t seq = (size_t)((cp >> 1) * B + b) * 2 + (cp & 1);
         float v = 0.f;
-        if (P.has_force) v = P.force_val;
-        else if (cp < 2 * ncfg && kk < NW) v = __ldg(P.weights + (pooled ? seq : seq * T + t) * 24 + kk);
+        if (P.has_force) {
+          v = P.force_val;
+        } else if (wsrc[k] >= 0) {
+          const int seq = wsrc[k] + 2 * b;
+          v = __ldg(P.weights + (pooled ? seq : seq * T + t) * 24 + (k == 0 ? wkk0 : k == 1 ? wkk1 : wkk2));
+        }
         w3[k] = v;
       }
     };
-    // wait for row c of the stream; returns its slot
-    auto acquire_row = [&](int c) -> const float* {
-      const RowPos rp = locate_row(c, half, half_rcp);
+    auto acquire_item = [&](RowPos rp) -> float* {   // wait for item rp of the stream; returns its slot
       if (lane == 0) spin_until(slot_lap + rp.slot, rp.lap + 1, "slot_lap");
       __syncwarp();
       mix_wait(&full[rp.slot], (uint32_t)rp.lap & 1u);
-      return reinterpret_cast<const float*>(ring + (size_t)rp.slot * ROWB);
-    };
-    auto release_row = [&](int c) {   // lane 0 only
-      const RowPos rp = locate_row(c, half, half_rcp);
-      mbar_arrive(&empty[rp.slot]);
+      return reinterpret_cast<float*>(ring + (size_t)rp.slot * SLOTB);
     };
     auto claim = [&](int which) -> int {   // next ticket of phase `which`: frame q % nfr of sample q / nfr
       int q = 0;
-      if (lane == 0) q = atomicAdd(claims + which, 1);
+      if (lane == 0)
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(q) : "r"(smem_u32(claims + which)) : "memory");
       return __shfl_sync(0xffffffffu, q, 0);
     };
     // DDIM update with the normalisation folded in: x' = A pred + Bc x, pred = (g - mean) / std
     //   (gaussian_diffusion.py:1936-1965 with eta = 0: x' = pred sqrt(ab_prev) + sqrt(1 - ab_prev) eps,
     //    eps = (sqrt(1/ab) x - pred) / sqrt(1/ab - 1))  ->  x' = TA g + TB + Bc x with per-feature tables TA, TB
-    f32x2 bc2 = pack2(0.f, 0.f);
-    if (phase2) {
-      const double c_recip = P.coef[step * 4 + 0], c_recipm1 = P.coef[step * 4 + 1];
-      const double c_ap = P.coef[step * 4 + 2], c_eps = P.coef[step * 4 + 3];
-      const float A = (float)(c_ap - c_eps / c_recipm1), Bc = (float)(c_eps / c_recipm1 * c_recip);
-      bc2 = pack2(Bc, Bc);
-      for (int i = threadIdx.x; i < ROWF; i += MIX_CONSUMERS * 32) {
-        const int fi = i >= NFEAT ? i - NFEAT : i;
-        const float r1s = 1.0f / P.std1[fi], r2s = 1.0f / P.std2[fi];
-        tab[i] = A * r1s;                              // TA, stream 1 (individual-model normaliser)
-        tab[ROWF + i] = -A * P.mean1[fi] * r1s;        // TB
-        tab[2 * ROWF + i] = A * r2s;                   // TA, stream 2 (interaction-model normaliser)
-        tab[3 * ROWF + i] = -A * P.mean2[fi] * r2s;    // TB
-      }
-      consumer_sync();
-    }
     const int tickets = S * nfr;
     int next1 = nfr > 0 ? claim(0) : tickets, next2 = (nfr > 0 && phase2) ? claim(1) : tickets;
+    int nk1 = 0;   // sample of ticket next1 (tickets only grow: no division)
+    auto prefetch_w = [&](float* w3) {
+      if (next1 < tickets) {
+        while (next1 >= (nk1 + 1) * nfr) ++nk1;
+        load_w(cluster_id + nk1 * nclusters, t_begin + next1 - nk1 * nfr, w3);
+      }
+    };
     float w3[3] = {0.f, 0.f, 0.f};
-    if (next1 < tickets) load_w(cluster_id + (next1 / nfr) * nclusters, t_begin + next1 % nfr, w3);
+    prefetch_w(w3);   // in flight while the tables below are built
+    f32x2 bc2 = pack2(0.f, 0.f);
+    if (phase2) {
+      // (first read in phase 2 of sample 0, i.e. behind the consumer barrier that ends its phase 1)
+      const float c_recip = P.coef[step * 4 + 0], c_recipm1 = P.coef[step * 4 + 1];
+      const float c_ap = P.coef[step * 4 + 2], c_eps = P.coef[step * 4 + 3];
+      float sd1[2], sd2[2], mn1[2], mn2[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {   // all loads first: one memory latency for the whole prologue
+        const int i = threadIdx.x + q * MIX_CONSUMERS * 32;
+        const int fi = i >= NFEAT ? i - NFEAT : i;
+        const bool ok = i < ROWF;
+        sd1[q] = ok ? P.std1[fi] : 1.f; sd2[q] = ok ? P.std2[fi] : 1.f;
+        mn1[q] = ok ? P.mean1[fi] : 0.f; mn2[q] = ok ? P.mean2[fi] : 0.f;
+      }
+      const float A = (float)((double)c_ap - (double)c_eps / (double)c_recipm1);
+      const float Bc = (float)((double)c_eps / (double)c_recipm1 * (double)c_recip);
+      bc2 = pack2(Bc, Bc);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = threadIdx.x + q * MIX_CONSUMERS * 32;
+        if (i < ROWF) {
+          const float r1s = 1.0f / sd1[q], r2s = 1.0f / sd2[q];
+          tab[i] = A * r1s;                          // TA, stream 1 (individual-model normaliser)
+          tab[ROWF + i] = -A * mn1[q] * r1s;         // TB
+          tab[2 * ROWF + i] = A * r2s;               // TA, stream 2 (interaction-model normaliser)
+          tab[3 * ROWF + i] = -A * mn2[q] * r2s;     // TB
+        }
+      }
+    }
 
     for (int k = 0; k <= S; ++k) {
       if (k < S) {
@@ -462,16 +498,16 @@ mixstep_kernel(const MixStepParams P) {
 #pragma unroll
           for (int q = 0; q < 3; ++q) wv[lane + 32 * q] = w3[q];
           next1 = claim(0);
-          if (next1 < tickets) load_w(cluster_id + (next1 / nfr) * nclusters, t_begin + next1 % nfr, w3);
-          const int c0 = cb + fl * R1;
+          prefetch_w(w3);
           const long long tc0 = tr ? clock64() : 0;
-          const float* o1c = acquire_row(c0);       // (the __syncwarp inside also orders the wv stores)
-          const float* o2c = acquire_row(c0 + 1);
-          const float* o1u = two ? acquire_row(c0 + 2) : o1c;
-          const float* o2u = two ? acquire_row(c0 + 3) : o2c;
+          const RowPos ip = locate_row(cb + fl, NS, ns_rcp);
+          const float* o1c = acquire_item(ip);       // (the __syncwarp inside also orders the wv stores)
+          const float* o2c = o1c + ROWF;
+          const float* o1u = two ? o1c + 2 * ROWF : o1c;
+          const float* o2u = two ? o1c + 3 * ROWF : o2c;
           const size_t rc = ((size_t)b * T + t) * ROWF;            // cond half row
           const size_t ru = ((size_t)(B + b) * T + t) * ROWF;      // uncond half row
-          const uint32_t wva = smem_u32(wv);
+          float4* const gp = reinterpret_cast<float4*>((P.mix_only == 2 ? P.mix_out : P.final_out) + rc) + lane;
           const long long tc1 = tr ? clock64() : 0;
 #pragma unroll
           for (int i = 0; i < NIT4; ++i) {
@@ -484,8 +520,8 @@ mixstep_kernel(const MixStepParams P) {
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {   // two features per packed fp32x2 instruction
                 const int e = 2 * h2;
-                wcv[e] = __uint_as_float(lds32(wva + woff[i * 4 + e]));
-                wcv[e + 1] = __uint_as_float(lds32(wva + woff[i * 4 + e + 1]));
+                wcv[e] = wv[woff[i * 4 + e]];          // (plain loads: the five iterations are independent and the
+                wcv[e + 1] = wv[woff[i * 4 + e + 1]];  //  compiler may interleave them)
                 const f32x2 av = h2 ? pack2(a4.z, a4.w) : pack2(a4.x, a4.y);
                 const f32x2 bv = h2 ? pack2(b4.z, b4.w) : pack2(b4.x, b4.y);
                 const f32x2 mc = fma2(pack2(wcv[e], wcv[e + 1]), fma2(bv, neg1, av), bv);   // b + w (a - b)
@@ -493,8 +529,8 @@ mixstep_kernel(const MixStepParams P) {
                 unpack2(mc, mcv[e], mcv[e + 1]);
                 muv[e] = muv[e + 1] = wuv[e] = wuv[e + 1] = 0.f;
                 if (two) {
-                  wuv[e] = __uint_as_float(lds32(wva + 192 + woff[i * 4 + e]));
-                  wuv[e + 1] = __uint_as_float(lds32(wva + 192 + woff[i * 4 + e + 1]));
+                  wuv[e] = wv[48 + woff[i * 4 + e]];
+                  wuv[e + 1] = wv[48 + woff[i * 4 + e + 1]];
                   const f32x2 cv = h2 ? pack2(c4.z, c4.w) : pack2(c4.x, c4.y);
                   const f32x2 dv = h2 ? pack2(d4.z, d4.w) : pack2(d4.x, d4.y);
                   const f32x2 mu = fma2(pack2(wuv[e], wuv[e + 1]), fma2(dv, neg1, cv), dv);
@@ -527,14 +563,13 @@ mixstep_kernel(const MixStepParams P) {
               if (P.mix_only != 1) {
                 // the guided prediction: Mixer.forward's CFG output, the sampler's result at the last step (rows of
                 // the un-doubled batch coincide with the cond half), phase 2's input at every other step
-                float* gdst = (P.mix_only == 2 ? P.mix_out : P.final_out) + rc;
-                *reinterpret_cast<float4*>(gdst + 4 * j) = make_float4(g[0], g[1], g[2], g[3]);
+                gp[32 * i] = make_float4(g[0], g[1], g[2], g[3]);
               }
             }
           }
           __syncwarp();
           if (lane == 0) {
-            for (int r = 0; r < R1; ++r) release_row(c0 + r);
+            mbar_arrive(&empty[ip.slot]);
           }
           mix_trace(tr, warp, ntr, (1LL << 32) | (k * nfr + fl), tc0, tc1, tr ? clock64() : 0);
         }
@@ -596,12 +631,14 @@ mixstep_kernel(const MixStepParams P) {
           const int fl = next2 - n * nfr;
           next2 = claim(1);
           const int t = t_begin + fl;
-          const int c0 = cb + fl * R2;
           const size_t rx = ((size_t)b * T + t) * ROWF;
+          float4* const x1p = reinterpret_cast<float4*>(P.x1 + rx) + lane;
+          float4* const x2p = reinterpret_cast<float4*>(P.x2 + rx) + lane;
           const long long tc0 = tr ? clock64() : 0;
-          const float* xr1 = acquire_row(c0);
-          const float* xr2 = acquire_row(c0 + 1);
-          float* crow = const_cast<float*>(acquire_row(c0 + 2));
+          const RowPos ip = locate_row(cb + fl, NS, ns_rcp);
+          const float* xr1 = acquire_item(ip);
+          const float* xr2 = xr1 + ROWF;
+          float* crow = const_cast<float*>(xr1) + 2 * ROWF;
           const long long tc1 = tr ? clock64() : 0;
           // stream 2 (interaction space): the raw guided prediction, normalised inside the tables
 #pragma unroll
@@ -613,7 +650,7 @@ mixstep_kernel(const MixStepParams P) {
               float o[4];
               unpack2(fma2(pack2(ta.x, ta.y), pack2(g4.x, g4.y), fma2(bc2, pack2(x4.x, x4.y), pack2(tb.x, tb.y))), o[0], o[1]);
               unpack2(fma2(pack2(ta.z, ta.w), pack2(g4.z, g4.w), fma2(bc2, pack2(x4.z, x4.w), pack2(tb.z, tb.w))), o[2], o[3]);
-              *reinterpret_cast<float4*>(P.x2 + rx + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+              x2p[32 * i] = make_float4(o[0], o[1], o[2], o[3]);
             }
           }
           __syncwarp();
@@ -650,13 +687,13 @@ mixstep_kernel(const MixStepParams P) {
               float o[4];
               unpack2(fma2(pack2(ta.x, ta.y), pack2(g4.x, g4.y), fma2(bc2, pack2(x4.x, x4.y), pack2(tb.x, tb.y))), o[0], o[1]);
               unpack2(fma2(pack2(ta.z, ta.w), pack2(g4.z, g4.w), fma2(bc2, pack2(x4.z, x4.w), pack2(tb.z, tb.w))), o[2], o[3]);
-              *reinterpret_cast<float4*>(P.x1 + rx + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+              x1p[32 * i] = make_float4(o[0], o[1], o[2], o[3]);
             }
           }
           fence_proxy_async_smem();   // the centring wrote into the slot: order it before the next bulk copy into it
           __syncwarp();
           if (lane == 0) {
-            for (int r = 0; r < R2; ++r) release_row(c0 + r);
+            mbar_arrive(&empty[ip.slot]);
           }
           mix_trace(tr, warp, ntr, (2LL << 32) | (n * nfr + fl), tc0, tc1, tr ? clock64() : 0);
         }
@@ -718,6 +755,80 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
   cfg.gridDim = dim3((unsigned)(nclusters * MIX_CLUSTER));
   if (NW == 1) MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<1>, P));
   else MMDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mixstep_kernel<23>, P));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// smooth_time_kernel: temporal Gaussian blur of a generated motion, the post-processing step of the reference's
+// inference script (scripts/infer/mixermdm.py:127-132: gaussian_filter1d(motion, sigma = 1, axis = 0,
+// mode = 'nearest') on the (T, 2, 262) view of output[0]). out[b,t,:] = sum_k w[k] x[b, clamp(t+k-R, 0, T-1), :].
+// HBM-bound (one read, one write per value): a thread owns one float4 column of one sample for a run of frames
+// and slides a register window of 2R+1 rows over it, so every input row is read once per run (+2R halo rows).
+// ------------------------------------------------------------------------------------------------
+constexpr int SMOOTH_MAX_R = 8;
+constexpr int SMOOTH_RUN = 32;   // frames per thread
+
+struct SmoothParams {
+  const float* x;
+  float* out;
+  int B, T, F4;   // F4 = features / 4
+  int R;
+  float w[2 * SMOOTH_MAX_R + 1];
+};
+
+template <int R>
+__global__ void __launch_bounds__(128) smooth_time_kernel(const SmoothParams P) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= P.F4) return;
+  const int b = blockIdx.z, t0 = blockIdx.y * SMOOTH_RUN;
+  const int t1 = min(P.T, t0 + SMOOTH_RUN);
+  const float4* src = reinterpret_cast<const float4*>(P.x) + (size_t)b * P.T * P.F4 + col;
+  float4* dst = reinterpret_cast<float4*>(P.out) + (size_t)b * P.T * P.F4 + col;
+  auto row = [&](int t) { return __ldg(src + (size_t)min(max(t, 0), P.T - 1) * P.F4); };
+  float4 win[2 * R + 1];
+#pragma unroll
+  for (int k = 0; k < 2 * R; ++k) win[k + 1] = row(t0 - R + k);
+  for (int t = t0; t < t1; ++t) {
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) win[k] = win[k + 1];
+    win[2 * R] = row(t + R);
+    // symmetric taps summed pairwise around the centre, like scipy's correlate1d does for a symmetric kernel
+    float4 acc = make_float4(P.w[R] * win[R].x, P.w[R] * win[R].y, P.w[R] * win[R].z, P.w[R] * win[R].w);
+#pragma unroll
+    for (int k = 1; k <= R; ++k) {
+      const float wk = P.w[R + k];
+      acc.x = fmaf(wk, win[R - k].x + win[R + k].x, acc.x);
+      acc.y = fmaf(wk, win[R - k].y + win[R + k].y, acc.y);
+      acc.z = fmaf(wk, win[R - k].z + win[R + k].z, acc.z);
+      acc.w = fmaf(wk, win[R - k].w + win[R + k].w, acc.w);
+    }
+    dst[(size_t)t * P.F4] = acc;
+  }
+}
+
+int launch_smooth_time(const float* x, float* out, int B, int T, int F, const float* weights, int R,
+                       cudaStream_t stream) {
+  MMDM_REQUIRE(B >= 1 && T >= 1 && F >= 4 && (F % 4) == 0, "smooth_motion: bad shape B=%d T=%d F=%d", B, T, F);
+  MMDM_REQUIRE(R >= 0 && R <= SMOOTH_MAX_R, "smooth_motion: kernel radius %d outside [0, %d]", R, SMOOTH_MAX_R);
+  MMDM_REQUIRE(x != out, "smooth_motion: in-place filtering is not supported");
+  MMDM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "smooth_motion: buffers must be 16-byte aligned");
+  SmoothParams P = {};
+  P.x = x; P.out = out; P.B = B; P.T = T; P.F4 = F / 4; P.R = R;
+  for (int k = 0; k < 2 * R + 1; ++k) P.w[k] = weights[k];
+  const dim3 grid((unsigned)((P.F4 + 127) / 128), (unsigned)((T + SMOOTH_RUN - 1) / SMOOTH_RUN), (unsigned)B);
+  switch (R) {
+    case 0: smooth_time_kernel<0><<<grid, 128, 0, stream>>>(P); break;
+    case 1: smooth_time_kernel<1><<<grid, 128, 0, stream>>>(P); break;
+    case 2: smooth_time_kernel<2><<<grid, 128, 0, stream>>>(P); break;
+    case 3: smooth_time_kernel<3><<<grid, 128, 0, stream>>>(P); break;
+    case 4: smooth_time_kernel<4><<<grid, 128, 0, stream>>>(P); break;
+    case 5: smooth_time_kernel<5><<<grid, 128, 0, stream>>>(P); break;
+    case 6: smooth_time_kernel<6><<<grid, 128, 0, stream>>>(P); break;
+    case 7: smooth_time_kernel<7><<<grid, 128, 0, stream>>>(P); break;
+    default: smooth_time_kernel<8><<<grid, 128, 0, stream>>>(P); break;
+  }
+  MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

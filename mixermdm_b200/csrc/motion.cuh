@@ -35,6 +35,9 @@ struct MixStepParams {
 };
 
 int launch_mixstep(const MixStepParams& P, cudaStream_t stream);
+// temporal Gaussian blur (scripts/infer/mixermdm.py:131): x, out (B,T,F) fp32, weights[2R+1] symmetric taps (host)
+int launch_smooth_time(const float* x, float* out, int B, int T, int F, const float* weights, int R,
+                       cudaStream_t stream);
 int launch_pool_mean(const __nv_bfloat16* h, int S, int T, int D, __nv_bfloat16* out, cudaStream_t stream);
 int motion_init();
 

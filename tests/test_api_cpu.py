@@ -141,3 +141,17 @@ def test_sharded_sampling_equals_single_process_bitwise(total):
         for r in range(2):
             got = torch.from_numpy(np.load(os.path.join(d, f"rank{r}.npy")))
             assert torch.equal(got, ref)      # both ranks hold the full batch, identical to the 1-process result
+
+
+def test_gaussian_taps_match_scipy_impulse_response():
+    """postprocess.gaussian_taps restates scipy's kernel (scripts/infer/mixermdm.py:131 uses sigma = 1)."""
+    import numpy as np
+    from scipy.ndimage import gaussian_filter1d
+    from mixermdm_b200.postprocess import gaussian_taps
+    for sigma in (0.5, 1.0, 2.0):
+        taps, radius = gaussian_taps(sigma)
+        imp = np.zeros(4 * radius + 1)
+        imp[2 * radius] = 1.0
+        ref = gaussian_filter1d(imp, sigma, mode="nearest")[radius:3 * radius + 1]
+        assert radius == int(4 * sigma + 0.5) and len(taps) == 2 * radius + 1
+        assert np.abs(taps - ref).max() < 1e-15

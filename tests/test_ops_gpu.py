@@ -160,3 +160,24 @@ def test_small_linear(ops):
     r = torch.nn.functional.silu(a @ w.t() + b)
     torch.cuda.synchronize()
     assert _relerr(o, r) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 299, 524), (3, 300, 524), (2, 5, 524), (1, 1, 524), (4, 77, 264)])
+@pytest.mark.parametrize("sigma", [1.0, 2.0])
+def test_smooth_motion_matches_scipy(shape, sigma):
+    """Post-processing of the reference's inference script (scripts/infer/mixermdm.py:131):
+    gaussian_filter1d(motion, sigma, axis=time, mode='nearest'); scipy is the oracle."""
+    from scipy.ndimage import gaussian_filter1d
+    from mixermdm_b200 import postprocess
+    x = _rand(shape, 7)
+    y = postprocess.smooth_motion(x, sigma)
+    torch.cuda.synchronize()
+    ref = gaussian_filter1d(x.cpu().numpy(), sigma, axis=1, mode="nearest")
+    assert y.shape == x.shape
+    assert (y.cpu() - torch.from_numpy(ref)).abs().max().item() < 2e-6
+    # the script's own call: one sample viewed as (T, 2, 262)
+    if shape[2] == 524:
+        one = postprocess.motion_to_persons(x[0], sigma=sigma)
+        ref1 = gaussian_filter1d(x[0].cpu().numpy().reshape(shape[1], 2, -1), sigma, axis=0, mode="nearest")
+        assert one.shape == (shape[1], 2, 262)
+        assert (one.cpu() - torch.from_numpy(ref1)).abs().max().item() < 2e-6

@@ -34,6 +34,11 @@ struct Args {
   int group;           // items per producer group (lane-parallel issue); 0 = one thread issues everything
   int consumers;       // consumer warps
   int touch;           // consumers read the slot (one float4 per lane per copy)
+  int streams;         // 1: the copies of an item are consecutive in memory; 0: copy k comes from its own region
+                       //    (k * region_bytes apart), like the out1a/out2a/x1/x2/g rows of the mix kernel
+  size_t region_bytes;
+  float* wdst;         // != null: consumers also write `wrows` rows of copy_bytes per item (coalesced float4)
+  int wrows;
 };
 
 __global__ void __launch_bounds__(512, 1) ring_kernel(const Args a) {
@@ -53,7 +58,10 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const Args a) {
     fence_barrier_init();
   }
   __syncthreads();
-  const uint8_t* base = a.src + (size_t)blockIdx.x * a.items_per_cta * a.copies * a.pitch;
+  const uint8_t* base = a.src + (size_t)blockIdx.x * a.items_per_cta * (a.streams ? a.copies : 1) * a.pitch;
+  auto src_of = [&](int c, int k) {
+    return a.streams ? base + ((size_t)c * a.copies + k) * a.pitch : base + (size_t)k * a.region_bytes + (size_t)c * a.pitch;
+  };
   const int NS = a.nslots;
   if (warp == a.consumers) {
     if (a.group == 0) {
@@ -63,8 +71,8 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const Args a) {
           if (lap > 0) mbar_wait(&empty[slot], (uint32_t)(lap - 1) & 1u);
           mbar_arrive_expect_tx(&full[slot], (uint32_t)(a.copies * a.copy_bytes));
           for (int k = 0; k < a.copies; ++k)
-            bulk_g2s(smem_u32(ring + (size_t)slot * slot_bytes + k * a.copy_bytes),
-                     base + ((size_t)c * a.copies + k) * a.pitch, (uint32_t)a.copy_bytes, smem_u32(&full[slot]));
+            bulk_g2s(smem_u32(ring + (size_t)slot * slot_bytes + k * a.copy_bytes), src_of(c, k),
+                     (uint32_t)a.copy_bytes, smem_u32(&full[slot]));
           st_vol(issued, c + 1);
         }
       }
@@ -85,8 +93,8 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const Args a) {
         }
         __syncwarp();
         if (valid)
-          bulk_g2s(smem_u32(ring + (size_t)slot * slot_bytes + k * a.copy_bytes),
-                   base + ((size_t)c * a.copies + k) * a.pitch, (uint32_t)a.copy_bytes, smem_u32(&full[slot]));
+          bulk_g2s(smem_u32(ring + (size_t)slot * slot_bytes + k * a.copy_bytes), src_of(c, k),
+                   (uint32_t)a.copy_bytes, smem_u32(&full[slot]));
         __syncwarp();
         if (lane == 0) st_vol(issued, min((g + 1) * G, a.items_per_cta));
       }
@@ -105,6 +113,14 @@ __global__ void __launch_bounds__(512, 1) ring_kernel(const Args a) {
         for (int i = lane; i < n4; i += 32) {
           const float4 v = p[i];
           acc += v.x + v.y + v.z + v.w;
+        }
+      }
+      if (a.wdst != nullptr) {
+        const int n4 = a.copy_bytes / 16;
+        for (int r = 0; r < a.wrows; ++r) {
+          float4* w = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.wdst) + (size_t)r * a.region_bytes +
+                                                ((size_t)blockIdx.x * a.items_per_cta + c) * a.pitch);
+          for (int i = lane; i < n4; i += 32) w[i] = make_float4(acc, 1.f, 2.f, 3.f);
         }
       }
       __syncwarp();
@@ -136,7 +152,7 @@ static void run(const char* name, Args a, int grid, uint8_t* flush, size_t flush
     cudaEventElapsedTime(&ms, e0, e1);
     if (it > 0 && ms < best) best = ms;
   }
-  const double bytes = (double)grid * a.items_per_cta * a.copies * a.copy_bytes;
+  const double bytes = (double)grid * a.items_per_cta * (a.copies + (a.wdst ? a.wrows : 0)) * a.copy_bytes;
   printf("%-58s %8.1f us  %7.1f GB/s  (%5.1f GB/s per SM, %d B in flight per SM)\n", name, best * 1e3, bytes / best / 1e6,
          bytes / best / 1e6 / grid, a.nslots * a.copies * a.copy_bytes);
 }
@@ -150,11 +166,17 @@ int main() {
   cudaMalloc(&flush, (size_t)256 << 20);
   cudaMalloc(&sink, 4096);
   const int grid = 148;
-  auto mk = [&](int copies, int bytes, int pitch, int nslots, int group, int consumers, int touch) {
+  float* wbuf;
+  cudaMalloc(&wbuf, total);
+  const size_t region = total / 8;   // 128 MB per stream
+  auto mk = [&](int copies, int bytes, int pitch, int nslots, int group, int consumers, int touch, int streams = 1,
+                int wrows = 0) {
     Args a;
     a.src = src; a.sink = sink; a.copies = copies; a.copy_bytes = bytes; a.pitch = pitch; a.nslots = nslots;
     a.group = group; a.consumers = consumers; a.touch = touch;
-    a.items_per_cta = (int)((size_t)4 << 20) / (copies * pitch);   // ~4 MB per CTA
+    a.streams = streams; a.region_bytes = region; a.wdst = wrows ? wbuf : nullptr; a.wrows = wrows;
+    a.items_per_cta = streams ? (int)((size_t)4 << 20) / (copies * pitch) : (int)(region / 148 / pitch);
+    if (!streams && a.items_per_cta > 400) a.items_per_cta = 400;
     return a;
   };
   char name[128];
@@ -171,6 +193,16 @@ int main() {
     snprintf(name, sizeof(name), "copies=%d bytes=%5d pitch=%5d slots=%2d group=%2d cons=%2d touch=%d", c.copies, c.bytes,
              c.pitch, c.nslots, c.group, c.consumers, c.touch);
     run(name, mk(c.copies, c.bytes, c.pitch, c.nslots, c.group, c.consumers, c.touch), grid, flush, (size_t)256 << 20);
+  }
+  // the mix kernel's access pattern: every item = 4 (or 7) rows of 2096 B from separate arrays, optionally with 3
+  // rows written back per item; 132 or 148 CTAs
+  printf("--- separate-array streams (mix-kernel pattern)\n");
+  struct Cfg2 { int copies, nslots, group, wrows, grid; };
+  const Cfg2 c2[] = {{4, 25, 8, 0, 148}, {4, 25, 8, 0, 132}, {4, 25, 8, 2, 132}, {7, 14, 4, 3, 132}, {4, 12, 8, 0, 132}};
+  for (const Cfg2& c : c2) {
+    snprintf(name, sizeof(name), "arrays=%d bytes=2096 slots=%2d group=%d written rows=%d grid=%d", c.copies, c.nslots, c.group,
+             c.wrows, c.grid);
+    run(name, mk(c.copies, 2096, 2096, c.nslots, c.group, 14, 1, 0, c.wrows), c.grid, flush, (size_t)256 << 20);
   }
   return 0;
 }

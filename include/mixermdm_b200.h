@@ -217,6 +217,13 @@ int mmdm_denoiser_forward(mmdm_handle* h, int which, const float* x, const int64
 int mmdm_smooth_motion(const float* x, float* out, int B, int T, int F, const float* weights, int radius,
                        void* stream);
 
+/* Output format of the evaluation generators (reference: evaluation/datasets.py:121-134, 452-465): the sampled
+ * motion (B,T,2*nfeats) is optionally de-normalised per person (MotionNormalizer.backward: x*std+mean; mean/std are
+ * (nfeats) DEVICE arrays, both or neither) and padded with zero frames to max_length -> out (B,max_length,2*nfeats),
+ * i.e. the (B,max_length,2,nfeats) array the generators store. */
+int mmdm_format_motion(const float* x, float* out, int B, int T, int max_length, int nfeats, const float* mean,
+                       const float* std_, void* stream);
+
 /* per-kernel-class device timing (CUDA events on the launch stream, no graph): enable, run steps, read. */
 int mmdm_profile_enable(mmdm_handle* h, int on);
 /* writes up to max_entries records; returns the number written */

@@ -798,6 +798,12 @@ int mmdm_smooth_motion(const float* x, float* out, int B, int T, int F, const fl
   return launch_smooth_time(x, out, B, T, F, weights, radius, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mmdm_format_motion(const float* x, float* out, int B, int T, int max_length, int nfeats, const float* mean,
+                       const float* std_, void* stream) {
+  MMDM_REQUIRE(x && out, "mmdm_format_motion: null argument");
+  return launch_format_motion(x, out, B, T, max_length, nfeats, mean, std_, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int mmdm_profile_enable(mmdm_handle* h, int on) {
   MMDM_REQUIRE(h, "mmdm_profile_enable: null handle");
   h->prof.flush();

@@ -832,6 +832,45 @@ int launch_smooth_time(const float* x, float* out, int B, int T, int F, const fl
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// format_motion_kernel: output format of the evaluation generators (evaluation/datasets.py:121-134): the sampled
+// (B, T, 2*nf) motion is de-normalised per person (MotionNormalizer.backward: x * std + mean, optional) and padded
+// with zero frames to the data set's max_length -> (B, Tmax, 2, nf). One pass, one thread per output value pair.
+// ------------------------------------------------------------------------------------------------
+__global__ void format_motion_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int T, int Tmax,
+                                     int nf, const float* __restrict__ mean, const float* __restrict__ stdv) {
+  const int F = 2 * nf;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // pair index
+  const long long total = (long long)B * Tmax * (F / 2);
+  if (idx >= total) return;
+  const int f = (int)(idx % (F / 2)) * 2;
+  const long long bt = idx / (F / 2);
+  const int t = (int)(bt % Tmax), b = (int)(bt / Tmax);
+  float2 v = make_float2(0.f, 0.f);
+  if (t < T) {
+    v = *reinterpret_cast<const float2*>(x + ((size_t)b * T + t) * F + f);
+    if (mean != nullptr) {
+      const int f0 = f >= nf ? f - nf : f, f1 = f + 1 >= nf ? f + 1 - nf : f + 1;
+      v.x = v.x * stdv[f0] + mean[f0];
+      v.y = v.y * stdv[f1] + mean[f1];
+    }
+  }
+  *reinterpret_cast<float2*>(out + ((size_t)b * Tmax + t) * F + f) = v;
+}
+
+int launch_format_motion(const float* x, float* out, int B, int T, int Tmax, int nf, const float* mean,
+                         const float* stdv, cudaStream_t stream) {
+  MMDM_REQUIRE(B >= 1 && T >= 1 && Tmax >= T && nf >= 2 && (nf % 2) == 0,
+               "format_motion: bad shape B=%d T=%d max_length=%d nfeats=%d", B, T, Tmax, nf);
+  MMDM_REQUIRE((mean == nullptr) == (stdv == nullptr), "format_motion: mean and std come together");
+  MMDM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 7) == 0,
+               "format_motion: buffers must be 8-byte aligned");
+  const long long total = (long long)B * Tmax * nf;
+  format_motion_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, out, B, T, Tmax, nf, mean, stdv);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // mean over the T tokens of every sequence: (S*T, D) bf16 -> (S, D) bf16   (influence.py:116-118, modes 1 and 3)
 __global__ void pool_mean_kernel(const __nv_bfloat16* __restrict__ h, int T, int D, __nv_bfloat16* __restrict__ out) {
   const int s = blockIdx.x;

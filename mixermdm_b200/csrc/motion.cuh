@@ -38,6 +38,10 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream);
 // temporal Gaussian blur (scripts/infer/mixermdm.py:131): x, out (B,T,F) fp32, weights[2R+1] symmetric taps (host)
 int launch_smooth_time(const float* x, float* out, int B, int T, int F, const float* weights, int R,
                        cudaStream_t stream);
+// evaluation output format (evaluation/datasets.py:121-134): (B,T,2*nf) -> (B,Tmax,2*nf), x*std+mean per person when
+// mean/std (nf, device) are given, zero frames beyond T
+int launch_format_motion(const float* x, float* out, int B, int T, int Tmax, int nf, const float* mean,
+                         const float* stdv, cudaStream_t stream);
 int launch_pool_mean(const __nv_bfloat16* h, int S, int T, int D, __nv_bfloat16* out, cudaStream_t stream);
 int motion_init();
 

@@ -376,3 +376,57 @@ def test_full_size_batch32_loop_properties(full_model):
     assert torch.isfinite(a).all()
     assert torch.equal(a, b)
     assert torch.equal(a[:16], half)
+
+
+def test_format_motion_matches_numpy():
+    """evaluation/datasets.py:121-134: reshape to (B,T,2,262), MotionNormalizer.backward, zero padding to max_length"""
+    from mixermdm_b200.generation import format_generated
+    g = np.random.default_rng(5)
+    x = torch.from_numpy(g.normal(size=(3, 37, 524)).astype(np.float32))
+    mean, std = g.normal(size=262).astype(np.float32), (g.random(262) + 0.5).astype(np.float32)
+    for m, s in ((None, None), (mean, std)):
+        y = format_generated(x.to(DEV), 64, m, s)
+        torch.cuda.synchronize()
+        ref = x.numpy().reshape(3, 37, 2, 262)
+        if m is not None:
+            ref = ref * std + mean
+        ref = np.concatenate([ref, np.zeros((3, 64 - 37, 2, 262), np.float32)], axis=1)
+        assert y.shape == (3, 64, 2, 262)
+        assert np.abs(y.cpu().numpy() - ref).max() < 1e-6
+    with pytest.raises(ValueError):
+        format_generated(x.to(DEV), 10)
+
+
+def test_batched_generator_equals_one_prompt_per_call(golden):
+    """Packing prompts of equal length into one sampler call (generation.BatchedGenerator) returns bit for bit what the
+    reference's batch_size=1 evaluation loop gets from one forward_test per prompt (samples are independent)."""
+    from mixermdm_b200.generation import BatchedGenerator, MotionRequest, format_generated
+    from mixermdm_b200.mixermdm import AttrDict, MixerMDM
+    _, meta = golden
+    dd, dm = meta["dims"]["den"], meta["dims"]["mix"]
+    den = AttrDict(NAME="in2IN", NUM_LAYERS=dd["num_layers"], NUM_HEADS=dd["num_heads"], DROPOUT=0.1, INPUT_DIM=262,
+                   LATENT_DIM=dd["latent_dim"], FF_SIZE=dd["ff_size"], ACTIVATION="gelu", CHECKPOINT=None, STRATEGY="ddim50")
+    cfg = AttrDict(NAME="MixerMDM", MODEL1=AttrDict(den, NAME="in2INind"), MODEL2=den, ACTIVATION="gelu",
+                   MOTION_REP="global", CFG_WEIGHT=3.5, MIXING_MODE=4, DIFFUSION_STEPS=1000, BETA_SCHEDULER="cosine",
+                   SAMPLER="uniform", FORCE_INFLUENCE_VAL=None,
+                   GENERATOR=AttrDict(NUM_LAYERS=dm["n_blocks"], NUM_HEADS=dm["n_heads"], DROPOUT=0.1, INPUT_DIM=262,
+                                      LATENT_DIM=dm["latent_dim"], FF_SIZE=dm["ff_size"]),
+                   DISCRIMINATOR=AttrDict(NUM_LAYERS=1, NUM_HEADS=4, DROPOUT=0.1, INPUT_DIM=262, LATENT_DIM=64, FF_SIZE=128))
+    model = MixerMDM(cfg, normalizers=synth.normalizer_stats(), store_influence=False)
+    model.mixing.load_state_dict(synth.synthetic_state_dict(model.mixing.state_dict(), seed=meta["weights_seed"]), strict=True)
+    model = model.to(DEV)
+    g = torch.Generator().manual_seed(11)
+    lens, reps = [24, 17, 24, 24], [1, 2, 3, 1]
+    reqs = [MotionRequest(torch.randn(6144, generator=g).to(DEV), T, r, torch.randn(r, T, 524, generator=g).to(DEV))
+            for T, r in zip(lens, reps)]
+    (m1, s1), _ = synth.normalizer_stats()
+    gen = BatchedGenerator(model, max_length=32, normalizer=(m1, s1), max_batch=8)
+    res = gen.generate(reqs)
+    assert gen.calls == 2                                   # lengths {24, 17}: two sampler calls for four prompts
+    for r, got in zip(reqs, res):
+        one = model.forward_test({"cond": r.cond.unsqueeze(0).expand(r.repeats, -1).contiguous(), "noise": r.noise.clone(),
+                                  "motion_lens": torch.full((r.repeats,), r.motion_len, dtype=torch.long)})["output"]
+        want = format_generated(one, 32, m1, s1)
+        torch.cuda.synchronize()
+        assert got.shape == (r.repeats, 32, 2, 262)
+        assert torch.equal(got, want)

@@ -578,6 +578,27 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + C::BK - 1) / C::BK;
+  // Work items. The tiles that fill whole waves of the grid are 256 x 256; a short last wave (e.g. 8 of 600 tiles
+  // on 74 pairs - it would cost a full tile time with 66 pairs idle) is cut into 256 x 64 quarter tiles that spread
+  // over the grid. A quarter tile re-reads its A block and over-fetches B (the box stays 128 rows), so it is only
+  // used where it removes idle time.
+  const int full_tiles = (num_tiles / npairs) * npairs;
+  const int rem_tiles = num_tiles - full_tiles;
+  const bool split_tail = ep.split_tail && full_tiles > 0 && rem_tiles > 0 && 4 * rem_tiles <= npairs;
+  const int num_items = split_tail ? full_tiles + 4 * rem_tiles : num_tiles;
+  auto item_of = [&](int it, int& m_idx, int& n0, int& ncols) {
+    int tile = it, quarter = 0;
+    ncols = BN;
+    if (split_tail && it >= full_tiles) {
+      const int sub = it - full_tiles;
+      tile = full_tiles + (sub >> 2);
+      quarter = sub & 3;
+      ncols = BN / 4;
+    }
+    if (ep.rev) tile = num_tiles - 1 - tile;   // walk the tiles from the last row block down (see GemmEpi::rev)
+    m_idx = tile / num_n;
+    n0 = (tile % num_n) * BN + quarter * (BN / 4);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -604,10 +625,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = pair; it < num_tiles; it += npairs) {
-        const int tile = ep.rev ? num_tiles - 1 - it : it;
-        const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
-        const int n0 = (tile % num_n) * BN + (int)rank * (BN / 2);
+      for (int it = pair; it < num_items; it += npairs) {
+        int m_idx, n_item, ncols;
+        item_of(it, m_idx, n_item, ncols);
+        const int m0 = m_idx * (2 * C::BM) + (int)rank * C::BM;
+        const int n0 = n_item + (int)rank * (ncols / 2);   // each CTA supplies half of the item's weight rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * C::STAGE_BYTES;
@@ -625,7 +647,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * C::BM, BN);
+      constexpr uint32_t idesc_full = umma_idesc_bf16(2 * C::BM, BN), idesc_quarter = umma_idesc_bf16(2 * C::BM, BN / 4);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -636,7 +658,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint64_t da0 = umma_desc_k_sw128(smem_u32(smem));
       const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem) + C::A_BYTES);
       uint32_t soff = 0;
-      for (int tile = pair; tile < num_tiles; tile += npairs) {
+      for (int it = pair; it < num_items; it += npairs) {
+        const uint32_t idesc = (split_tail && it >= full_tiles) ? idesc_quarter : idesc_full;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -664,43 +687,57 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = warp & 3;
     const int part = (warp - 4) >> 2;                       // column part of the tile this warp drains
     constexpr int NPART = C::EPI_WARPS / 4, NCHUNK = BN / 32;
-    const int c0 = NPART == 2 ? part * 4 : part * 3;        // first chunk ...
-    const int cnt = NPART == 2 ? 4 : (part < 2 ? 3 : NCHUNK - 6);   // ... and chunk count
+    // chunks (32 columns) of an item this warp drains: a full tile has 8, a quarter tile 2
+    auto my_chunks = [&](int ncols, int& c0, int& cnt) {
+      if (ncols == BN) {
+        c0 = NPART == 2 ? part * 4 : part * 3;
+        cnt = NPART == 2 ? 4 : (part < 2 ? 3 : NCHUNK - 6);
+      } else {
+        c0 = part;
+        cnt = part < 2 ? 1 : 0;
+      }
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     const uint32_t stg = stg_base + (uint32_t)(warp - 4) * C::STG_WARP_BYTES;
     EpiBias<BN> bias = {}, bias_next = {};
-    // ep.rev walks the tiles from the last row block down (see GemmEpi::rev)
-    auto tile_of = [&](int it) { return ep.rev ? num_tiles - 1 - it : it; };
-    if (!transposed_mode(MODE) && pair < num_tiles)
-      bias_next = bias_fetch<BN, MODE>(ep, (tile_of(pair) % num_n) * BN, c0, lane, N);
-    for (int it = pair; it < num_tiles; it += npairs) {
-      const int tile = tile_of(it);
-      const int m0 = (tile / num_n) * (2 * C::BM) + (int)rank * C::BM;
-      const int n0 = (tile % num_n) * BN;
+    if (!transposed_mode(MODE) && pair < num_items) {
+      int mi, ni, nc, c0n, cntn;
+      item_of(pair, mi, ni, nc);
+      my_chunks(nc, c0n, cntn);
+      bias_next = bias_fetch<BN, MODE>(ep, ni, c0n, lane, N);
+    }
+    for (int it = pair; it < num_items; it += npairs) {
+      int m_idx, n0, ncols, c0, cnt;
+      item_of(it, m_idx, n0, ncols);
+      my_chunks(ncols, c0, cnt);
+      const int m0 = m_idx * (2 * C::BM) + (int)rank * C::BM;
       if (transposed_mode(MODE)) {
         bias = bias_fetch<BN, MODE>(ep, n0, c0, lane, N);
       } else if (MODE != EPI_FINAL) {
         bias_publish<BN>(bias_next, stg, lane);
-        if (it + npairs < num_tiles)
-          bias_next = bias_fetch<BN, MODE>(ep, (tile_of(it + npairs) % num_n) * BN, c0, lane, N);
+        if (it + npairs < num_items) {
+          int mi, ni, nc, c0n, cntn;
+          item_of(it + npairs, mi, ni, nc);
+          my_chunks(nc, c0n, cntn);
+          bias_next = bias_fetch<BN, MODE>(ep, ni, c0n, lane, N);
+        }
       }
-      if (MODE == EPI_RESID && ep.vec_ok) {
+      if (MODE == EPI_RESID && ep.vec_ok && cnt > 0) {
         const int col = n0 + c0 * 32;
         if (col < N) {
           const int r = m0 + q * 32 + lane;
           if (r < M) {
             const float* p = ep.resid + (size_t)r * ep.ldo + col;
-#pragma unroll
-            for (int i = 0; i < (BN / 2) * 4 / 128; ++i)
+            for (int i = 0; i < cnt; ++i)   // one 128-byte line per chunk of the row
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 32));
           }
         }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias);
+      if (cnt > 0) epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
@@ -846,6 +883,12 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
                "gemm: operands must be 16-byte aligned");
   MMDM_REQUIRE(ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   GemmEpi e2 = ep;
+  static int split_tail = -1;
+  if (split_tail < 0) {
+    const char* e = getenv("MMDM_GEMM_SPLIT_TAIL");   // A/B measurements: 0 keeps whole tiles in the last wave
+    split_tail = (e && e[0] == '0') ? 0 : 1;
+  }
+  e2.split_tail = split_tail;
   e2.vec_ok = ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (ep.ldo % 8) == 0 &&
                (ep.resid == nullptr || (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0) &&
                (ep.out_bf16 == nullptr || (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0) &&

@@ -39,6 +39,7 @@ struct GemmEpi {
   // Walk the output tiles from the last row block down (CTA-pair kernel only). The engine alternates the direction
   // from launch to launch so that a kernel starts on the rows its producer wrote last, which are still in L2.
   int rev = 0;
+  int split_tail = 0;                    // set by launch_gemm: cut a short last wave into quarter tiles (CTA-pair kernel)
   int vec_ok = 0;                        // set by launch_gemm: pointers/pitches allow 16-byte vector access
   int final_vec_ok = 0;                  // set by launch_gemm: EPI_FINAL rows allow 8-byte vector stores
 };

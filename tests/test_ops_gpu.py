@@ -25,7 +25,7 @@ def _relerr(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (300, 1024, 1024), (1200, 3072, 1024),
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (300, 1024, 1024), (1200, 3072, 1024), (4864, 1024, 256),
                                    (1000, 262, 1024), (777, 1536, 512), (600, 512, 264), (128, 2048, 2048)])
 def test_linear_bf16_bias(ops, M, N, K):
     from mixermdm_b200._lib import EPI_BF16
@@ -40,9 +40,12 @@ def test_linear_bf16_bias(ops, M, N, K):
     assert (out.float() - ref).abs().max().item() < 0.06
 
 
-def test_linear_gelu_resid_f32(ops):
+# (900, 512, 1024): fewer tiles than CTA pairs. (4864, 512, 1024): 76 / 38 pair tiles on 74 pairs -> the last wave is cut
+# into 256 x 64 quarter tiles (FFN-1: 2 tiles -> 8 quarters; FFN-2 has no short last wave: 38 tiles).
+# (4864, 1024, 1024): both GEMMs end in quarter tiles (76 tiles each).
+@pytest.mark.parametrize("M,D,F", [(900, 512, 1024), (4864, 512, 1024), (4864, 1024, 1024)])
+def test_linear_gelu_resid_f32(ops, M, D, F):
     from mixermdm_b200._lib import EPI_GELU_BF16, EPI_RESID, EPI_F32
-    M, D, F = 900, 512, 1024
     x = _rand((M, D), 4, dtype=torch.bfloat16)
     w1 = _rand((F, D), 5, 1 / math.sqrt(D), dtype=torch.bfloat16)
     b1 = _rand((F,), 6)

@@ -107,8 +107,10 @@ int launch_align(const float* out1, const float* out2, float* out1a, float* out2
 // Persistent 4-CTA clusters, one sample at a time per cluster; CTA `rank` owns frames [rank*FR, rank*FR+FR).
 // HBM latency under load is ~2 us, so an SM needs >= 100 KB of reads in flight to stream at its share of the
 // bandwidth (tools/micro/bulk_ring.cu). Shared memory is therefore ONE ring of 25 frame slots (4 rows of 2096 B,
-// one full / one empty mbarrier per slot) that two producer warps fill with cp.async.bulk - one row per lane -
-// far ahead of the 14 consumer warps, which take frames from a ticket counter in the order the ring is filled:
+// one mbarrier per slot) filled with cp.async.bulk. There are no producer warps: the 16 warps take frames from a
+// ticket counter in the order the ring is filled, and the warp that has just emptied a slot sends the copies of the
+// frame 25 positions further down the stream into it (lane 0 arms the barrier, lanes 0..3 send one row each), so a
+// slot is back in flight the moment its data is no longer needed:
 //   phase 1 of a sample, per frame: rows out1a, out2a of the cond and of the uncond half  -> mix, guidance,
 //           floor search; the guided prediction g goes to global memory (P.final_out doubles as that scratch:
 //           it is only a result at the last step) where it stays in L2,
@@ -119,9 +121,8 @@ int launch_align(const float* out1, const float* out2, float* out1a, float* out2
 // arrives) and the visibility of g have a whole phase to complete and the ring never drains at a phase boundary.
 // Streaming reads carry an L2 evict_first policy so that they do not push g out of L2.
 // ------------------------------------------------------------------------------------------------
-constexpr int MIX_CONSUMERS = 14;
-constexpr int MIX_PRODUCERS = 2;
-constexpr int MIX_THREADS = (MIX_CONSUMERS + MIX_PRODUCERS) * 32;
+constexpr int MIX_CONSUMERS = 16;
+constexpr int MIX_THREADS = MIX_CONSUMERS * 32;       // no producer warps: the warp that empties a slot refills it
 constexpr int MIX_CLUSTER = 4;                         // 4 SMs per sample: 33 clusters resident (8-CTA clusters: 15)
 constexpr int ROWF = 2 * NFEAT;                        // 524 floats per (sample, frame) row
 constexpr int ROWB = ROWF * 4;                         // 2096 bytes
@@ -149,8 +150,8 @@ __host__ __device__ inline MixLayout mix_layout() {
   L.ex_off = o;    o += 2 * (int)sizeof(MixExport);     // [sample parity]
   L.cx_off = o;    o += 2 * 2 * 8 * 4;                  // centring transforms [sample parity][person]
   o = (o + 15) / 16 * 16;
-  L.bar_off = o;   o += (2 * MIX_MAX_SLOTS + 1) * 8;    // full[] | empty[] | mid
-  L.ctr_off = o;   o += 16 + MIX_MAX_SLOTS * 4;         // p1_done, claims[2], slot_lap[]
+  L.bar_off = o;   o += (MIX_MAX_SLOTS + 1) * 8;        // full[] | mid
+  L.ctr_off = o;   o += 16 + MIX_MAX_SLOTS * 4;         // claims[2], slot_lap[]
   o = (o + 15) / 16 * 16;
   L.ring_off = o;
   int n = (MIX_SMEM_MAX - o) / SLOTB;
@@ -198,11 +199,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 // Monotonic counters, plain volatile shared-memory words (a release store compiles to MEMBAR.ALL.CTA):
-//   slot_lap[s]: how often the producer has acquired slot s. An mbarrier parity wait is only meaningful within one
+//   slot_lap[s]: how often slot s has been armed. An mbarrier parity wait is only meaningful within one
 //              phase of the barrier's current one and the consumers look further ahead than that, so a warp first
-//              waits until the producer has acquired the slot for its row - it has then seen the slot's previous
-//              use released, the slot's full barrier is in that row's phase - and only then on the barrier.
-//   p1_done  : samples whose phase 1 this CTA has finished (their g rows may be fetched).
+//              waits until the slot has been armed for its frame - its previous use is then over, the slot's
+//              barrier is in that frame's phase - and only then on the barrier.
 __device__ __forceinline__ void st_volatile_smem(int* p, int v) {
   asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
@@ -253,7 +253,7 @@ __device__ __forceinline__ void mix_wait(uint64_t* bar, uint32_t parity) {
 struct RowPos { int slot, lap; };
 __device__ __forceinline__ RowPos locate_row(int c, int NS, uint32_t ns_rcp) {
   RowPos r;
-  r.lap = (int)__umulhi((uint32_t)c, ns_rcp);
+  r.lap = NS == 1 ? c : (int)__umulhi((uint32_t)c, ns_rcp);   // (ceil(2^32 / 1) does not fit 32 bits)
   r.slot = c - r.lap * NS;
   return r;
 }
@@ -293,13 +293,12 @@ mixstep_kernel(const MixStepParams P) {
   MixExport* ex = reinterpret_cast<MixExport*>(smem + L.ex_off);
   float* cxs = reinterpret_cast<float*>(smem + L.cx_off);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* empty = full + MIX_MAX_SLOTS;
-  uint64_t* mid_bar = empty + MIX_MAX_SLOTS;
-  int* p1_done = reinterpret_cast<int*>(smem + L.ctr_off);
-  int* claims = p1_done + 1;      // frame tickets handed out so far, per phase
-  int* slot_lap = p1_done + 4;    // per slot: number of times the producer has acquired it
+  uint64_t* mid_bar = full + MIX_MAX_SLOTS;
+  int* claims = reinterpret_cast<int*>(smem + L.ctr_off);   // frame tickets handed out so far, per phase
+  int* slot_lap = claims + 4;                  // per slot: number of times it has been armed
   uint8_t* ring = smem + L.ring_off;
-  const int NS = L.nslots;
+  const int NS = min(L.nslots, max(nfr, 1));   // (a slot is refilled by the frame NS items later, which must not be a
+                                               //  later frame's phase 2 than the one being finished: NS <= nfr)
   const uint32_t ns_rcp = (uint32_t)((0x100000000ULL + NS - 1) / NS);
 
   const int step = P.mix_only ? 0 : *P.step_ptr;
@@ -308,11 +307,9 @@ mixstep_kernel(const MixStepParams P) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
     }
     mbar_init(mid_bar, MIX_CLUSTER);
     for (int i = 0; i < NS; ++i) slot_lap[i] = 0;
-    *p1_done = 0;
     claims[0] = 0;
     claims[1] = 0;
     fence_barrier_init();
@@ -328,61 +325,8 @@ mixstep_kernel(const MixStepParams P) {
   auto base_p1 = [&](int k) { return k * r1 + (k > 0 ? k - 1 : 0) * r2; };
   auto base_p2 = [&](int k) { return min(k + 1, S) * r1 + (k - 1) * r2; };   // P2(k-1), issued in stage k
 
-  if (warp >= MIX_CONSUMERS) {
-    // ---- producer warps: lane = (item of the group, row of the item); groups of 8 items alternate between the
-    // two warps. The lane of an item's first row waits for the slot, arms its barrier with the bytes of all rows and
-    // publishes the acquisition; the lanes of the other rows then send their copies.
-    const int pw = warp - MIX_CONSUMERS;
-    uint64_t pol_stream;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    const int li = lane >> 2, r = lane & 3;
-    for (int g = pw; g * 8 < total_items; g += MIX_PRODUCERS) {
-      const int c = g * 8 + li;
-      const long long tp0 = tr ? clock64() : 0;
-      if (c < total_items) {
-        // decode c -> (sample, phase, frame)
-        int n, fl;
-        bool p1;
-        if (c < r1) {
-          n = 0; fl = c; p1 = true;
-        } else {
-          const int cp = c - r1, k = 1 + cp / (r1 + r2), rem = cp - (k - 1) * (r1 + r2);
-          if (k < S && rem < r1) { n = k; fl = rem; p1 = true; }
-          else { n = k - 1; fl = k < S ? rem - r1 : rem; p1 = false; }
-        }
-        const int rows = p1 ? R1 : R2;
-        if (r < rows) {
-          const int b = cluster_id + n * nclusters;
-          const float* src;
-          if (p1) src = ((r & 1) ? P.out2a : P.out1a) + ((size_t)((r >> 1) * B + b) * T + t_begin + fl) * ROWF;
-          else src = (r == 0 ? P.x1 : r == 1 ? P.x2 : P.final_out) + ((size_t)b * T + t_begin + fl) * ROWF;
-          const RowPos rp = locate_row(c, NS, ns_rcp);
-          if (r == 0) {
-            if (rp.lap > 0) {
-              // the slot's previous use may belong to the other producer warp: once that one has acquired it, the
-              // empty barrier is in the phase this wait means (a parity wait must not be a whole phase early)
-              spin_until(slot_lap + rp.slot, rp.lap, "slot_lap (producer)");
-              mix_wait(&empty[rp.slot], (uint32_t)(rp.lap - 1) & 1u);
-            }
-            mbar_arrive_expect_tx(&full[rp.slot], (uint32_t)rows * ROWB);
-            st_volatile_smem(slot_lap + rp.slot, rp.lap + 1);
-          } else {
-            spin_until(slot_lap + rp.slot, rp.lap + 1, "slot_lap (row lane)");
-          }
-          if (!p1 && r == 2) {   // g of this frame was written by this CTA's consumers in phase 1 of sample n
-            spin_until(p1_done, n + 1, "p1_done");
-            fence_proxy_async_all();
-          }
-          bulk_g2s_hint(smem_u32(ring + (size_t)rp.slot * SLOTB + r * ROWB), src, ROWB, smem_u32(&full[rp.slot]),
-                        pol_stream);
-        }
-      }
-      const long long tp1 = tr ? clock64() : 0;
-      __syncwarp();
-      mix_trace(tr, warp, ntr, (3LL << 32) | g, tp0, tp1, tr ? clock64() : 0);
-    }
-  } else {
-    // ---- consumer warps --------------------------------------------------------------------------
+  {
+    // ---- every warp is a consumer (and refills the slots it empties) --------------------------------------------------------------------------
     // Frames are handed out dynamically (one shared-memory ticket counter per phase) so that the ring is consumed
     // in the order it is filled - a warp held up by the cluster exchange or a late row does not sit on slots the
     // others are waiting behind. Every warp holds the ticket of its NEXT frame while it works on the current one:
@@ -444,6 +388,73 @@ mixstep_kernel(const MixStepParams P) {
     // DDIM update with the normalisation folded in: x' = A pred + Bc x, pred = (g - mean) / std
     //   (gaussian_diffusion.py:1936-1965 with eta = 0: x' = pred sqrt(ab_prev) + sqrt(1 - ab_prev) eps,
     //    eps = (sqrt(1/ab) x - pred) / sqrt(1/ab - 1))  ->  x' = TA g + TB + Bc x with per-feature tables TA, TB
+    // Arm slot (c % NS) with item c of the stream: lane 0 arms the barrier with the bytes of all rows and publishes
+    // the acquisition, lanes 0..3 send one row copy each. Called by the warp that has just emptied the slot (item
+    // c - NS), so a slot is back in flight the moment its data is no longer needed, and at start-up for the first
+    // NS items. The g row of a phase-2 item waits for the flag of its frame (set by the warp that wrote the row in
+    // phase 1: an earlier ticket, so that warp does not depend on this one).
+    uint64_t pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    // send the rows of item (phase p1, sample n, frame fl) into slot rp: lane 0 arms the barrier and publishes the
+    // acquisition, lanes 0..3 send one row copy each
+    auto arm_item = [&](bool p1, int n, int fl, RowPos rp, bool defer_g) {
+      const int rows = p1 ? R1 : R2;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[rp.slot], (uint32_t)rows * ROWB);
+        st_volatile_smem(slot_lap + rp.slot, rp.lap + 1);
+      }
+      __syncwarp();
+      if (lane < rows) {
+        const int r = lane;
+        const int b = cluster_id + n * nclusters;
+        const float* src;
+        if (p1) src = ((r & 1) ? P.out2a : P.out1a) + ((size_t)((r >> 1) * B + b) * T + t_begin + fl) * ROWF;
+        else src = (r == 0 ? P.x1 : r == 1 ? P.x2 : P.final_out) + ((size_t)b * T + t_begin + fl) * ROWF;
+        if (!(defer_g && !p1 && r == 2))
+          bulk_g2s_hint(smem_u32(ring + (size_t)rp.slot * SLOTB + r * ROWB), src, ROWB, smem_u32(&full[rp.slot]), pol_stream);
+      }
+      __syncwarp();
+    };
+    // Refill the slot a warp has just emptied with the item NS positions further down the stream (same slot, next
+    // lap), which lies in the current segment or the one after it (NS <= nfr). Segments: P1(0), then
+    // [P1(k), P2(k-1)] for k = 1..S-1, then P2(S-1); without a phase 2 just P1(0..S-1).
+    // The g row of a phase-2 item was written (and fenced for the async proxy) before the consumer barrier that ended
+    // phase 1 of its sample. That barrier lies behind this warp unless the item is armed from that very phase 1 (only
+    // with one sample per cluster): those rows are sent right after the barrier (send_deferred_g).
+    auto rearm = [&](bool cur_p1, int n_cur, int f, RowPos cur) {
+      int t = f + NS, n = n_cur;
+      bool p1 = cur_p1;
+      if (t >= nfr) {
+        t -= nfr;
+        if (r2 == 0) { n = n_cur + 1; }                              // P1(n) -> P1(n+1)
+        else if (cur_p1) {
+          if (n_cur >= 1) { p1 = false; n = n_cur - 1; }             // P1(k) -> P2(k-1)
+          else if (S > 1) { n = 1; }                                 // P1(0) -> P1(1)
+          else { p1 = false; n = 0; }                                // P1(0) -> P2(0)   (one sample)
+        } else {
+          if (n_cur + 2 < S) { p1 = true; n = n_cur + 2; }           // P2(j) -> P1(j+2)
+          else { n = n_cur + 1; }                                    // P2(j) -> P2(j+1)
+        }
+        if (n >= S) return;                                          // end of the stream
+      }
+      RowPos rp = cur;
+      ++rp.lap;
+      arm_item(p1, n, t, rp, cur_p1 && S == 1);
+    };
+    auto send_deferred_g = [&]() {   // S == 1: g rows of the phase-2 frames 0 .. NS-1, whose slots were armed during phase 1
+      for (int fl = warp; fl < min(NS, nfr); fl += MIX_CONSUMERS) {
+        if (lane == 0) {
+          const RowPos rp = locate_row(r1 + fl, NS, ns_rcp);
+          bulk_g2s_hint(smem_u32(ring + (size_t)rp.slot * SLOTB + 2 * ROWB),
+                        P.final_out + ((size_t)cluster_id * T + t_begin + fl) * ROWF, ROWB, smem_u32(&full[rp.slot]), pol_stream);
+        }
+      }
+    };
+    for (int c = warp; c < min(NS, total_items); c += MIX_CONSUMERS) {   // start-up: the first NS items are P1(0) frames
+      RowPos rp; rp.slot = c; rp.lap = 0;
+      arm_item(true, 0, c, rp, false);
+    }
+
     const int tickets = S * nfr;
     int next1 = nfr > 0 ? claim(0) : tickets, next2 = (nfr > 0 && phase2) ? claim(1) : tickets;
     int nk1 = 0;   // sample of ticket next1 (tickets only grow: no division)
@@ -568,9 +579,7 @@ mixstep_kernel(const MixStepParams P) {
             }
           }
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&empty[ip.slot]);
-          }
+          rearm(true, k, fl, ip);   // the slot goes straight back into flight with the frame NS items ahead
           mix_trace(tr, warp, ntr, (1LL << 32) | (k * nfr + fl), tc0, tc1, tr ? clock64() : 0);
         }
         if (phase2) {
@@ -578,9 +587,10 @@ mixstep_kernel(const MixStepParams P) {
           ym1 = warp_min(ym1);
           float* yw = ymin_w + (k & 1) * (MIX_CONSUMERS * 2);
           if (lane == 0) { yw[warp * 2] = ym0; yw[warp * 2 + 1] = ym1; }
-          fence_proxy_async_all();   // my g stores are ordered before the producers' bulk reads of them
+          fence_proxy_async_all();   // my g stores are ordered before the bulk reads of those rows in phase 2
           const long long ts0 = tr ? clock64() : 0;
           consumer_sync();
+          if (S == 1) send_deferred_g();
           mix_trace(tr, warp, ntr, (4LL << 32) | k, ts0, tr ? clock64() : 0, 0);
           if (warp == 0) {
             MixExport* exk = ex + (k & 1);
@@ -593,7 +603,6 @@ mixstep_kernel(const MixStepParams P) {
               const int p = lane / 9, e = lane - p * 9;
               exk->f0[p][e] = __ldcg(P.final_out + (size_t)b * T * ROWF + p * NFEAT + e);
             }
-            if (lane == 0) st_volatile_smem(p1_done, k + 1);
             __syncwarp();
             if (lane < MIX_CLUSTER) mbar_arrive_remote_release(mapa_u32(smem_u32(mid_bar), (uint32_t)lane));
             mbar_wait_cluster(mid_bar, (uint32_t)k & 1u);
@@ -692,9 +701,7 @@ mixstep_kernel(const MixStepParams P) {
           }
           fence_proxy_async_smem();   // the centring wrote into the slot: order it before the next bulk copy into it
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&empty[ip.slot]);
-          }
+          rearm(false, n, fl, ip);
           mix_trace(tr, warp, ntr, (2LL << 32) | (n * nfr + fl), tc0, tc1, tr ? clock64() : 0);
         }
       }

@@ -105,6 +105,8 @@ typedef struct mmdm_mixstep_args {
                                 ((c*B+b)*2+p) (pooled modes 1,3); 1 (modes 1,2) or 23 (modes 3,4) valid columns */
   const float* out1a; const float* out2a;  /* (ncfg*B,T,524) aligned predictions */
   float* x1; float* x2;      /* (B,T,524) state streams, updated in place */
+  /* out1a/out2a and x1/x2 are dense (.,T,524) buffers, or interleaved row by row - [out1a row | out2a row] with
+     out2a == out1a + 524, likewise x2 == x1 + 524 - which the kernel fetches with one bulk copy per pair of rows */
   float* final_out;          /* (B,T,524): the guided prediction of the step. The result at index 0; at every other
                                 index the kernel's own hand-over buffer between its two phases (contents = the raw
                                 guided prediction of that step) */

@@ -208,13 +208,15 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
   ws.zero_row = c.take<float>(h->cfg.text_dim);
   ws.out1 = c.take<float>((size_t)Bx * T * nf2);
   ws.out2 = c.take<float>((size_t)Bx * T * nf2);
-  ws.out1a = c.take<float>((size_t)Bx * T * nf2);
-  ws.out2a = c.take<float>((size_t)Bx * T * nf2);
+  // aligned predictions and sampler state: the two buffers of each pair are interleaved row by row
+  // ([out1a row | out2a row], [x1 row | x2 row]), so the fused mix kernel fetches a pair with one 4192-byte bulk copy
+  ws.out1a = c.take<float>((size_t)2 * Bx * T * nf2);
+  ws.out2a = ws.out1a ? ws.out1a + nf2 : nullptr;
   ws.hfin = c.take<bf16>(M * h->net[2].w.D);
   ws.hpool = c.take<bf16>((size_t)S * h->net[2].w.D);
   ws.wmix = c.take<float>(M * 24);
-  ws.x1 = c.take<float>((size_t)B * T * nf2);
-  ws.x2 = c.take<float>((size_t)B * T * nf2);
+  ws.x1 = c.take<float>((size_t)2 * B * T * nf2);
+  ws.x2 = ws.x1 ? ws.x1 + nf2 : nullptr;
   ws.final = c.take<float>((size_t)B * T * nf2);
   ws.step = c.take<int>(4);
   ws.ts_idx = c.take<int>(h->cfg.nsteps);
@@ -364,7 +366,8 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
 // dup != 0, shared by the two CFG halves (Bx = 2*Bu). out: (Bx, T, persons*nfeats), de-normalised when
 // std/mean are given.
 static int run_denoiser(mmdm_handle* h, int ni, const float* x, int Bu, int dup, int persons, const float* temb,
-                        const int* step_ptr, float* out, const float* stdv, const float* meanv, cudaStream_t st) {
+                        const int* step_ptr, float* out, const float* stdv, const float* meanv, cudaStream_t st,
+                        int x_pitch = 0) {
   Net& n = h->net[ni];
   Workspace& ws = h->ws;
   const int T = h->T, D = n.w.D, nf = h->cfg.nfeats, kpad = h->cfg.kpad;
@@ -374,7 +377,7 @@ static int run_denoiser(mmdm_handle* h, int ni, const float* x, int Bu, int dup,
   MMDM_TRY(run_conditioning(h, ni, S, temb, step_ptr, st));
   {
     Scope sc(h, "pack_state", st);
-    MMDM_TRY(launch_pack_state(x, Bu, T, nf, kpad, persons, ws.xin, st));
+    MMDM_TRY(launch_pack_state(x, Bu, T, nf, kpad, persons, ws.xin, st, x_pitch));
   }
   GemmEpi ee;
   ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
@@ -422,22 +425,22 @@ static const int COL_INTER = 0, COL_IND = 3 * 768, COL_MIX = 5 * 768;
 
 // the Mixer body after conditioning tables are in place. Bu unique rows (+dup) as in run_denoiser.
 static int run_mixer_nets(mmdm_handle* h, const float* x1, const float* x2, int Bu, int dup, const float* const temb[3],
-                          const int* step_ptr, cudaStream_t st) {
+                          const int* step_ptr, cudaStream_t st, int x_pitch = 0) {
   Workspace& ws = h->ws;
   const int T = h->T, nf = h->cfg.nfeats, kpad = h->cfg.kpad;
   const int Bx = dup ? 2 * Bu : Bu, S = 2 * Bx, M = S * T;
   const int Bt = Bu;
   // individual denoiser on both persons (text slices: cond1_1, cond1_2)
   MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bt, dup, 2, 0, st));
-  MMDM_TRY(run_denoiser(h, 0, x1, Bu, dup, 2, temb[0], step_ptr, ws.out1, h->cfg.std1, h->cfg.mean1, st));
+  MMDM_TRY(run_denoiser(h, 0, x1, Bu, dup, 2, temb[0], step_ptr, ws.out1, h->cfg.std1, h->cfg.mean1, st, x_pitch));
   // interaction denoiser (text slices: emb, emb_individual1, emb_individual2)
   MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bt, dup, 3, 1, st));
-  MMDM_TRY(run_denoiser(h, 1, x2, Bu, dup, 2, temb[1], step_ptr, ws.out2, h->cfg.std2, h->cfg.mean2, st));
+  MMDM_TRY(run_denoiser(h, 1, x2, Bu, dup, 2, temb[1], step_ptr, ws.out2, h->cfg.std2, h->cfg.mean2, st, x_pitch));
   // alignment + Mixer embedding
   {
     Scope sc(h, "align", st, 0, (double)Bx * T * (2.0 * nf) * 4 * 4 + 2.0 * M * kpad * 2);
     MMDM_TRY(launch_align(ws.out1, ws.out2, ws.out1a, ws.out2a, ws.xin, ws.xin + (size_t)M * kpad, Bx, T, kpad,
-                          h->cfg.align, st));
+                          h->cfg.align, st, 2 * 2 * nf));
   }
   Net& n = h->net[2];
   const int D = n.w.D;
@@ -478,6 +481,7 @@ static MixStepParams mix_params(mmdm_handle* h) {
   P.cfg_scale = h->cfg.cfg_scale; P.step_ptr = h->ws.step; P.nsteps = h->cfg.nsteps; P.coef = h->cfg.coef;
   P.weights = h->ws.wmix;
   P.out1a = h->ws.out1a; P.out2a = h->ws.out2a; P.x1 = h->ws.x1; P.x2 = h->ws.x2; P.final_out = nullptr;
+  P.pred_pitch = P.state_pitch = 2 * 2 * h->cfg.nfeats;
   P.mean1 = h->cfg.mean1; P.std1 = h->cfg.std1; P.mean2 = h->cfg.mean2; P.std2 = h->cfg.std2;
   P.hist_i1 = nullptr; P.hist_i2 = nullptr;
   return P;
@@ -502,15 +506,16 @@ static int step_body(mmdm_handle* h, float* final_out, float* h1, float* h2, cud
                      const EvalHist* eh = nullptr) {
   const float* temb[3] = {h->ws.temb_tab[0], h->ws.temb_tab[1], h->ws.temb_tab[2]};
   h->rev = 0;
-  MMDM_TRY(run_mixer_nets(h, h->ws.x1, h->ws.x2, h->B, 1, temb, h->ws.step, st));
+  MMDM_TRY(run_mixer_nets(h, h->ws.x1, h->ws.x2, h->B, 1, temb, h->ws.step, st, 2 * 2 * h->cfg.nfeats));
   MMDM_TRY(run_head(h, 4 * h->B, h->T, st));
   MixStepParams P = mix_params(h);
   P.final_out = final_out ? final_out : h->ws.final;
   P.hist_i1 = h1; P.hist_i2 = h2;
   if (eh != nullptr && eh->out1 != nullptr) {
     const size_t n = (size_t)2 * h->B * h->T * 2 * h->cfg.nfeats;
-    MMDM_CHECK_CUDA(cudaMemcpyAsync(eh->out1 + n * eh->slot, h->ws.out1a, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    MMDM_CHECK_CUDA(cudaMemcpyAsync(eh->out2 + n * eh->slot, h->ws.out2a, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const size_t rowb = (size_t)2 * h->cfg.nfeats * sizeof(float), nrows = (size_t)2 * h->B * h->T;
+    MMDM_CHECK_CUDA(cudaMemcpy2DAsync(eh->out1 + n * eh->slot, rowb, h->ws.out1a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+    MMDM_CHECK_CUDA(cudaMemcpy2DAsync(eh->out2 + n * eh->slot, rowb, h->ws.out2a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
     P.mix_out = eh->mix + n * eh->slot;
   }
   {
@@ -635,8 +640,10 @@ int mmdm_set_state(mmdm_handle* h, const float* x1, const float* x2, int step_in
   MMDM_REQUIRE(step_index >= 0 && step_index < h->cfg.nsteps, "mmdm_set_state: step index %d out of range", step_index);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
-  MMDM_CHECK_CUDA(cudaMemcpyAsync(h->ws.x1, x1, bytes, cudaMemcpyDeviceToDevice, st));
-  MMDM_CHECK_CUDA(cudaMemcpyAsync(h->ws.x2, x2, bytes, cudaMemcpyDeviceToDevice, st));
+  const size_t rowb = (size_t)2 * h->cfg.nfeats * sizeof(float), nrows = (size_t)h->B * h->T;   // (x1 | x2 interleaved rows)
+  (void)bytes;
+  MMDM_CHECK_CUDA(cudaMemcpy2DAsync(h->ws.x1, 2 * rowb, x1, rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+  MMDM_CHECK_CUDA(cudaMemcpy2DAsync(h->ws.x2, 2 * rowb, x2, rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
   MMDM_TRY(launch_set_int(h->ws.step, step_index, st));
   return 0;
 }
@@ -645,8 +652,10 @@ int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream) {
   MMDM_REQUIRE(h && h->ws_base, "mmdm_get_state: handle not bound");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
-  if (x1) MMDM_CHECK_CUDA(cudaMemcpyAsync(x1, h->ws.x1, bytes, cudaMemcpyDeviceToDevice, st));
-  if (x2) MMDM_CHECK_CUDA(cudaMemcpyAsync(x2, h->ws.x2, bytes, cudaMemcpyDeviceToDevice, st));
+  const size_t rowb = (size_t)2 * h->cfg.nfeats * sizeof(float), nrows = (size_t)h->B * h->T;
+  (void)bytes;
+  if (x1) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(x1, rowb, h->ws.x1, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+  if (x2) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(x2, rowb, h->ws.x2, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -724,7 +733,7 @@ int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const i
   MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 3, 1, st));
   MMDM_TRY(run_denoiser(h, 1, x2, Bx, 0, 2, ws.temb_dyn, nullptr, ws.out2, h->cfg.std2, h->cfg.mean2, st));
   MMDM_TRY(launch_align(ws.out1, ws.out2, ws.out1a, ws.out2a, ws.xin, ws.xin + (size_t)M * kpad, Bx, T, kpad,
-                        h->cfg.align, st));
+                        h->cfg.align, st, 2 * 2 * nf));
   Net& n = h->net[2];
   const int D = n.w.D;
   MMDM_TRY(run_time_embed(h, 2, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
@@ -748,8 +757,10 @@ int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const i
   P.hist_i1 = infl_i1; P.hist_i2 = infl_i2;
   MMDM_TRY(launch_mixstep(P, st));
   const size_t bytes = (size_t)Bx * T * 2 * nf * sizeof(float);
-  if (out1) MMDM_CHECK_CUDA(cudaMemcpyAsync(out1, ws.out1a, bytes, cudaMemcpyDeviceToDevice, st));
-  if (out2) MMDM_CHECK_CUDA(cudaMemcpyAsync(out2, ws.out2a, bytes, cudaMemcpyDeviceToDevice, st));
+  const size_t rowb = (size_t)2 * nf * sizeof(float), nrows = (size_t)Bx * T;
+  (void)bytes;
+  if (out1) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(out1, rowb, ws.out1a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+  if (out2) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(out2, rowb, ws.out2a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -785,6 +796,10 @@ int mmdm_mix_cfg_ddim(const mmdm_mixstep_args* a, void* stream) {
   P.step_ptr = a->step_ptr; P.nsteps = a->nsteps; P.coef = a->coef;
   P.weights = a->weights;
   P.out1a = a->out1a; P.out2a = a->out2a; P.x1 = a->x1; P.x2 = a->x2; P.final_out = a->final_out;
+  // dense (.,T,524) buffers, or - recognised by out2a == out1a + 524 (x2 == x1 + 524), which dense buffers cannot
+  // satisfy - the two interleaved row by row ([out1a row | out2a row], pitch 1048): one bulk copy per pair of rows
+  P.pred_pitch = (a->out2a == a->out1a + 524) ? 1048 : 524;
+  P.state_pitch = (a->x1 != nullptr && a->x2 == a->x1 + 524) ? 1048 : 524;
   P.mean1 = a->mean1; P.std1 = a->std1; P.mean2 = a->mean2; P.std2 = a->std2;
   P.hist_i1 = a->hist_i1; P.hist_i2 = a->hist_i2;
   if (!P.mix_only)

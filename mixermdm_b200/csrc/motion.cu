@@ -28,7 +28,7 @@ constexpr int ALIGN_WARPS = 8;
 __global__ void __launch_bounds__(ALIGN_WARPS * 32)
 align_kernel(const float* __restrict__ out1, const float* __restrict__ out2, float* __restrict__ out1a,
              float* __restrict__ out2a, __nv_bfloat16* __restrict__ emb_i, __nv_bfloat16* __restrict__ emb_I,
-             int Be, int T, int kpad, int do_align) {
+             int Be, int T, int kpad, int do_align, int pitch_a) {
   __shared__ float buf[ALIGN_WARPS][4][NFEAT + 2];  // [model*2 + person][feature]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ALIGN_WARPS + warp;
@@ -76,8 +76,8 @@ align_kernel(const float* __restrict__ out1, const float* __restrict__ out2, flo
     if (lane < 8) b[lane >> 2][OFF_FC + (lane & 3)] = 0.f;  // align_motions drops the foot contacts (201-d)
   }
   __syncwarp();
-  float* w1 = out1a + ((size_t)be * T + t) * (2 * NFEAT);
-  float* w2 = out2a + ((size_t)be * T + t) * (2 * NFEAT);
+  float* w1 = out1a + ((size_t)be * T + t) * pitch_a;
+  float* w2 = out2a + ((size_t)be * T + t) * pitch_a;
   for (int f = lane; f < 2 * NFEAT; f += 32) {
     const int p = f >= NFEAT, fi = f - p * NFEAT;
     w1[f] = b[p][fi];
@@ -93,10 +93,10 @@ align_kernel(const float* __restrict__ out1, const float* __restrict__ out2, flo
 }
 
 int launch_align(const float* out1, const float* out2, float* out1a, float* out2a, __nv_bfloat16* emb_i,
-                 __nv_bfloat16* emb_I, int Be, int T, int kpad, int do_align, cudaStream_t stream) {
+                 __nv_bfloat16* emb_I, int Be, int T, int kpad, int do_align, cudaStream_t stream, int pitch_a) {
   const long long items = (long long)Be * T;
   const unsigned blocks = (unsigned)((items + ALIGN_WARPS - 1) / ALIGN_WARPS);
-  align_kernel<<<blocks, ALIGN_WARPS * 32, 0, stream>>>(out1, out2, out1a, out2a, emb_i, emb_I, Be, T, kpad, do_align);
+  align_kernel<<<blocks, ALIGN_WARPS * 32, 0, stream>>>(out1, out2, out1a, out2a, emb_i, emb_I, Be, T, kpad, do_align, pitch_a);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -397,6 +397,9 @@ mixstep_kernel(const MixStepParams P) {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
     // send the rows of item (phase p1, sample n, frame fl) into slot rp: lane 0 arms the barrier and publishes the
     // acquisition, lanes 0..3 send one row copy each
+    // When out1a|out2a (x1|x2) are interleaved row by row, a pair of rows is one contiguous 4192-byte copy.
+    const bool pred_pairs = P.out2a == P.out1a + ROWF && P.pred_pitch == 2 * ROWF;
+    const bool state_pairs = P.x2 == P.x1 + ROWF && P.state_pitch == 2 * ROWF;
     auto arm_item = [&](bool p1, int n, int fl, RowPos rp, bool defer_g) {
       const int rows = p1 ? R1 : R2;
       if (lane == 0) {
@@ -407,11 +410,18 @@ mixstep_kernel(const MixStepParams P) {
       if (lane < rows) {
         const int r = lane;
         const int b = cluster_id + n * nclusters;
-        const float* src;
-        if (p1) src = ((r & 1) ? P.out2a : P.out1a) + ((size_t)((r >> 1) * B + b) * T + t_begin + fl) * ROWF;
-        else src = (r == 0 ? P.x1 : r == 1 ? P.x2 : P.final_out) + ((size_t)b * T + t_begin + fl) * ROWF;
-        if (!(defer_g && !p1 && r == 2))
-          bulk_g2s_hint(smem_u32(ring + (size_t)rp.slot * SLOTB + r * ROWB), src, ROWB, smem_u32(&full[rp.slot]), pol_stream);
+        const uint32_t dst = smem_u32(ring + (size_t)rp.slot * SLOTB + r * ROWB), bar = smem_u32(&full[rp.slot]);
+        if (p1) {
+          const float* row = P.out1a + ((size_t)((r >> 1) * B + b) * T + t_begin + fl) * P.pred_pitch;
+          if (pred_pairs) { if (!(r & 1)) bulk_g2s_hint(dst, row, 2 * ROWB, bar, pol_stream); }
+          else bulk_g2s_hint(dst, (r & 1) ? row + (P.out2a - P.out1a) : row, ROWB, bar, pol_stream);
+        } else if (r < 2) {
+          const float* row = P.x1 + ((size_t)b * T + t_begin + fl) * P.state_pitch;
+          if (state_pairs) { if (r == 0) bulk_g2s_hint(dst, row, 2 * ROWB, bar, pol_stream); }
+          else bulk_g2s_hint(dst, r ? row + (P.x2 - P.x1) : row, ROWB, bar, pol_stream);
+        } else if (!defer_g) {
+          bulk_g2s_hint(dst, P.final_out + ((size_t)b * T + t_begin + fl) * ROWF, ROWB, bar, pol_stream);
+        }
       }
       __syncwarp();
     };
@@ -640,7 +650,7 @@ mixstep_kernel(const MixStepParams P) {
           const int fl = next2 - n * nfr;
           next2 = claim(1);
           const int t = t_begin + fl;
-          const size_t rx = ((size_t)b * T + t) * ROWF;
+          const size_t rx = ((size_t)b * T + t) * P.state_pitch;
           float4* const x1p = reinterpret_cast<float4*>(P.x1 + rx) + lane;
           float4* const x2p = reinterpret_cast<float4*>(P.x2 + rx) + lane;
           const long long tc0 = tr ? clock64() : 0;
@@ -728,6 +738,8 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
   MMDM_REQUIRE(P.mode >= 1 && P.mode <= 4, "Mixing mode not recognized (%d)", P.mode);
   MMDM_REQUIRE(P.T >= 1 && P.B >= 1 && (long long)P.B * P.T * 12 < (1LL << 31), "mixstep: bad shape B=%d T=%d", P.B, P.T);
   MMDM_REQUIRE(P.ncfg == 1 || P.ncfg == 2, "mixstep: ncfg must be 1 or 2 (got %d)", P.ncfg);
+  MMDM_REQUIRE(P.pred_pitch >= 524 && (P.pred_pitch % 4) == 0 && (P.mix_only || (P.state_pitch >= 524 && (P.state_pitch % 4) == 0)),
+               "mixstep: row pitches must be multiples of 4 floats, at least 524 (got %d, %d)", P.pred_pitch, P.state_pitch);
   MMDM_REQUIRE(P.weights != nullptr, "mixstep: Mixer weights missing");
   MMDM_REQUIRE(((reinterpret_cast<uintptr_t>(P.out1a) | reinterpret_cast<uintptr_t>(P.out2a) |
                  reinterpret_cast<uintptr_t>(P.weights) | reinterpret_cast<uintptr_t>(P.x1) |

@@ -5,8 +5,9 @@ namespace mmdm {
 
 // out1/out2: (Be,T,524) fp32 de-normalised predictions (individual / interaction model).
 // out1a/out2a: aligned copies; emb_i/emb_I: bf16 rows ((be*2+p)*T+t, kpad) for the Mixer's motion_embed.
+// pitch_a: floats between consecutive (be,t) rows of out1a / out2a (524, or 1048 when the two are interleaved row by row)
 int launch_align(const float* out1, const float* out2, float* out1a, float* out2a, __nv_bfloat16* emb_i,
-                 __nv_bfloat16* emb_I, int Be, int T, int kpad, int do_align, cudaStream_t stream);
+                 __nv_bfloat16* emb_I, int Be, int T, int kpad, int do_align, cudaStream_t stream, int pitch_a = 524);
 
 struct MixStepParams {
   int B, T, mode;                    // un-doubled batch, frames, mixing mode 1..4
@@ -22,8 +23,11 @@ struct MixStepParams {
   int nsteps;
   const float* coef;                 // [nsteps][4] = sqrt_recip_ab, sqrt_recipm1_ab, sqrt(ab_prev), sqrt(1-ab_prev)
   const float* weights;              // sigmoid(head) rows, pitch 24: per token (modes 2,4) or per sequence (1,3)
-  const float* out1a;                // (2B,T,524)
+  const float* out1a;                // (2B,T,524) rows with pitch pred_pitch
   const float* out2a;
+  int pred_pitch;                    // floats between consecutive (b,t) rows of out1a / out2a: 524, or 1048 when the two
+                                     // buffers are interleaved row by row (out2a == out1a + 524): one bulk copy per pair
+  int state_pitch;                   // same for x1 / x2
   float* x1;                         // (B,T,524) state, individual space (updated in place)
   float* x2;                         // (B,T,524) state, interaction space
   float* final_out;                  // (B,T,524) guided prediction: the result at step index 0, otherwise the

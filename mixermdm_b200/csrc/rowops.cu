@@ -225,7 +225,7 @@ int launch_small_linear(const float* a, int lda, const float* w, const float* b,
 // state (B, T, persons*nf) fp32 -> bf16 GEMM operand rows ((b*persons+p)*T + t, kpad), zero padded to kpad.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_state_kernel(const float* __restrict__ x, int B, int T, int nf, int kpad, int persons,
-                                  __nv_bfloat16* __restrict__ out) {
+                                  int row_pitch, __nv_bfloat16* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * persons * T * kpad;
   if (idx >= total) return;
@@ -235,14 +235,15 @@ __global__ void pack_state_kernel(const float* __restrict__ x, int B, int T, int
   const int sp = (int)(row / T);
   const int b = sp / persons, p = sp - b * persons;
   float v = 0.f;
-  if (k < nf) v = x[((size_t)b * T + t) * (persons * nf) + p * nf + k];
+  if (k < nf) v = x[((size_t)b * T + t) * row_pitch + p * nf + k];
   out[idx] = __float2bfloat16_rn(v);
 }
 
 int launch_pack_state(const float* x, int B, int T, int nf, int kpad, int persons, __nv_bfloat16* out,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int row_pitch) {
+  if (row_pitch <= 0) row_pitch = persons * nf;
   const long long total = (long long)B * persons * T * kpad;
-  pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, B, T, nf, kpad, persons, out);
+  pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, B, T, nf, kpad, persons, row_pitch, out);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

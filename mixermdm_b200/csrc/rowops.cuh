@@ -22,9 +22,9 @@ int launch_gather_rows(const float* table, int rows, const long long* idx64, con
 int launch_small_linear(const float* a, int lda, const float* w, const float* b, float* out, int ldo, int R,
                         int N, int K, int act, cudaStream_t stream);
 
-// (B,T,persons*nf) fp32 -> ((b*persons+p)*T+t, kpad) bf16, zero padded
+// (B,T,persons*nf) fp32 [rows row_pitch floats apart; 0 = dense] -> ((b*persons+p)*T+t, kpad) bf16, zero padded
 int launch_pack_state(const float* x, int B, int T, int nf, int kpad, int persons, __nv_bfloat16* out,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int row_pitch = 0);
 
 int launch_set_int(int* p, int v, cudaStream_t stream);
 int launch_add_int(int* p, int v, cudaStream_t stream);

@@ -16,14 +16,21 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--frames", type=int, default=300)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--dense", action="store_true", help="separate out1a/out2a and x1/x2 buffers instead of the engine's "
+                                                     "row-interleaved pairs")
 a = ap.parse_args()
 lib = _lib.load()
 B, T, dev = a.batch, a.frames, "cuda"
 sched = schedule.SpacedSchedule(schedule.space_timesteps(1000, "ddim50"), schedule.get_named_beta_schedule("cosine", 1000))
 g = torch.Generator(device=dev).manual_seed(0)
 r = lambda *s: torch.randn(*s, device=dev, generator=g)
-out1a, out2a = r(2 * B, T, 524), r(2 * B, T, 524)
-x1, x2, fin = r(B, T, 524), r(B, T, 524), torch.empty(B, T, 524, device=dev)
+if a.dense:
+    out1a, out2a = r(2 * B, T, 524), r(2 * B, T, 524)
+    x1, x2 = r(B, T, 524), r(B, T, 524)
+else:   # the engine's layout: [out1a row | out2a row], [x1 row | x2 row]
+    preds, state = r(2 * B, T, 2, 524), r(B, T, 2, 524)
+    out1a, out2a, x1, x2 = preds[:, :, 0], preds[:, :, 1], state[:, :, 0], state[:, :, 1]
+fin = torch.empty(B, T, 524, device=dev)
 coef = torch.from_numpy(sched.ddim_coefficients()).to(dev)
 step = torch.tensor([17], dtype=torch.int32, device=dev)
 m1, s1, m2, s2 = r(262) * 0.1, r(262).abs() + 0.5, r(262) * 0.1, r(262).abs() + 0.5

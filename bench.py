@@ -109,7 +109,7 @@ class ClockSampler:
 
 def ncu_traffic(args):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu launch list of this
-    same workload (profiles/r01_launches_v4.csv -> profiles/r01_kernel_traffic.json, tools/summarize_launches.py).
+    same workload (profiles/r01_launches_v5.csv -> profiles/r01_kernel_traffic.json, tools/summarize_launches.py).
     Only valid for the configuration that was profiled (batch 32 x 300 frames, mode 4)."""
     path = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
     if not (os.path.exists(path) and args.batch == 32 and args.frames == 300 and args.mode == 4):
@@ -331,7 +331,7 @@ def main():
                 "frac": achieved_tf / peaks["tflops_sustained"],
                 "traffic": traffic.get("gemm_class", {}).get("dram_bytes_per_launch"),
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the GEMM launches of one DDIM "
-                                  "step (profiles/r01_launches_v4.csv)" if traffic else None,
+                                  "step (profiles/r01_launches_v5.csv)" if traffic else None,
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step), of measured",
                 "launches": gem_n, "avg_launch_us": 1e3 * gem_ms / max(gem_n, 1),
                 "flops_per_launch": gem_fl / max(gem_n, 1), "share_of_step": gem_ms / tot_ms if tot_ms else None}

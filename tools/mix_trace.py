@@ -1,5 +1,5 @@
-"""clock64 timeline of block 0 of the fused mix kernel (mmdm_debug_mix_trace): per consumer warp and frame the time
-spent waiting for the rows and working on them, per producer group the time to acquire slots and to issue the copies.
+"""clock64 timeline of block 0 of the fused mix kernel (mmdm_debug_mix_trace): per warp and frame the time spent
+waiting for the frame's rows and working on them (incl. re-arming the slot), and the waits at the consumer barriers.
    python tools/mix_trace.py [--batch 128] [--mode 4]"""
 import argparse
 import ctypes as C
@@ -53,67 +53,26 @@ tr = trace.cpu().numpy().reshape(16, NE, 4)
 t0 = tr[:, :, 1][tr[:, :, 1] > 0].min()
 tend = tr[:, :, 1:].max()
 print(f"block 0 active for {tend - t0} cycles")
-kinds = {1: "P1 frame", 2: "P2 frame", 3: "producer group", 4: "sync after P1", 5: "sync before P2", 6: "slot acquire"}
+kinds = {1: "P1 frame", 2: "P2 frame", 4: "sync after P1", 5: "sync before P2"}
 for wp in range(16):
     ev = tr[wp][tr[wp, :, 1] > 0]
     if len(ev) == 0:
         continue
     line = [f"warp {wp:2d}: {len(ev):3d} events"]
-    for kind in (1, 2, 3, 4, 5, 6):
+    for kind in (1, 2, 4, 5):
         e = ev[(ev[:, 0] >> 32) == kind]
         if len(e) == 0:
             continue
         a_ = (e[:, 2] - e[:, 1])
-        if kind == 6:
-            b_ = (e[:, 3] - e[:, 2])
-            line.append(f"own items: n={len(e)} wait for slot mean {a_.mean():.0f} max {a_.max()} | issue copies mean {b_.mean():.0f} max {b_.max()}")
-        elif kind in (4, 5):
+        if kind in (4, 5):
             line.append(f"{kinds[kind]}: n={len(e)} wait mean {a_.mean():.0f} max {a_.max()}")
         else:
             b_ = (e[:, 3] - e[:, 2])
             line.append(f"{kinds[kind]}: n={len(e)} {'acquire' if kind == 3 else 'wait'} mean {a_.mean():.0f} max {a_.max()} | "
                         f"{'issue' if kind == 3 else 'work'} mean {b_.mean():.0f} max {b_.max()}")
     print("  ".join(line))
-# ring hand-over: item c (traced for producer warp 14 of block 0: the even items) reuses the slot of item c - NS; how long after that item's release did
-# the producer hold the slot again (re-arm delay), and how long after the re-arm did the consumer see the data?
-NS = 25
-rel, ready = {}, {}
-stream = []   # item index in ring order -> (phase kind, ticket)
-per = T // 4 + (1 if T % 4 else 0)
-for wp in range(14):
-    for e in tr[wp][tr[wp, :, 1] > 0]:
-        kind = int(e[0] >> 32)
-        if kind in (1, 2):
-            rel[(kind, int(e[0] & 0xffffffff))] = int(e[3])
-            ready[(kind, int(e[0] & 0xffffffff))] = int(e[2])
-nfr = min(per, T)   # block 0 = rank 0
-S = max(k[1] for k in rel) // nfr + 1
-def item_of(kind, ticket):
-    k, fl = ticket // nfr, ticket % nfr
-    if kind == 1:
-        return k * nfr + max(k - 1, 0) * nfr + fl
-    return min(k + 2, S) * nfr + k * nfr + fl
-by_item = {item_of(k, t): (k, t) for (k, t) in rel}
-acq = {}
-for wp in (14, 15):
-    for e in tr[wp][tr[wp, :, 1] > 0]:
-        if int(e[0] >> 32) == 6 and e[2] > 0:
-            acq[int(e[0] & 0xffffffff)] = (int(e[1]), int(e[2]))
-d_rearm, d_data, d_wait = [], [], []
-for item, (t_loc, t_acq) in sorted(acq.items()):
-    prev = by_item.get(item - NS)
-    cur = by_item.get(item)
-    if prev is not None:
-        d_rearm.append(t_acq - rel[prev])
-        d_wait.append(t_acq - t_loc)
-    if cur is not None:
-        d_data.append(ready[cur] - t_acq)
-if d_rearm:
-    print(f"re-arm delay (slot released -> producer holds it again): mean {np.mean(d_rearm):.0f} median {np.median(d_rearm):.0f} "
-          f"min {np.min(d_rearm)} max {np.max(d_rearm)} cycles; producer waited for the slot {np.mean(d_wait):.0f} cycles on average")
-    print(f"re-arm -> consumer sees the data: mean {np.mean(d_data):.0f} median {np.median(d_data):.0f} min {np.min(d_data)} max {np.max(d_data)}")
-# timeline of warp 1 (a plain consumer) and producer warp 14: first 40 events
-for wp in (1, 14):
+# timeline of warps 0 (does the cluster exchange) and 1: first 60 events
+for wp in (0, 1):
     print(f"--- warp {wp} timeline (tag kind:index, start, wait/acquire, work/issue)")
     ev = tr[wp][tr[wp, :, 1] > 0][:60]
     for e in ev:

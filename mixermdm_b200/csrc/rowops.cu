@@ -224,25 +224,41 @@ int launch_small_linear(const float* a, int lda, const float* w, const float* b,
 // ------------------------------------------------------------------------------------------------
 // state (B, T, persons*nf) fp32 -> bf16 GEMM operand rows ((b*persons+p)*T + t, kpad), zero padded to kpad.
 // ------------------------------------------------------------------------------------------------
+// One thread per 8 output elements (one 16-byte store); kpad % 8 == 0, person blocks start 8-byte aligned (nf even).
 __global__ void pack_state_kernel(const float* __restrict__ x, int B, int T, int nf, int kpad, int persons,
                                   int row_pitch, __nv_bfloat16* __restrict__ out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * persons * T * kpad;
+  const int chunks = kpad >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = B * persons * T * chunks;
   if (idx >= total) return;
-  const int k = (int)(idx % kpad);
-  const long long row = idx / kpad;
-  const int t = (int)(row % T);
-  const int sp = (int)(row / T);
+  const int row = idx / chunks, k0 = (idx - row * chunks) << 3;
+  const int sp = row / T, t = row - sp * T;
   const int b = sp / persons, p = sp - b * persons;
-  float v = 0.f;
-  if (k < nf) v = x[((size_t)b * T + t) * row_pitch + p * nf + k];
-  out[idx] = __float2bfloat16_rn(v);
+  const float* src = x + ((size_t)b * T + t) * row_pitch + p * nf + k0;
+  float v[8];
+  if (k0 + 8 <= nf && ((nf & 1) == 0) && ((row_pitch & 1) == 0)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __ldg(reinterpret_cast<const float2*>(src) + i);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = k0 + i < nf ? __ldg(src + i) : 0.f;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + (size_t)row * kpad + k0) = o;
 }
 
 int launch_pack_state(const float* x, int B, int T, int nf, int kpad, int persons, __nv_bfloat16* out,
                       cudaStream_t stream, int row_pitch) {
   if (row_pitch <= 0) row_pitch = persons * nf;
-  const long long total = (long long)B * persons * T * kpad;
+  MMDM_REQUIRE((kpad % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+               "pack_state: kpad must be a multiple of 8 and the buffers aligned");
+  const long long total = (long long)B * persons * T * (kpad / 8);
+  MMDM_REQUIRE(total < (1LL << 31), "pack_state: problem too large");
   pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, B, T, nf, kpad, persons, row_pitch, out);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -184,7 +184,9 @@ def test_align_kernel_vs_oracle():
 
 # (4, 45): ragged split of the frames over the 4 CTAs of a cluster (12/12/12/9). (40, 300): BASELINE frame count and
 # more samples than clusters fit on the device, so the persistent loop and the ring wrap across samples are covered.
-@pytest.mark.parametrize("shape", [(4, 45), (40, 300), (3, 2)])
+# (100, 64): three to four samples per cluster (33 clusters are resident), i.e. every segment transition of the
+# software-pipelined frame stream (P1 -> P1, P1 -> P2 of the previous sample, P2 -> P1 two samples on, P2 -> P2).
+@pytest.mark.parametrize("shape", [(4, 45), (40, 300), (3, 2), (100, 64)])
 @pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("final", [False, True])
 def test_mix_cfg_ddim_kernel_vs_oracle(mode, final, shape):

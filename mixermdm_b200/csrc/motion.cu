@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32)
 align_kernel(const float* __restrict__ out1, const float* __restrict__ out2, float* __restrict__ out1a,
              float* __restrict__ out2a, __nv_bfloat16* __restrict__ emb_i, __nv_bfloat16* __restrict__ emb_I,
              int Be, int T, int kpad, int do_align, int pitch_a) {
-  __shared__ float buf[ALIGN_WARPS][4][NFEAT + 2];  // [model*2 + person][feature]
+  __shared__ __align__(16) float buf[ALIGN_WARPS][4][NFEAT + 2];  // [model*2 + person][feature]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ALIGN_WARPS + warp;
   if (item >= (long long)Be * T) return;
@@ -37,10 +37,12 @@ align_kernel(const float* __restrict__ out1, const float* __restrict__ out2, flo
   const float* r1 = out1 + ((size_t)be * T + t) * (2 * NFEAT);
   const float* r2 = out2 + ((size_t)be * T + t) * (2 * NFEAT);
   float(*b)[NFEAT + 2] = buf[warp];
-  for (int f = lane; f < 2 * NFEAT; f += 32) {
-    const int p = f >= NFEAT, fi = f - p * NFEAT;
-    b[p][fi] = r1[f];
-    b[2 + p][fi] = r2[f];
+  // rows are 8-byte aligned and a person's block is an even number of floats: 262 float2 per row, 131 per person
+  for (int j = lane; j < NFEAT; j += 32) {
+    const int p = j >= NFEAT / 2, fi = 2 * j - p * NFEAT;
+    const float2 v1 = __ldg(reinterpret_cast<const float2*>(r1) + j), v2 = __ldg(reinterpret_cast<const float2*>(r2) + j);
+    *reinterpret_cast<float2*>(&b[p][fi]) = v1;
+    *reinterpret_cast<float2*>(&b[2 + p][fi]) = v2;
   }
   __syncwarp();
   if (do_align) {
@@ -78,22 +80,34 @@ align_kernel(const float* __restrict__ out1, const float* __restrict__ out2, flo
   __syncwarp();
   float* w1 = out1a + ((size_t)be * T + t) * pitch_a;
   float* w2 = out2a + ((size_t)be * T + t) * pitch_a;
-  for (int f = lane; f < 2 * NFEAT; f += 32) {
-    const int p = f >= NFEAT, fi = f - p * NFEAT;
-    w1[f] = b[p][fi];
-    w2[f] = b[2 + p][fi];
+  for (int j = lane; j < NFEAT; j += 32) {
+    const int p = j >= NFEAT / 2, fi = 2 * j - p * NFEAT;
+    reinterpret_cast<float2*>(w1)[j] = *reinterpret_cast<const float2*>(&b[p][fi]);
+    reinterpret_cast<float2*>(w2)[j] = *reinterpret_cast<const float2*>(&b[2 + p][fi]);
   }
-  // bf16 operand rows: sequence index be*2+p
-  for (int idx = lane; idx < 2 * kpad; idx += 32) {
-    const int p = idx >= kpad, k = idx - p * kpad;
-    const size_t row = ((size_t)(be * 2 + p) * T + t) * kpad + k;
-    emb_i[row] = __float2bfloat16_rn(k < NFEAT ? b[p][k] : 0.f);
-    emb_I[row] = __float2bfloat16_rn(k < NFEAT ? b[2 + p][k] : 0.f);
+  // bf16 operand rows (sequence index be*2+p), eight values = one 16-byte store per lane and round
+  const int chunks = kpad >> 3;
+  for (int idx = lane; idx < 4 * chunks; idx += 32) {
+    const int m = idx / chunks, k0 = (idx - m * chunks) << 3;   // m = model * 2 + person
+    const int p = m & 1;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = k0 + i < NFEAT ? b[m][k0 + i] : 0.f;
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    __nv_bfloat16* dst = (m < 2 ? emb_i : emb_I) + ((size_t)(be * 2 + p) * T + t) * kpad + k0;
+    *reinterpret_cast<uint4*>(dst) = o;
   }
 }
 
 int launch_align(const float* out1, const float* out2, float* out1a, float* out2a, __nv_bfloat16* emb_i,
                  __nv_bfloat16* emb_I, int Be, int T, int kpad, int do_align, cudaStream_t stream, int pitch_a) {
+  MMDM_REQUIRE((kpad % 8) == 0 && (pitch_a % 2) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(out1) | reinterpret_cast<uintptr_t>(out2) | reinterpret_cast<uintptr_t>(out1a) |
+                     reinterpret_cast<uintptr_t>(out2a)) & 7) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(emb_i) | reinterpret_cast<uintptr_t>(emb_I)) & 15) == 0,
+               "align: buffers must be 8-byte (fp32) / 16-byte (bf16 rows, kpad %% 8 == 0) aligned");
   const long long items = (long long)Be * T;
   const unsigned blocks = (unsigned)((items + ALIGN_WARPS - 1) / ALIGN_WARPS);
   align_kernel<<<blocks, ALIGN_WARPS * 32, 0, stream>>>(out1, out2, out1a, out2a, emb_i, emb_I, Be, T, kpad, do_align, pitch_a);

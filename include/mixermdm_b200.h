@@ -226,6 +226,12 @@ int mmdm_smooth_motion(const float* x, float* out, int B, int T, int F, const fl
 int mmdm_format_motion(const float* x, float* out, int B, int T, int max_length, int nfeats, const float* mean,
                        const float* std_, void* stream);
 
+/* Test hook (host only, no GPU): the index arithmetic of the fused mix kernel's frame stream (csrc/mix_stream.cuh).
+ * For item `item` of the stream of S samples x nfr frames (with or without a phase 2) in a ring of ring_slots <= nfr
+ * slots: out[0..9] = phase (1|2), sample, frame, ring slot, lap, item index recomputed from (phase, sample, frame),
+ * successor valid, phase / sample / frame of the item ring_slots positions later (the one that takes over the slot). */
+int mmdm_debug_mix_stream(int S, int nfr, int has_phase2, int ring_slots, int item, int32_t* out);
+
 /* per-kernel-class device timing (CUDA events on the launch stream, no graph): enable, run steps, read. */
 int mmdm_profile_enable(mmdm_handle* h, int on);
 /* writes up to max_entries records; returns the number written */

@@ -14,6 +14,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "mix_stream.cuh"
 #include "motion.cuh"
 #include "rowops.cuh"
 
@@ -817,6 +818,24 @@ int mmdm_format_motion(const float* x, float* out, int B, int T, int max_length,
                        const float* std_, void* stream) {
   MMDM_REQUIRE(x && out, "mmdm_format_motion: null argument");
   return launch_format_motion(x, out, B, T, max_length, nfeats, mean, std_, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mmdm_debug_mix_stream(int S, int nfr, int has_phase2, int ring_slots, int item, int32_t* out) {
+  MMDM_REQUIRE(out && S >= 1 && nfr >= 1 && ring_slots >= 1 && ring_slots <= nfr, "mmdm_debug_mix_stream: bad argument");
+  MixStream st;
+  st.S = S; st.nfr = nfr; st.has2 = has_phase2 ? 1 : 0;
+  MMDM_REQUIRE(item >= 0 && item < mix_stream_items(st), "mmdm_debug_mix_stream: item %d outside the stream", item);
+  bool p1;
+  int n, fl, slot, lap;
+  mix_item_decode(st, item, p1, n, fl);
+  mix_ring_pos(item, ring_slots, mix_ring_rcp(ring_slots), slot, lap);
+  out[0] = p1 ? 1 : 2; out[1] = n; out[2] = fl; out[3] = slot; out[4] = lap;
+  out[5] = p1 ? mix_base_p1(st, n) + fl : mix_base_p2(st, n) + fl;   // must give `item` back
+  bool q1 = p1;
+  int qn = n, qf = fl;
+  const bool ok = mix_item_after(st, ring_slots, q1, qn, qf);
+  out[6] = ok ? 1 : 0; out[7] = q1 ? 1 : 2; out[8] = qn; out[9] = qf;
+  return 0;
 }
 
 int mmdm_profile_enable(mmdm_handle* h, int on) {

@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include "mix_stream.cuh"
 #include "motion_math.cuh"
 
 namespace cg = cooperative_groups;
@@ -262,13 +263,11 @@ __device__ __forceinline__ void mix_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Ring position of item c of the CTA's stream: slot c % NS, use number ("lap") c / NS.
-// (ns_rcp = ceil(2^32 / NS): exact quotient for the < 2^20 items a CTA streams)
+// Ring position of item c of the CTA's stream (mix_stream.cuh)
 struct RowPos { int slot, lap; };
 __device__ __forceinline__ RowPos locate_row(int c, int NS, uint32_t ns_rcp) {
   RowPos r;
-  r.lap = NS == 1 ? c : (int)__umulhi((uint32_t)c, ns_rcp);   // (ceil(2^32 / 1) does not fit 32 bits)
-  r.slot = c - r.lap * NS;
+  mix_ring_pos(c, NS, ns_rcp, r.slot, r.lap);
   return r;
 }
 
@@ -313,7 +312,7 @@ mixstep_kernel(const MixStepParams P) {
   uint8_t* ring = smem + L.ring_off;
   const int NS = min(L.nslots, max(nfr, 1));   // (a slot is refilled by the frame NS items later, which must not be a
                                                //  later frame's phase 2 than the one being finished: NS <= nfr)
-  const uint32_t ns_rcp = (uint32_t)((0x100000000ULL + NS - 1) / NS);
+  const uint32_t ns_rcp = mix_ring_rcp(NS);
 
   const int step = P.mix_only ? 0 : *P.step_ptr;
   const bool final_step = (step == 0) && !P.mix_only;
@@ -336,8 +335,10 @@ mixstep_kernel(const MixStepParams P) {
   const int R1 = 2 * ncfg, R2 = 3;
   const int r1 = nfr, r2 = phase2 ? nfr : 0;   // items per sample and phase
   const int total_items = S * (r1 + r2);
-  auto base_p1 = [&](int k) { return k * r1 + (k > 0 ? k - 1 : 0) * r2; };
-  auto base_p2 = [&](int k) { return min(k + 1, S) * r1 + (k - 1) * r2; };   // P2(k-1), issued in stage k
+  MixStream stream;
+  stream.S = S; stream.nfr = nfr; stream.has2 = phase2 ? 1 : 0;
+  auto base_p1 = [&](int k) { return mix_base_p1(stream, k); };
+  auto base_p2 = [&](int k) { return mix_base_p2(stream, k - 1); };   // P2(k-1), processed in stage k
 
   {
     // ---- every warp is a consumer (and refills the slots it empties) --------------------------------------------------------------------------
@@ -446,21 +447,9 @@ mixstep_kernel(const MixStepParams P) {
     // phase 1 of its sample. That barrier lies behind this warp unless the item is armed from that very phase 1 (only
     // with one sample per cluster): those rows are sent right after the barrier (send_deferred_g).
     auto rearm = [&](bool cur_p1, int n_cur, int f, RowPos cur) {
-      int t = f + NS, n = n_cur;
       bool p1 = cur_p1;
-      if (t >= nfr) {
-        t -= nfr;
-        if (r2 == 0) { n = n_cur + 1; }                              // P1(n) -> P1(n+1)
-        else if (cur_p1) {
-          if (n_cur >= 1) { p1 = false; n = n_cur - 1; }             // P1(k) -> P2(k-1)
-          else if (S > 1) { n = 1; }                                 // P1(0) -> P1(1)
-          else { p1 = false; n = 0; }                                // P1(0) -> P2(0)   (one sample)
-        } else {
-          if (n_cur + 2 < S) { p1 = true; n = n_cur + 2; }           // P2(j) -> P1(j+2)
-          else { n = n_cur + 1; }                                    // P2(j) -> P2(j+1)
-        }
-        if (n >= S) return;                                          // end of the stream
-      }
+      int n = n_cur, t = f;
+      if (!mix_item_after(stream, NS, p1, n, t)) return;   // end of the stream
       RowPos rp = cur;
       ++rp.lap;
       arm_item(p1, n, t, rp, cur_p1 && S == 1);

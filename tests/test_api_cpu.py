@@ -155,3 +155,43 @@ def test_gaussian_taps_match_scipy_impulse_response():
         ref = gaussian_filter1d(imp, sigma, mode="nearest")[radius:3 * radius + 1]
         assert radius == int(4 * sigma + 0.5) and len(taps) == 2 * radius + 1
         assert np.abs(taps - ref).max() < 1e-15
+
+
+def _mix_stream_reference(S, nfr, has2):
+    """the fused mix kernel's frame stream, spelled out: P1(0), [P1(k), P2(k-1)] for k = 1..S-1, P2(S-1)"""
+    items = [(1, 0, f) for f in range(nfr)]
+    for k in range(1, S + 1):
+        if k < S:
+            items += [(1, k, f) for f in range(nfr)]
+        if has2:
+            items += [(2, k - 1, f) for f in range(nfr)]
+    return items
+
+
+def test_mix_kernel_stream_arithmetic_matches_enumeration():
+    """csrc/mix_stream.cuh through mmdm_debug_mix_stream (host code, no GPU): decoding an item, its index from
+    (phase, sample, frame), its ring slot / lap (reciprocal multiply) and the item that takes over its slot
+    ring_slots positions later, for every item of many stream shapes - incl. one-slot rings, one sample per
+    cluster, no phase 2 and 3+ samples, where all four segment transitions occur."""
+    import ctypes as C
+    from mixermdm_b200 import _lib
+    lib = _lib.load()
+    out = (C.c_int32 * 10)()
+    for S in (1, 2, 3, 4, 5):
+        for nfr in (1, 2, 3, 12, 25, 76):
+            for has2 in (0, 1):
+                ref = _mix_stream_reference(S, nfr, has2)
+                for NS in sorted({1, 2, min(nfr, 25), nfr}):
+                    if NS > nfr:
+                        continue
+                    for c, (ph, n, f) in enumerate(ref):
+                        assert lib.mmdm_debug_mix_stream(S, nfr, has2, NS, c, out) == 0
+                        assert (out[0], out[1], out[2]) == (ph, n, f), (S, nfr, has2, NS, c)
+                        assert (out[3], out[4]) == (c % NS, c // NS)
+                        assert out[5] == c
+                        if c + NS < len(ref):
+                            assert out[6] == 1 and (out[7], out[8], out[9]) == ref[c + NS], (S, nfr, has2, NS, c)
+                        else:
+                            assert out[6] == 0
+    assert lib.mmdm_debug_mix_stream(2, 4, 1, 5, 0, out) != 0          # ring deeper than a sample's frames: rejected
+    assert lib.mmdm_debug_mix_stream(2, 4, 1, 4, 16, out) != 0         # item outside the stream

@@ -4,7 +4,9 @@
  * (src/models/mixermdm.py:490-602, 660-811; src/models/in2in.py:401-462; src/models/utils/influence.py:93-126;
  * src/models/utils/cfg_sampler.py:31-56; src/models/utils/gaussian_diffusion.py:1769-2091). The Python mirror
  * in mixermdm_b200/ keeps those signatures and calls the entry points below through ctypes. Conventions:
- *   - every function returns 0 on success, a negative code on failure; mmdm_last_error() gives the message;
+ *   - every function returns 0 on success, a negative code on failure; mmdm_last_error(h) gives the message;
+ *   - a handle belongs to the device that was current in mmdm_create; its entry points make that device current
+ *     for the duration of the call, so the caller may sit on another GPU of the same process;
  *   - the caller owns every device buffer (weights, workspace, state); nothing is allocated behind its back
  *     except the handle itself; no host synchronisation; everything is enqueued on `stream`
  *     (a cudaStream_t passed as void*) and is CUDA-graph capturable;
@@ -20,10 +22,14 @@
 extern "C" {
 #endif
 
-#define MMDM_ABI_VERSION 1
+#define MMDM_ABI_VERSION 2
+
+typedef struct mmdm_handle mmdm_handle;
 
 int mmdm_abi_version(void);
-const char* mmdm_last_error(void);
+/* message of the last failed call on handle h; with h == NULL the calling thread's last failure of a call that has
+ * no handle (mmdm_create, the operator-level entry points). No process-global error state. */
+const char* mmdm_last_error(const mmdm_handle* h);
 /* bring-up switch: 1 routes GEMMs through a slow SIMT kernel with the same epilogue (tests only). */
 void mmdm_debug_gemm_simt(int on);
 
@@ -174,8 +180,6 @@ typedef struct mmdm_config {
   const float* mean1; const float* std1;  /* MotionNormalizerTorchHML3D (individual model) */
   const float* mean2; const float* std2;  /* MotionNormalizerTorch      (interaction model) */
 } mmdm_config;
-
-typedef struct mmdm_handle mmdm_handle;
 
 int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_handle** out);
 void mmdm_destroy(mmdm_handle* h);

@@ -5,6 +5,7 @@ import os
 from . import _build
 
 _LIB = None
+ABI_VERSION = 2   # MMDM_ABI_VERSION of include/mixermdm_b200.h
 
 
 class MmdmError(RuntimeError):
@@ -42,14 +43,18 @@ def load():
                         "(the CUDA extension is mandatory, there is no fallback path)")
     lib = C.CDLL(path)
     lib.mmdm_last_error.restype = C.c_char_p
+    lib.mmdm_last_error.argtypes = [C.c_void_p]
     lib.mmdm_abi_version.restype = C.c_int
+    if lib.mmdm_abi_version() != ABI_VERSION:
+        raise MmdmError(f"{path}: ABI version {lib.mmdm_abi_version()} != {ABI_VERSION}; rebuild the library")
     _LIB = lib
     return lib
 
 
-def check(rc, what=""):
+def check(rc, what="", handle=None):
+    """raise on a non-zero return code with the message kept for `handle` (None: the thread's handle-less calls)"""
     if rc != 0:
-        msg = load().mmdm_last_error().decode("utf-8", "replace")
+        msg = load().mmdm_last_error(handle).decode("utf-8", "replace")
         raise MmdmError(f"{what} failed (rc={rc}): {msg}")
 
 
@@ -58,6 +63,7 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def cur_stream():
+def cur_stream(device=None):
+    """the current torch stream of `device` (default: the current device) as a cudaStream_t"""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

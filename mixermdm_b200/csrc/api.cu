@@ -39,7 +39,6 @@ using namespace mmdm;
 extern "C" {
 
 int mmdm_abi_version(void) { return MMDM_ABI_VERSION; }
-const char* mmdm_last_error(void) { return mmdm::get_last_error(); }
 void mmdm_debug_gemm_simt(int on) { mmdm::gemm_set_debug_simt(on); }
 
 int mmdm_linear_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,

@@ -509,16 +509,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
-static int num_sms_attn() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms_attn() { return device_sm_count(); }
 
 template <int HD>
 static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk,
@@ -572,7 +563,9 @@ extern "C" int mmdm_debug_attn_trace(long long* dev_ptr) {
 }
 #endif
 
-int attention_init() {
+int attention_init() {   // kernel attributes are per device
+  static PerDeviceFlag attr;
+  if (!attr.first()) return 0;
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)AttnCfg<128>::SMEM_BYTES));
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -583,8 +576,7 @@ int attention_init() {
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
                      int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H, int hd, int kv_xor,
                      cudaStream_t stream, int rev) {
-  static int inited = attention_init();
-  MMDM_REQUIRE(inited == 0, "attention: kernel attribute setup failed");
+  MMDM_REQUIRE(attention_init() == 0, "attention: kernel attribute setup failed");
   MMDM_REQUIRE(T >= 1 && T <= 303, "attention: T=%d outside the single-tile range [1,303]", T);
   MMDM_REQUIRE(hd == 64 || hd == 128, "attention: head dim %d not in {64,128}", hd);
   MMDM_REQUIRE((ldq % 8) == 0 && (ldk % 8) == 0 && (Tp % 8) == 0 && (ldo % 8) == 0 && Tp >= T,

@@ -41,6 +41,32 @@ int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const
                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                     CUtensorMapSwizzle swizzle);
 
+// Per-device host state. Kernel attributes (cudaFuncSetAttribute) and SM counts belong to a device, not to the
+// process: a second GPU driven from the same process needs its own. kMaxDevices bounds the small tables below.
+constexpr int kMaxDevices = 64;
+int current_device();   // ordinal of the calling thread's current device, clamped to [0, kMaxDevices)
+int device_sm_count();  // multiprocessors of the current device (cached per device)
+struct PerDeviceFlag {  // "done once per device" latch; first(): true exactly once for the current device
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+// makes `device` current for the lifetime of the object (no-op when it already is)
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    int cur = -1;
+    if (device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------

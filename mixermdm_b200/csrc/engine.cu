@@ -110,6 +110,9 @@ struct Workspace {
 using namespace mmdm;
 
 struct mmdm_handle {
+  int device = 0;            // ordinal the handle was created on; every entry point makes it current
+  std::string last_error;    // message of the last failed call on this handle (mmdm_last_error(h))
+  int step_host = -1;        // host mirror of the device-side DDIM index (-1: no state set)
   mmdm_config cfg;
   Net net[3];
   std::vector<int32_t> timestep_map;
@@ -546,6 +549,22 @@ static void drop_graph(mmdm_handle* h) {
   h->graph = nullptr;
 }
 
+const char* get_last_error();
+
+// Every handle entry point runs through here: the handle's device is made current for the call (the caller may
+// sit on another GPU of the process) and a failure's message is kept per handle.
+template <typename F>
+static int guarded(mmdm_handle* h, F&& body) {
+  if (!h) {
+    set_last_error("null handle");
+    return -1;
+  }
+  DeviceGuard dg(h->device);
+  const int rc = body();
+  if (rc != 0) h->last_error = get_last_error();
+  return rc;
+}
+
 }  // namespace mmdm
 
 // ------------------------------------------------------------------------------------------------
@@ -562,6 +581,7 @@ int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_han
   MMDM_TRY(attention_init());
   MMDM_TRY(motion_init());
   mmdm_handle* h = new mmdm_handle();
+  h->device = current_device();
   h->cfg = *cfg;
   {
     const char* e = getenv("MMDM_SERPENTINE");
@@ -597,6 +617,7 @@ int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_han
 
 void mmdm_destroy(mmdm_handle* h) {
   if (!h) return;
+  DeviceGuard dg(h->device);
   drop_graph(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   h->prof.flush();
@@ -612,174 +633,197 @@ size_t mmdm_workspace_bytes(const mmdm_handle* h, int B, int T) {
 }
 
 int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T) {
-  MMDM_REQUIRE(h && ws, "mmdm_bind_workspace: null argument");
-  MMDM_REQUIRE(T >= 1 && T <= 303, "mmdm_bind_workspace: T=%d outside [1,303]", T);
-  MMDM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
-  size_t need = mmdm_workspace_bytes(h, B, T);
-  MMDM_REQUIRE(bytes >= need, "workspace too small: %zu < %zu", bytes, need);
-  drop_graph(h);
-  carve(h, B, T, ws, &h->ws, nullptr);
-  h->ws_base = ws; h->ws_bytes = bytes; h->B = B; h->T = T; h->Bx = 2 * B; h->Tp = (T + 7) / 8 * 8;
-  h->temb_ready = false;
-  return 0;
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && ws, "mmdm_bind_workspace: null argument");
+    MMDM_REQUIRE(T >= 1 && T <= 303, "mmdm_bind_workspace: T=%d outside [1,303]", T);
+    MMDM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+    size_t need = mmdm_workspace_bytes(h, B, T);
+    MMDM_REQUIRE(bytes >= need, "workspace too small: %zu < %zu", bytes, need);
+    drop_graph(h);
+    carve(h, B, T, ws, &h->ws, nullptr);
+    h->ws_base = ws; h->ws_bytes = bytes; h->B = B; h->T = T; h->Bx = 2 * B; h->Tp = (T + 7) / 8 * 8;
+    h->temb_ready = false;
+    return 0;
+  });
 }
 
 int mmdm_set_condition(mmdm_handle* h, const float* cond, void* stream) {
-  MMDM_REQUIRE(h && h->ws_base && cond, "mmdm_set_condition: handle not bound / null cond");
-  MMDM_REQUIRE(h->net[0].present && h->net[1].present && h->net[2].present, "mmdm_set_condition: handle holds a single network");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMDM_TRY(ensure_temb(h, st));
-  const int ld = 8 * h->cfg.text_dim;
-  MMDM_TRY(run_text(h, 0, cond, ld, h->B, COL_IND, 2, st));
-  MMDM_TRY(run_text(h, 1, cond, ld, h->B, COL_INTER, 3, st));
-  MMDM_TRY(run_text(h, 2, cond, ld, h->B, COL_MIX, 3, st));
-  return 0;
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base && cond, "mmdm_set_condition: handle not bound / null cond");
+    MMDM_REQUIRE(h->net[0].present && h->net[1].present && h->net[2].present, "mmdm_set_condition: handle holds a single network");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MMDM_TRY(ensure_temb(h, st));
+    const int ld = 8 * h->cfg.text_dim;
+    MMDM_TRY(run_text(h, 0, cond, ld, h->B, COL_IND, 2, st));
+    MMDM_TRY(run_text(h, 1, cond, ld, h->B, COL_INTER, 3, st));
+    MMDM_TRY(run_text(h, 2, cond, ld, h->B, COL_MIX, 3, st));
+    return 0;
+  });
 }
 
 int mmdm_set_state(mmdm_handle* h, const float* x1, const float* x2, int step_index, void* stream) {
-  MMDM_REQUIRE(h && h->ws_base && x1 && x2, "mmdm_set_state: handle not bound / null state");
-  MMDM_REQUIRE(step_index >= 0 && step_index < h->cfg.nsteps, "mmdm_set_state: step index %d out of range", step_index);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
-  const size_t rowb = (size_t)2 * h->cfg.nfeats * sizeof(float), nrows = (size_t)h->B * h->T;   // (x1 | x2 interleaved rows)
-  (void)bytes;
-  MMDM_CHECK_CUDA(cudaMemcpy2DAsync(h->ws.x1, 2 * rowb, x1, rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
-  MMDM_CHECK_CUDA(cudaMemcpy2DAsync(h->ws.x2, 2 * rowb, x2, rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
-  MMDM_TRY(launch_set_int(h->ws.step, step_index, st));
-  return 0;
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base && x1 && x2, "mmdm_set_state: handle not bound / null state");
+    MMDM_REQUIRE(step_index >= 0 && step_index < h->cfg.nsteps, "mmdm_set_state: step index %d out of range", step_index);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
+    const size_t rowb = (size_t)2 * h->cfg.nfeats * sizeof(float), nrows = (size_t)h->B * h->T;   // (x1 | x2 interleaved rows)
+    (void)bytes;
+    MMDM_CHECK_CUDA(cudaMemcpy2DAsync(h->ws.x1, 2 * rowb, x1, rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+    MMDM_CHECK_CUDA(cudaMemcpy2DAsync(h->ws.x2, 2 * rowb, x2, rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+    MMDM_TRY(launch_set_int(h->ws.step, step_index, st));
+    h->step_host = step_index;
+    return 0;
+  });
 }
 
 int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream) {
-  MMDM_REQUIRE(h && h->ws_base, "mmdm_get_state: handle not bound");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
-  const size_t rowb = (size_t)2 * h->cfg.nfeats * sizeof(float), nrows = (size_t)h->B * h->T;
-  (void)bytes;
-  if (x1) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(x1, rowb, h->ws.x1, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
-  if (x2) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(x2, rowb, h->ws.x2, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base, "mmdm_get_state: handle not bound");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
+    const size_t rowb = (size_t)2 * h->cfg.nfeats * sizeof(float), nrows = (size_t)h->B * h->T;
+    (void)bytes;
+    if (x1) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(x1, rowb, h->ws.x1, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+    if (x2) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(x2, rowb, h->ws.x2, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  });
 }
 
 int mmdm_step(mmdm_handle* h, float* final_out, void* stream) {
-  MMDM_REQUIRE(h && h->ws_base, "mmdm_step: handle not bound");
-  MMDM_REQUIRE(h->net[0].present && h->net[1].present && h->net[2].present, "mmdm_step: handle holds a single network");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMDM_TRY(ensure_temb(h, st));
-  return step_body(h, final_out, nullptr, nullptr, st);
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base, "mmdm_step: handle not bound");
+    MMDM_REQUIRE(h->net[0].present && h->net[1].present && h->net[2].present, "mmdm_step: handle holds a single network");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the DDIM index lives on the device (graph replays); the host mirror only guards against stepping past index 0,
+    // which would read the coefficient / embedding tables out of bounds
+    MMDM_REQUIRE(h->step_host >= 0, "mmdm_step: no step left (set a state first; the DDIM index ran past 0)");
+    MMDM_TRY(ensure_temb(h, st));
+    MMDM_TRY(step_body(h, final_out, nullptr, nullptr, st));
+    h->step_host -= 1;
+    return 0;
+  });
 }
 
 int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* out, float* hist_i1, float* hist_i2,
                 float* hist_out1, float* hist_out2, float* hist_mix, int use_graph, void* stream) {
-  MMDM_REQUIRE(h && h->ws_base && cond && noise && out, "mmdm_sample: handle not bound / null argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMDM_TRY(mmdm_set_condition(h, cond, stream));
-  MMDM_TRY(mmdm_set_state(h, noise, noise, h->cfg.nsteps - 1, stream));
-  const size_t out_bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
-  const bool eval_hist = hist_out1 || hist_out2 || hist_mix;
-  if (eval_hist) MMDM_REQUIRE(hist_out1 && hist_out2 && hist_mix, "mmdm_sample: the three eval-mode history buffers come together");
-  if (use_graph && !h->prof.on && !eval_hist) {
-    if (h->graph && (h->graph_h1 != hist_i1 || h->graph_h2 != hist_i2)) drop_graph(h);
-    if (!h->graph) {
-      cudaGraph_t g = nullptr;
-      if (!h->cap_stream) MMDM_CHECK_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
-      MMDM_CHECK_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-      const long long before = h->launches;
-      int rc = step_body(h, nullptr, hist_i1, hist_i2, h->cap_stream);
-      h->graph_step_launches = h->launches - before;
-      h->launches = before;   // capturing enqueues nothing; replays are counted below
-      cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
-      if (rc != 0) {
-        if (g) cudaGraphDestroy(g);
-        return rc;
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base && cond && noise && out, "mmdm_sample: handle not bound / null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MMDM_TRY(mmdm_set_condition(h, cond, stream));
+    MMDM_TRY(mmdm_set_state(h, noise, noise, h->cfg.nsteps - 1, stream));
+    const size_t out_bytes = (size_t)h->B * h->T * 2 * h->cfg.nfeats * sizeof(float);
+    const bool eval_hist = hist_out1 || hist_out2 || hist_mix;
+    if (eval_hist) MMDM_REQUIRE(hist_out1 && hist_out2 && hist_mix, "mmdm_sample: the three eval-mode history buffers come together");
+    if (use_graph && !h->prof.on && !eval_hist) {
+      if (h->graph && (h->graph_h1 != hist_i1 || h->graph_h2 != hist_i2)) drop_graph(h);
+      if (!h->graph) {
+        cudaGraph_t g = nullptr;
+        if (!h->cap_stream) MMDM_CHECK_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        MMDM_CHECK_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = h->launches;
+        int rc = step_body(h, nullptr, hist_i1, hist_i2, h->cap_stream);
+        h->graph_step_launches = h->launches - before;
+        h->launches = before;   // capturing enqueues nothing; replays are counted below
+        cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
+        if (rc != 0) {
+          if (g) cudaGraphDestroy(g);
+          return rc;
+        }
+        MMDM_CHECK_CUDA(e);
+        MMDM_CHECK_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
+        cudaGraphDestroy(g);
+        h->graph_h1 = hist_i1; h->graph_h2 = hist_i2;
       }
-      MMDM_CHECK_CUDA(e);
-      MMDM_CHECK_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
-      cudaGraphDestroy(g);
-      h->graph_h1 = hist_i1; h->graph_h2 = hist_i2;
+      for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_CHECK_CUDA(cudaGraphLaunch(h->graph, st));
+      h->launches += h->graph_step_launches * h->cfg.nsteps;
+    } else {
+      EvalHist eh;
+      eh.out1 = hist_out1; eh.out2 = hist_out2; eh.mix = hist_mix;
+      for (int i = 0; i < h->cfg.nsteps; ++i) {
+        eh.slot = i;
+        MMDM_TRY(step_body(h, nullptr, hist_i1, hist_i2, st, eval_hist ? &eh : nullptr));
+      }
     }
-    for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_CHECK_CUDA(cudaGraphLaunch(h->graph, st));
-    h->launches += h->graph_step_launches * h->cfg.nsteps;
-  } else {
-    EvalHist eh;
-    eh.out1 = hist_out1; eh.out2 = hist_out2; eh.mix = hist_mix;
-    for (int i = 0; i < h->cfg.nsteps; ++i) {
-      eh.slot = i;
-      MMDM_TRY(step_body(h, nullptr, hist_i1, hist_i2, st, eval_hist ? &eh : nullptr));
-    }
-  }
-  MMDM_CHECK_CUDA(cudaMemcpyAsync(out, h->ws.final, out_bytes, cudaMemcpyDeviceToDevice, st));
-  return 0;
+    h->step_host = -1;   // the loop consumed every index
+    MMDM_CHECK_CUDA(cudaMemcpyAsync(out, h->ws.final, out_bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  });
 }
 
 int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const int64_t* timesteps, const float* cond,
                        float* out_influenced, float* out1, float* out2, float* infl_i1, float* infl_i2, int Bx,
                        int cfg_combine, float cfg_scale, void* stream) {
-  MMDM_REQUIRE(h && h->ws_base && x1 && x2 && timesteps && cond && out_influenced, "mmdm_mixer_forward: null argument");
-  MMDM_REQUIRE(Bx >= 1 && Bx <= h->Bx, "mmdm_mixer_forward: Bx=%d exceeds the bound workspace (%d rows)", Bx, h->Bx);
-  MMDM_REQUIRE(h->net[0].present && h->net[1].present && h->net[2].present, "mmdm_mixer_forward: handle holds a single network");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMDM_TRY(ensure_temb(h, st));
-  Workspace& ws = h->ws;
-  const int ld = 8 * h->cfg.text_dim;
-  MMDM_TRY(run_text(h, 0, cond, ld, Bx, COL_IND, 2, st));
-  MMDM_TRY(run_text(h, 1, cond, ld, Bx, COL_INTER, 3, st));
-  MMDM_TRY(run_text(h, 2, cond, ld, Bx, COL_MIX, 3, st));
-  // per-sample timestep embeddings are (re)computed per network right before that network runs
-  MMDM_TRY(run_time_embed(h, 0, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
-  const int T = h->T, nf = h->cfg.nfeats, kpad = h->cfg.kpad;
-  const int S = 2 * Bx, M = S * T;
-  MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 2, 0, st));
-  MMDM_TRY(run_denoiser(h, 0, x1, Bx, 0, 2, ws.temb_dyn, nullptr, ws.out1, h->cfg.std1, h->cfg.mean1, st));
-  MMDM_TRY(run_time_embed(h, 1, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
-  MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 3, 1, st));
-  MMDM_TRY(run_denoiser(h, 1, x2, Bx, 0, 2, ws.temb_dyn, nullptr, ws.out2, h->cfg.std2, h->cfg.mean2, st));
-  MMDM_TRY(launch_align(ws.out1, ws.out2, ws.out1a, ws.out2a, ws.xin, ws.xin + (size_t)M * kpad, Bx, T, kpad,
-                        h->cfg.align, st, 2 * 2 * nf));
-  Net& n = h->net[2];
-  const int D = n.w.D;
-  MMDM_TRY(run_time_embed(h, 2, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
-  MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 3, 1, st));
-  MMDM_TRY(run_conditioning(h, 2, S, ws.temb_dyn, nullptr, st));
-  GemmEpi ee;
-  ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
-  MMDM_TRY(gemm(h, "gemm_embed", ws.xin, kpad, n.w.embed_w, kpad, 2 * M, D, kpad, ee, st));
-  const float* mI = ws.h + (size_t)M * D;
-  for (int l = 0; l < n.w.L; ++l)
-    MMDM_TRY(run_block(h, 2, l, ws.h, mI, S, T, l == n.w.L - 1 ? ws.hfin : nullptr, st));
-  MMDM_TRY(run_head(h, S, T, st));
-  MixStepParams P = mix_params(h);
-  if (cfg_combine) {
-    MMDM_REQUIRE(Bx % 2 == 0, "mmdm_mixer_forward: cfg_combine needs an even number of rows");
-    P.B = Bx / 2; P.ncfg = 2; P.mix_only = 2; P.cfg_scale = cfg_scale;
-  } else {
-    P.B = Bx; P.ncfg = 1; P.mix_only = 1;
-  }
-  P.mix_out = out_influenced;
-  P.hist_i1 = infl_i1; P.hist_i2 = infl_i2;
-  MMDM_TRY(launch_mixstep(P, st));
-  const size_t bytes = (size_t)Bx * T * 2 * nf * sizeof(float);
-  const size_t rowb = (size_t)2 * nf * sizeof(float), nrows = (size_t)Bx * T;
-  (void)bytes;
-  if (out1) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(out1, rowb, ws.out1a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
-  if (out2) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(out2, rowb, ws.out2a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base && x1 && x2 && timesteps && cond && out_influenced, "mmdm_mixer_forward: null argument");
+    MMDM_REQUIRE(Bx >= 1 && Bx <= h->Bx, "mmdm_mixer_forward: Bx=%d exceeds the bound workspace (%d rows)", Bx, h->Bx);
+    MMDM_REQUIRE(h->net[0].present && h->net[1].present && h->net[2].present, "mmdm_mixer_forward: handle holds a single network");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MMDM_TRY(ensure_temb(h, st));
+    Workspace& ws = h->ws;
+    const int ld = 8 * h->cfg.text_dim;
+    MMDM_TRY(run_text(h, 0, cond, ld, Bx, COL_IND, 2, st));
+    MMDM_TRY(run_text(h, 1, cond, ld, Bx, COL_INTER, 3, st));
+    MMDM_TRY(run_text(h, 2, cond, ld, Bx, COL_MIX, 3, st));
+    // per-sample timestep embeddings are (re)computed per network right before that network runs
+    MMDM_TRY(run_time_embed(h, 0, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
+    const int T = h->T, nf = h->cfg.nfeats, kpad = h->cfg.kpad;
+    const int S = 2 * Bx, M = S * T;
+    MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 2, 0, st));
+    MMDM_TRY(run_denoiser(h, 0, x1, Bx, 0, 2, ws.temb_dyn, nullptr, ws.out1, h->cfg.std1, h->cfg.mean1, st));
+    MMDM_TRY(run_time_embed(h, 1, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
+    MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 3, 1, st));
+    MMDM_TRY(run_denoiser(h, 1, x2, Bx, 0, 2, ws.temb_dyn, nullptr, ws.out2, h->cfg.std2, h->cfg.mean2, st));
+    MMDM_TRY(launch_align(ws.out1, ws.out2, ws.out1a, ws.out2a, ws.xin, ws.xin + (size_t)M * kpad, Bx, T, kpad,
+                          h->cfg.align, st, 2 * 2 * nf));
+    Net& n = h->net[2];
+    const int D = n.w.D;
+    MMDM_TRY(run_time_embed(h, 2, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
+    MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 3, 1, st));
+    MMDM_TRY(run_conditioning(h, 2, S, ws.temb_dyn, nullptr, st));
+    GemmEpi ee;
+    ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
+    MMDM_TRY(gemm(h, "gemm_embed", ws.xin, kpad, n.w.embed_w, kpad, 2 * M, D, kpad, ee, st));
+    const float* mI = ws.h + (size_t)M * D;
+    for (int l = 0; l < n.w.L; ++l)
+      MMDM_TRY(run_block(h, 2, l, ws.h, mI, S, T, l == n.w.L - 1 ? ws.hfin : nullptr, st));
+    MMDM_TRY(run_head(h, S, T, st));
+    MixStepParams P = mix_params(h);
+    if (cfg_combine) {
+      MMDM_REQUIRE(Bx % 2 == 0, "mmdm_mixer_forward: cfg_combine needs an even number of rows");
+      P.B = Bx / 2; P.ncfg = 2; P.mix_only = 2; P.cfg_scale = cfg_scale;
+    } else {
+      P.B = Bx; P.ncfg = 1; P.mix_only = 1;
+    }
+    P.mix_out = out_influenced;
+    P.hist_i1 = infl_i1; P.hist_i2 = infl_i2;
+    MMDM_TRY(launch_mixstep(P, st));
+    const size_t bytes = (size_t)Bx * T * 2 * nf * sizeof(float);
+    const size_t rowb = (size_t)2 * nf * sizeof(float), nrows = (size_t)Bx * T;
+    (void)bytes;
+    if (out1) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(out1, rowb, ws.out1a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+    if (out2) MMDM_CHECK_CUDA(cudaMemcpy2DAsync(out2, rowb, ws.out2a, 2 * rowb, rowb, nrows, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  });
 }
 
 int mmdm_denoiser_forward(mmdm_handle* h, int which, const float* x, const int64_t* timesteps, const float* cond,
                           float* out, int Bx, void* stream) {
-  MMDM_REQUIRE(h && h->ws_base && x && timesteps && cond && out, "mmdm_denoiser_forward: null argument");
-  MMDM_REQUIRE(which == MMDM_NET_INDIVIDUAL || which == MMDM_NET_INTERACTION, "Mode not recognized");
-  MMDM_REQUIRE(h->net[which].present, "mmdm_denoiser_forward: network %d is not loaded in this handle", which);
-  const int persons = which == MMDM_NET_INTERACTION ? 2 : 1;
-  MMDM_REQUIRE(Bx >= 1 && Bx <= h->Bx, "mmdm_denoiser_forward: Bx=%d exceeds the bound workspace (%d rows)", Bx, h->Bx);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMDM_TRY(ensure_temb(h, st));
-  Workspace& ws = h->ws;
-  const int nsl = which == MMDM_NET_INTERACTION ? 3 : 1;
-  MMDM_TRY(run_text(h, which, cond, nsl * h->cfg.text_dim, Bx, 0, nsl, st));
-  MMDM_TRY(run_time_embed(h, which, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
-  MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, Bx * persons, persons, Bx, 0, nsl, which == MMDM_NET_INTERACTION ? 1 : 0, st));
-  return run_denoiser(h, which, x, Bx, 0, persons, ws.temb_dyn, nullptr, out, nullptr, nullptr, st);
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base && x && timesteps && cond && out, "mmdm_denoiser_forward: null argument");
+    MMDM_REQUIRE(which == MMDM_NET_INDIVIDUAL || which == MMDM_NET_INTERACTION, "Mode not recognized");
+    MMDM_REQUIRE(h->net[which].present, "mmdm_denoiser_forward: network %d is not loaded in this handle", which);
+    const int persons = which == MMDM_NET_INTERACTION ? 2 : 1;
+    MMDM_REQUIRE(Bx >= 1 && Bx <= h->Bx, "mmdm_denoiser_forward: Bx=%d exceeds the bound workspace (%d rows)", Bx, h->Bx);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MMDM_TRY(ensure_temb(h, st));
+    Workspace& ws = h->ws;
+    const int nsl = which == MMDM_NET_INTERACTION ? 3 : 1;
+    MMDM_TRY(run_text(h, which, cond, nsl * h->cfg.text_dim, Bx, 0, nsl, st));
+    MMDM_TRY(run_time_embed(h, which, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
+    MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, Bx * persons, persons, Bx, 0, nsl, which == MMDM_NET_INTERACTION ? 1 : 0, st));
+    return run_denoiser(h, which, x, Bx, 0, persons, ws.temb_dyn, nullptr, out, nullptr, nullptr, st);
+  });
 }
 
 int mmdm_align_motions(const float* out1, const float* out2, float* out1a, float* out2a, void* emb_i, void* emb_I,
@@ -839,15 +883,18 @@ int mmdm_debug_mix_stream(int S, int nfr, int has_phase2, int ring_slots, int it
 }
 
 int mmdm_profile_enable(mmdm_handle* h, int on) {
-  MMDM_REQUIRE(h, "mmdm_profile_enable: null handle");
-  h->prof.flush();
-  h->prof.on = on != 0;
-  if (on) h->prof.recs.clear();
-  return 0;
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h, "mmdm_profile_enable: null handle");
+    h->prof.flush();
+    h->prof.on = on != 0;
+    if (on) h->prof.recs.clear();
+    return 0;
+  });
 }
 
 int mmdm_profile_read(mmdm_handle* h, mmdm_profile_entry* entries, int max_entries) {
   if (!h || !entries) return 0;
+  DeviceGuard dg(h->device);
   h->prof.flush();
   int n = 0;
   for (auto& r : h->prof.recs) {
@@ -864,5 +911,9 @@ int mmdm_profile_read(mmdm_handle* h, mmdm_profile_entry* entries, int max_entri
 }
 
 int64_t mmdm_launch_count(const mmdm_handle* h) { return h ? h->launches : 0; }
+
+const char* mmdm_last_error(const mmdm_handle* h) {
+  return (h && !h->last_error.empty()) ? h->last_error.c_str() : mmdm::get_last_error();
+}
 
 }  // extern "C"

@@ -23,16 +23,7 @@ static bool use_simt() {
   return g_debug_simt == 1;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_sm_count(); }
 
 // ------------------------------------------------------------------------------------------------
 // fused epilogue. One thread owns one output row of the tile and walks it in chunks of 32 columns (the
@@ -755,12 +746,10 @@ template <int MODE>
 static int launch_tc2(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                       const GemmEpi& ep, cudaStream_t stream) {
   using C = Gemm2Cfg<MODE>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceFlag attr;   // kernel attributes are per device
+  if (attr.first())
     MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES));
-    attr_done = true;
-  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -827,12 +816,10 @@ template <int BN, int MODE>
 static int launch_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                      const GemmEpi& ep, cudaStream_t stream) {
   using C = GemmCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceFlag attr;   // kernel attributes are per device
+  if (attr.first())
     MMDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES));
-    attr_done = true;
-  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -871,8 +858,8 @@ static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
   return launch_tc<128, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
 }
 
-// Kernel attributes are set lazily per instantiation (never inside a stream capture: the engine runs every
-// shape once eagerly before capturing, see mmdm_sample).
+// Kernel attributes are set lazily, once per instantiation and device, at the first launch. cudaFuncSetAttribute is
+// not a stream operation, so it is legal while mmdm_sample captures its step graph (which it does on first use).
 int gemm_init() { return 0; }
 
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,

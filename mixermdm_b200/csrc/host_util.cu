@@ -17,6 +17,23 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return g_last_error; }
 
+int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d < kMaxDevices ? d : kMaxDevices - 1;
+}
+
+int device_sm_count() {
+  static int n[kMaxDevices] = {};
+  const int d = current_device();
+  if (n[d] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148;
+    n[d] = v;
+  }
+  return n[d];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

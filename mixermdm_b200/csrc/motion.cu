@@ -723,21 +723,22 @@ mixstep_kernel(const MixStepParams P) {
   cluster_sync_all();   // no CTA retires while another one may still read its exports or signal its barriers
 }
 
-static int g_mix_clusters[2] = {0, 0};   // resident clusters per instantiation (0 = not queried yet)
+static int g_mix_clusters[kMaxDevices][2] = {};   // resident clusters per device and instantiation (0 = not queried yet)
 
 extern "C" int mmdm_debug_mix_trace(long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_mix_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -2;
 }
 
-int motion_init() {
+int motion_init() {   // kernel attributes are per device: done once for each device that launches
+  static PerDeviceFlag attr;
+  if (!attr.first()) return 0;
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(mixstep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX));
   MMDM_CHECK_CUDA(cudaFuncSetAttribute(mixstep_kernel<23>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX));
   return 0;
 }
 
 int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
-  static int inited = motion_init();
-  MMDM_REQUIRE(inited == 0, "mixstep: kernel attribute setup failed");
+  MMDM_REQUIRE(motion_init() == 0, "mixstep: kernel attribute setup failed");
   MMDM_REQUIRE(P.mode >= 1 && P.mode <= 4, "Mixing mode not recognized (%d)", P.mode);
   MMDM_REQUIRE(P.T >= 1 && P.B >= 1 && (long long)P.B * P.T * 12 < (1LL << 31), "mixstep: bad shape B=%d T=%d", P.B, P.T);
   MMDM_REQUIRE(P.ncfg == 1 || P.ncfg == 2, "mixstep: ncfg must be 1 or 2 (got %d)", P.ncfg);
@@ -762,7 +763,7 @@ int launch_mixstep(const MixStepParams& P, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int& resident = g_mix_clusters[NW == 1 ? 0 : 1];
+  int& resident = g_mix_clusters[current_device()][NW == 1 ? 0 : 1];
   if (resident == 0) {   // how many clusters the device holds at once (the kernel is persistent over the samples)
     cfg.gridDim = dim3((unsigned)(MIX_CLUSTER * 64));
     cfg.dynamicSmemBytes = MIX_SMEM_MAX;

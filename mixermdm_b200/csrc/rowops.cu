@@ -101,11 +101,9 @@ static void launch_ln_t(const float* h, int S, int T, const float* mod0, int ld_
   const int tasks = S * runs;
   const int blocks = (tasks + 3) / 4;   // 4 warps per block, 8 KB (16 KB dual) of modulation vectors per warp at D=1024
   const size_t smem1 = (size_t)4 * 2 * NV * 128 * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {   // the dual variant needs 64 KB at D = 1024
+  static PerDeviceFlag attr;   // per device; the dual variant needs 64 KB at D = 1024
+  if (attr.first())
     cudaFuncSetAttribute(ln_modulate_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem1));
-    attr_done = true;
-  }
   if (out1 != nullptr)
     ln_modulate_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, rev, mod0, ld_mod0, out0, mod1, ld_mod1, out1);
   else

@@ -95,8 +95,9 @@ class MixerDiffusion:
         out = res.pop(0)
         if mixer.store_influence:
             h1, h2 = res.pop(0), res.pop(0)
-            mixer.history_influence_i1.extend(list(h1.unbind(0)))
-            mixer.history_influence_i2.extend(list(h2.unbind(0)))
+            from .modules import history_view
+            mixer.history_influence_i1.extend(list(history_view(h1, mixer.mixing_mode).unbind(0)))
+            mixer.history_influence_i2.extend(list(history_view(h2, mixer.mixing_mode).unbind(0)))
         if want_out:
             o1, o2, om = res
             mixer.history_out1.extend(list(o1.unbind(0)))

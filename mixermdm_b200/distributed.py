@@ -38,9 +38,11 @@ def gather_batch(local, total, group=None):
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
 
 
-def sample_sharded(sample_fn, cond, T, base_seed=0, group=None, device=None):
+def sample_sharded(sample_fn, cond, T, base_seed=0, group=None, device=None, noise=None):
     """cond: (B, 6144) full batch of conditions (same on every rank). sample_fn(cond_slice, noise_slice) -> (b, T, 524)
     runs the local DDIM loop (e.g. `lambda c, n: diffusion.ddim_sample_loop(cfg_model, n.shape, noise=n, ...)`).
+    noise: optional (hi - lo, T, 524) initial noise of THIS rank's shard (e.g. `seeded_noise(range(lo, hi), T, seed)`
+    kept resident on the device); by default it is drawn here from the per-sample generators.
     Returns the gathered (B, T, 524) tensor."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -50,7 +52,10 @@ def sample_sharded(sample_fn, cond, T, base_seed=0, group=None, device=None):
     B = cond.shape[0]
     lo, hi = shard_bounds(B, rank, world)
     device = device if device is not None else cond.device
-    noise = seeded_noise(range(lo, hi), T, base_seed, device)
+    if noise is None:
+        noise = seeded_noise(range(lo, hi), T, base_seed, device)
+    elif noise.shape[0] != hi - lo or noise.shape[1] != T:
+        raise ValueError(f"noise: expected this rank's shard ({hi - lo}, {T}, 524), got {tuple(noise.shape)}")
     if hi > lo:
         local = sample_fn(cond[lo:hi].to(device).contiguous(), noise)
     else:

@@ -79,6 +79,15 @@ class MotionStats:
         self.motion_mean = torch.as_tensor(np.asarray(mean, dtype=np.float32))
         self.motion_std = torch.as_tensor(np.asarray(std, dtype=np.float32))
 
+    # Caller-side helpers with the reference's names (utils/utils.py:49-61, 69-82). Inside the sampling loop both are
+    # folded into the CUDA kernels (output-layer epilogue, fused mix kernel); these serve code that holds a
+    # `mixing.normalizer_model*` and converts a tensor outside the loop.
+    def forward(self, x):
+        return (x - self.motion_mean.to(x.device)) / self.motion_std.to(x.device)
+
+    def backward(self, x):
+        return x * self.motion_std.to(x.device) + self.motion_mean.to(x.device)
+
 
 def load_normalizers(normalizers=None):
     """returns (normalizer_model1 [HumanML3D stats, individual model], normalizer_model2 [InterHuman stats]).
@@ -182,6 +191,17 @@ class _Packer:
         return w
 
 
+def weights_fingerprint(module):
+    """Identity + version of every parameter and buffer under `module`. The engine runs on PACKED copies (bf16 casts,
+    concatenated AdaLN matrices) made once; the reference always reads the live parameters. Comparing this value
+    before each forward makes load_state_dict(), in-place updates (optimizer steps, .copy_()) and .to()/.half()
+    rebuild the packed copies instead of silently running on stale weights."""
+    acc = []
+    for t in list(module.parameters()) + list(module.buffers()):
+        acc.append((t.data_ptr(), t._version, t.dtype, t.device))
+    return hash(tuple(acc))
+
+
 def _absent_net(kind):
     w = NetWeights()
     w.kind, w.D, w.F, w.L, w.H = kind, 0, 0, 0, 0
@@ -204,9 +224,17 @@ class _Handle:
         self.lib.mmdm_workspace_bytes.restype = C.c_size_t
         self.lib.mmdm_launch_count.restype = C.c_int64
         with torch.cuda.device(device):
-            check(self.lib.mmdm_create(C.byref(cfg), arr, C.byref(self.h)), "mmdm_create")
+            check(self.lib.mmdm_create(C.byref(cfg), arr, C.byref(self.h)), "mmdm_create")   # device of the handle
         self.ws = None
         self.B = self.T = 0
+
+    def call(self, name, *args):
+        """invoke handle entry point `name`(h, *args); the C side makes the handle's device current for the call"""
+        check(getattr(self.lib, name)(self.h, *args), name, self.h)
+
+    def stream(self):
+        """the caller's current torch stream ON THE HANDLE'S DEVICE (not on whatever device happens to be current)"""
+        return cur_stream(self.device)
 
     def bind(self, B, T):
         if self.ws is not None and B == self.B and T == self.T:
@@ -218,14 +246,14 @@ class _Handle:
             self.ws = None
             self.ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
         base = (self.ws.data_ptr() + 1023) // 1024 * 1024
-        check(self.lib.mmdm_bind_workspace(self.h, C.c_void_p(base), C.c_size_t(need), B, T), "mmdm_bind_workspace")
+        self.call("mmdm_bind_workspace", C.c_void_p(base), C.c_size_t(need), B, T)
         self.B, self.T = B, T
 
     def launches(self):
         return int(self.lib.mmdm_launch_count(self.h))
 
     def profile(self, on):
-        check(self.lib.mmdm_profile_enable(self.h, int(on)), "mmdm_profile_enable")
+        self.call("mmdm_profile_enable", int(on))
 
     def profile_read(self):
         arr = (ProfileEntry * 64)()
@@ -244,6 +272,29 @@ class _Handle:
 
 def _f32c(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _expect(t, shape, name):
+    """the C ABI takes raw pointers: a wrong shape would be silently wrong rows or an out-of-bounds read"""
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+def _denoiser_call(hd, which, x, timesteps, cond):
+    """in2INDenoiser.forward through the handle. Like the reference (models/in2in.py:414-424, slices of cond) a cond
+    wider than the network's 768 / 2304 columns is accepted and its leading columns are used."""
+    Bx, T = x.shape[0], x.shape[1]
+    persons = 2 if which == NET_INTERACTION else 1
+    ncond = (3 if which == NET_INTERACTION else 1) * TEXT_DIM
+    _expect(x, (Bx, T, persons * NFEATS), "x")
+    _expect(timesteps, (Bx,), "timesteps")
+    if cond.dim() != 2 or cond.shape[0] != Bx or cond.shape[1] < ncond:
+        raise ValueError(f"cond: expected ({Bx}, >={ncond}), got {tuple(cond.shape)}")
+    x, cond = _f32c(x, hd.device), _f32c(cond[:, :ncond], hd.device)
+    ts = timesteps.detach().to(device=hd.device, dtype=torch.int64).contiguous()
+    out = torch.empty_like(x)
+    hd.call("mmdm_denoiser_forward", which, ptr(x), ptr(ts), ptr(cond), ptr(out), Bx, hd.stream())
+    return out
 
 
 class MixerEngine:
@@ -281,6 +332,7 @@ class MixerEngine:
         cfg.mean1, cfg.std1, cfg.mean2, cfg.std2 = pk.p(self.mean1), pk.p(self.std1), pk.p(self.mean2), pk.p(self.std2)
         self.hd = _Handle(cfg, nets, pk.keep, device)
         self.device = device
+        self.fingerprint = weights_fingerprint(mixer)
         self.nsteps = cfg.nsteps
         self.mixing_mode = cfg.mixing_mode
         self.cfg_scale = float(cfg_scale)
@@ -293,6 +345,16 @@ class MixerEngine:
     def bind(self, B, T):
         self.hd.bind(B, T)
 
+    def _check_batch(self, B):
+        """The reference's centring calls torch.cross without `dim` (utils/alignment.py:198): for a batch of exactly
+        3 the legacy rule picks the BATCH axis, so every sample is turned by +-90 degrees about X depending on the
+        other two samples' hips. That cross-sample artefact is not reproduced; rather than return something the
+        reference would not, a centred sampler step on 3 samples is refused (pad the batch to 4 or split it)."""
+        if B == 3 and self.center:
+            raise MmdmError("batch of exactly 3 samples: the reference's center_motion takes torch.cross over the batch "
+                            "axis there (legacy dim rule) and mixes samples; this engine does not reproduce that. "
+                            "Use another batch size (e.g. pad to 4).")
+
     def _check_state(self, x, name):
         if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
             raise TypeError(f"{name}: expected a contiguous fp32 CUDA tensor")
@@ -301,30 +363,42 @@ class MixerEngine:
     def set_condition(self, cond):
         cond = _f32c(cond, self.device)
         assert cond.shape == (self.hd.B, 8 * TEXT_DIM), f"cond must be ({self.hd.B}, {8 * TEXT_DIM})"
-        check(self.lib.mmdm_set_condition(self.hd.h, ptr(cond), cur_stream()), "mmdm_set_condition")
+        self.hd.call("mmdm_set_condition", ptr(cond), self.hd.stream())
 
     def set_state(self, x1, x2, step_index):
         x1, x2 = _f32c(x1, self.device), _f32c(x2, self.device)
-        check(self.lib.mmdm_set_state(self.hd.h, ptr(x1), ptr(x2), int(step_index), cur_stream()), "mmdm_set_state")
+        for x in (x1, x2):
+            if tuple(x.shape) != (self.hd.B, self.hd.T, 2 * NFEATS):
+                raise ValueError(f"state must be ({self.hd.B}, {self.hd.T}, {2 * NFEATS}), got {tuple(x.shape)}")
+        self.hd.call("mmdm_set_state", ptr(x1), ptr(x2), int(step_index), self.hd.stream())
 
     def get_state(self):
         shape = (self.hd.B, self.hd.T, 2 * NFEATS)
         x1 = torch.empty(shape, device=self.device)
         x2 = torch.empty(shape, device=self.device)
-        check(self.lib.mmdm_get_state(self.hd.h, ptr(x1), ptr(x2), cur_stream()), "mmdm_get_state")
+        self.hd.call("mmdm_get_state", ptr(x1), ptr(x2), self.hd.stream())
         return x1, x2
 
     def step(self, final_out=None):
-        check(self.lib.mmdm_step(self.hd.h, ptr(final_out), cur_stream()), "mmdm_step")
+        if final_out is not None:
+            self._check_state(final_out, "final_out")
+        self._check_batch(self.hd.B)
+        self.hd.call("mmdm_step", ptr(final_out), self.hd.stream())
 
     def sample(self, cond, noise, out=None, store_influence=False, use_graph=True, store_outputs=False):
         """whole DDIM loop; cond (B,6144), noise (B,T,524) device fp32 -> (B,T,524) real-space prediction.
         store_influence: also return the per-step expanded weights, 2 x (nsteps, 2B, T, 262).
         store_outputs:   also return out1 / out2 / out_influenced of every step, 3 x (nsteps, 2B, T, 524)."""
         B, T = noise.shape[0], noise.shape[1]
+        _expect(noise, (B, T, 2 * NFEATS), "noise")
+        _expect(cond, (B, 8 * TEXT_DIM), "cond")
+        self._check_batch(B)
         self.bind(B, T)
         cond = _f32c(cond, self.device)
         noise = _f32c(noise, self.device)
+        if out is not None:
+            self._check_state(out, "out")
+            _expect(out, (B, T, 2 * NFEATS), "out")
         if out is None:
             out = torch.empty(B, T, 2 * NFEATS, device=self.device)
         h1 = h2 = o1 = o2 = om = None
@@ -333,8 +407,8 @@ class MixerEngine:
             h2 = torch.empty(self.nsteps, 2 * B, T, NFEATS, device=self.device)
         if store_outputs:
             o1, o2, om = [torch.empty(self.nsteps, 2 * B, T, 2 * NFEATS, device=self.device) for _ in range(3)]
-        check(self.lib.mmdm_sample(self.hd.h, ptr(cond), ptr(noise), ptr(out), ptr(h1), ptr(h2), ptr(o1), ptr(o2),
-                                   ptr(om), int(use_graph), cur_stream()), "mmdm_sample")
+        self.hd.call("mmdm_sample", ptr(cond), ptr(noise), ptr(out), ptr(h1), ptr(h2), ptr(o1), ptr(o2), ptr(om),
+                     int(use_graph), self.hd.stream())
         res = [out]
         if store_influence:
             res += [h1, h2]
@@ -346,6 +420,10 @@ class MixerEngine:
     def mixer_forward(self, x1, x2, timesteps, cond, want_aux=False, want_influence=False, cfg_combine=False,
                       cfg_scale=None):
         Bx, T = x1.shape[0], x1.shape[1]
+        _expect(x1, (Bx, T, 2 * NFEATS), "x1")
+        _expect(x2, (Bx, T, 2 * NFEATS), "x2")
+        _expect(cond, (Bx, 8 * TEXT_DIM), "cond")
+        _expect(timesteps, (Bx,), "timesteps")
         x1, x2, cond = _f32c(x1, self.device), _f32c(x2, self.device), _f32c(cond, self.device)
         ts = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()
         rows = Bx // 2 if cfg_combine else Bx
@@ -354,10 +432,9 @@ class MixerEngine:
         o2 = torch.empty(Bx, T, 2 * NFEATS, device=self.device) if want_aux else None
         w1 = torch.empty(Bx, T, NFEATS, device=self.device) if want_influence else None
         w2 = torch.empty(Bx, T, NFEATS, device=self.device) if want_influence else None
-        check(self.lib.mmdm_mixer_forward(self.hd.h, ptr(x1), ptr(x2), ptr(ts), ptr(cond), ptr(out), ptr(o1), ptr(o2),
-                                          ptr(w1), ptr(w2), Bx, int(cfg_combine),
-                                          C.c_float(self.cfg_scale if cfg_scale is None else cfg_scale), cur_stream()),
-              "mmdm_mixer_forward")
+        self.hd.call("mmdm_mixer_forward", ptr(x1), ptr(x2), ptr(ts), ptr(cond), ptr(out), ptr(o1), ptr(o2), ptr(w1),
+                     ptr(w2), Bx, int(cfg_combine), C.c_float(self.cfg_scale if cfg_scale is None else cfg_scale),
+                     self.hd.stream())
         return out, o1, o2, w1, w2
 
     def cfg_forward(self, x, x2, timesteps, cond, scale, store_influence=False, owner=None):
@@ -369,18 +446,13 @@ class MixerEngine:
         out, _, _, w1, w2 = self.mixer_forward(xx, xx2, tt, cc, want_influence=store_influence, cfg_combine=True,
                                                cfg_scale=scale)
         if store_influence and owner is not None:
-            owner.history_influence_i1.append(w1)
-            owner.history_influence_i2.append(w2)
+            from .modules import history_view
+            owner.history_influence_i1.append(history_view(w1, self.mixing_mode))
+            owner.history_influence_i2.append(history_view(w2, self.mixing_mode))
         return out
 
     def denoiser_forward(self, which, x, timesteps, cond):
-        Bx, T = x.shape[0], x.shape[1]
-        x, cond = _f32c(x, self.device), _f32c(cond, self.device)
-        ts = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()
-        out = torch.empty_like(x)
-        check(self.lib.mmdm_denoiser_forward(self.hd.h, which, ptr(x), ptr(ts), ptr(cond), ptr(out), Bx, cur_stream()),
-              "mmdm_denoiser_forward")
-        return out
+        return _denoiser_call(self.hd, which, x, timesteps, cond)
 
 
 class StandaloneDenoiser:
@@ -403,20 +475,16 @@ class StandaloneDenoiser:
         cfg.coef = pk.p(dummy)
         self.hd = _Handle(cfg, nets, pk.keep, device)
         self.device = device
+        self.fingerprint = weights_fingerprint(den)
         self.rows = 0
         self.T = 0
 
-    def matches(self, x):
-        return x.device == self.device
+    def matches(self, den, x):
+        return x.device == self.device and weights_fingerprint(den) == self.fingerprint
 
     def forward(self, x, timesteps, cond):
         Bx, T = x.shape[0], x.shape[1]
         if Bx > self.rows or T != self.T:
             self.hd.bind((Bx + 1) // 2, T)
             self.rows, self.T = 2 * ((Bx + 1) // 2), T
-        x, cond = _f32c(x, self.device), _f32c(cond, self.device)
-        ts = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()
-        out = torch.empty_like(x)
-        check(self.hd.lib.mmdm_denoiser_forward(self.hd.h, self.kind, ptr(x), ptr(ts), ptr(cond), ptr(out), Bx,
-                                                cur_stream()), "mmdm_denoiser_forward")
-        return out
+        return _denoiser_call(self.hd, self.kind, x, timesteps, cond)

@@ -37,8 +37,9 @@ def format_generated(output, max_length, mean=None, std=None):
         if m.numel() != nf or s.numel() != nf:
             raise ValueError(f"mean/std must hold {nf} values")
     lib = _lib.load()
-    _lib.check(lib.mmdm_format_motion(_lib.ptr(x), _lib.ptr(out), B, T, int(max_length), nf, _lib.ptr(m), _lib.ptr(s),
-                                      _lib.cur_stream()), "format_motion")
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mmdm_format_motion(_lib.ptr(x), _lib.ptr(out), B, T, int(max_length), nf, _lib.ptr(m),
+                                          _lib.ptr(s), _lib.cur_stream()), "format_motion")
     return out.view(B, max_length, 2, nf)
 
 

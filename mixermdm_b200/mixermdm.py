@@ -21,7 +21,11 @@ from .modules import (ClassifierFreeSampleModelX2, FFN, Mixer, PositionalEncodin
 
 class AttrDict(dict):
     """minimal stand-in for yacs.CfgNode (attribute access + `in`), used when yacs is not installed"""
-    __getattr__ = dict.__getitem__
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None   # hasattr(), copy.deepcopy() and pickle rely on AttributeError
 
     def __setattr__(self, k, v):
         self[k] = v
@@ -196,7 +200,10 @@ class MixerMDM(nn.Module, _ClipTextTower):
         if load_submodel_checkpoints:
             for model, c in ((self.model1, self.cfg_model1), (self.model2, self.cfg_model2)):
                 ck = c.get("CHECKPOINT")
-                if ck and os.path.exists(ck):
+                if ck:   # like the reference (models/mixermdm.py:43-59) a configured but missing file is an error
+                    if not os.path.exists(ck):
+                        raise FileNotFoundError(f"sub-model checkpoint {ck!r} (cfg.CHECKPOINT) not found; pass "
+                                                "load_submodel_checkpoints=False to build without it")
                     model.load_state_dict(torch.load(ck, map_location="cpu"), strict=True)
         for m in (self.model1, self.model2):
             for p in m.parameters():

@@ -151,9 +151,15 @@ class in2INDenoiser(nn.Module):
         PE table; cond: (B,768) / (B,2304). Returns the normalised-space x0 prediction, same shape as x."""
         if mask is not None:
             raise NotImplementedError("key-padding masks are not part of the MixerMDM sampling path (mask=None)")
-        if self._standalone is None or not self._standalone.matches(x):
+        if self._standalone is None or not self._standalone.matches(self, x):
+            self._standalone = None   # parameters changed (load_state_dict, in-place update, .to()): repack
             self._standalone = _engine.StandaloneDenoiser(self, x)
         return self._standalone.forward(x, timesteps, cond)
+
+    def __getstate__(self):   # the engine holds ctypes pointers: copies / pickles rebuild it on first use
+        d = dict(self.__dict__)
+        d["_standalone"] = None
+        return d
 
 
 class Influence(nn.Module):
@@ -170,6 +176,12 @@ class Influence(nn.Module):
             self.out = nn.Linear(input_shape, 23)
         else:
             raise ValueError("Mode not recognized")
+
+
+def history_view(w, mixing_mode):
+    """The kernels write the weights expanded to the 262 features. The reference stores them that way for the
+    joint-wise modes 3/4, but as (Be, T, 1) for the global / temporal modes 1/2 (models/mixermdm.py:739-796)."""
+    return w[..., :1] if mixing_mode in (1, 2) else w
 
 
 class Mixer(nn.Module):
@@ -204,7 +216,8 @@ class Mixer(nn.Module):
         """the CUDA engine bound to a workspace for `batch_rows` network rows (CFG-doubled batch) of `frames`;
         rebuilt when a sampler asks for another schedule / guidance scale / centring flag"""
         eng = self._engine
-        stale = eng is None or eng.device != torch.device(device)
+        stale = (eng is None or eng.device != torch.device(device) or
+                 eng.fingerprint != _engine.weights_fingerprint(self))   # live parameters changed since packing
         if eng is not None and not stale:
             stale = ((sched is not None and not eng.sched.same_as(sched)) or
                      (cfg_scale is not None and float(cfg_scale) != eng.cfg_scale) or
@@ -222,8 +235,14 @@ class Mixer(nn.Module):
         return self._engine
 
     def invalidate_engine(self):
-        """call after changing parameters in place (e.g. load_state_dict) so the packed copies are rebuilt"""
+        """drop the packed weight copies now. Not needed for correctness: engine() compares a fingerprint of the live
+        parameters (identity + version counters) with the one taken at pack time and repacks on any difference."""
         self._engine = None
+
+    def __getstate__(self):   # the engine holds ctypes pointers: copies / pickles rebuild it on first use
+        d = dict(self.__dict__)
+        d["_engine"] = None
+        return d
 
     def forward(self, x1, timesteps, cond=None, mask=None, x2=None):
         """x1/x2: (Be,T,524) state in individual / interaction space, timesteps (Be,), cond (Be,6144).
@@ -235,8 +254,8 @@ class Mixer(nn.Module):
                                                     want_aux=(self.mode != "eval_intermediate"),
                                                     want_influence=self.store_influence)
         if self.store_influence:
-            self.history_influence_i1.append(w1)
-            self.history_influence_i2.append(w2)
+            self.history_influence_i1.append(history_view(w1, self.mixing_mode))
+            self.history_influence_i2.append(history_view(w2, self.mixing_mode))
         if self.mode == "train":
             return out, out1, out2
         if self.mode == "eval":

@@ -41,8 +41,9 @@ def linear_bf16(a, w, *, mode, out, bias=None, resid=None, out_bf16=None, vt=Non
     ep.mean = ptr(mean).value if mean is not None else None
     ep.nfeats = nfeats
     ep.persons_per_row = persons_per_row
-    check(lib.mmdm_linear_bf16(ptr(a), C.c_int(a.stride(0)), ptr(w), C.c_int(w.stride(0)), M, N, K, C.byref(ep),
-                               cur_stream()), "mmdm_linear_bf16")
+    with torch.cuda.device(a.device):   # kernels launch on the tensors' device, whatever the current one is
+        check(lib.mmdm_linear_bf16(ptr(a), C.c_int(a.stride(0)), ptr(w), C.c_int(w.stride(0)), M, N, K, C.byref(ep),
+                                   cur_stream()), "mmdm_linear_bf16")
     return out
 
 
@@ -55,18 +56,20 @@ def ln_modulate(h, T, mod0, out0=None, mod1=None, out1=None):
         out0 = torch.empty(M, D, dtype=torch.bfloat16, device=h.device)
     if mod1 is not None and out1 is None:
         out1 = torch.empty(M, D, dtype=torch.bfloat16, device=h.device)
-    check(lib.mmdm_ln_modulate(ptr(h), M, D, T, ptr(mod0), C.c_int(mod0.stride(0)), ptr(out0),
-                               ptr(mod1), C.c_int(mod1.stride(0) if mod1 is not None else 0), ptr(out1),
-                               cur_stream()), "mmdm_ln_modulate")
+    with torch.cuda.device(h.device):
+        check(lib.mmdm_ln_modulate(ptr(h), M, D, T, ptr(mod0), C.c_int(mod0.stride(0)), ptr(out0),
+                                   ptr(mod1), C.c_int(mod1.stride(0) if mod1 is not None else 0), ptr(out1),
+                                   cur_stream()), "mmdm_ln_modulate")
     return (out0, out1) if mod1 is not None else out0
 
 
 def attention(q, k, vt, out, S, T, H, hd, kv_xor=0):
     """q/k: 2-D bf16 views (rows = s*T+t) whose columns are the H*hd projected features; vt: (S*H, hd, Tp)."""
     lib = _lib.load()
-    check(lib.mmdm_attention(ptr(q), C.c_int(q.stride(0)), ptr(k), C.c_int(k.stride(0)), ptr(vt),
-                             C.c_int(vt.stride(1)), ptr(out), C.c_int(out.stride(0)), S, T, H, hd, kv_xor,
-                             cur_stream()), "mmdm_attention")
+    with torch.cuda.device(q.device):
+        check(lib.mmdm_attention(ptr(q), C.c_int(q.stride(0)), ptr(k), C.c_int(k.stride(0)), ptr(vt),
+                                 C.c_int(vt.stride(1)), ptr(out), C.c_int(out.stride(0)), S, T, H, hd, kv_xor,
+                                 cur_stream()), "mmdm_attention")
     return out
 
 
@@ -76,6 +79,7 @@ def small_linear(a, w, b=None, act=0):
     R, K = a.shape
     N = w.shape[0]
     out = torch.empty(R, N, dtype=torch.float32, device=a.device)
-    check(lib.mmdm_small_linear(ptr(a), C.c_int(a.stride(0)), ptr(w.contiguous()), ptr(b), ptr(out), N, R, N, K,
-                                act, cur_stream()), "mmdm_small_linear")
+    with torch.cuda.device(a.device):
+        check(lib.mmdm_small_linear(ptr(a), C.c_int(a.stride(0)), ptr(w.contiguous()), ptr(b), ptr(out), N, R, N, K,
+                                    act, cur_stream()), "mmdm_small_linear")
     return out

@@ -31,7 +31,9 @@ def smooth_motion(output, sigma=1.0, truncate=4.0):
     w = (C.c_float * len(taps))(*[float(v) for v in taps])
     out = torch.empty_like(x3)
     lib = _lib.load()
-    _lib.check(lib.mmdm_smooth_motion(_lib.ptr(x3), _lib.ptr(out), B, T, F, w, radius, _lib.cur_stream()), "smooth_motion")
+    with torch.cuda.device(x3.device):
+        _lib.check(lib.mmdm_smooth_motion(_lib.ptr(x3), _lib.ptr(out), B, T, F, w, radius, _lib.cur_stream()),
+                   "smooth_motion")
     return out.view_as(x)
 
 

@@ -56,7 +56,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mixermdm_b200.h but not exported"
-    assert lib.mmdm_abi_version() == 1
+    assert lib.mmdm_abi_version() == 2
     assert ctypes.sizeof(_lib.Epilogue) % 8 == 0
 
 
@@ -195,3 +195,78 @@ def test_mix_kernel_stream_arithmetic_matches_enumeration():
                             assert out[6] == 0
     assert lib.mmdm_debug_mix_stream(2, 4, 1, 5, 0, out) != 0          # ring deeper than a sample's frames: rejected
     assert lib.mmdm_debug_mix_stream(2, 4, 1, 4, 16, out) != 0         # item outside the stream
+
+
+def test_attrdict_behaves_like_a_config_node():
+    import copy
+    from mixermdm_b200.mixermdm import AttrDict
+    cfg = AttrDict(A=1, SUB=AttrDict(B=2))
+    assert cfg.A == 1 and cfg.SUB.B == 2 and "A" in cfg
+    assert not hasattr(cfg, "MISSING")               # AttributeError, not KeyError
+    with pytest.raises(AttributeError):
+        cfg.MISSING
+    c2 = copy.deepcopy(cfg)
+    c2.SUB.B = 3
+    assert cfg.SUB.B == 2 and c2.SUB.B == 3
+
+
+def test_weight_fingerprint_tracks_parameter_changes_and_modules_copy():
+    """the packed-weight cache is keyed on this fingerprint (stale weights after load_state_dict)"""
+    import copy
+    from mixermdm_b200.engine import weights_fingerprint
+    _, meta = load_golden()
+    mix, sd = build_mixer(meta["dims"])
+    f0 = weights_fingerprint(mix)
+    assert weights_fingerprint(mix) == f0
+    mix.load_state_dict(sd)                                   # same values, but copy_() bumps the version counters
+    f1 = weights_fingerprint(mix)
+    assert f1 != f0
+    with torch.no_grad():
+        next(mix.influence.parameters()).add_(1.0)            # in-place update (an optimizer step)
+    f2 = weights_fingerprint(mix)
+    assert f2 != f1
+    mix.double()                                              # _apply replaces the storages
+    assert weights_fingerprint(mix) != f2
+    mix._engine = object()                                    # stands in for the ctypes-holding engine
+    m2 = copy.deepcopy(mix)
+    assert m2._engine is None and m2.denoiser1._standalone is None
+    assert list(m2.state_dict().keys()) == list(mix.state_dict().keys())
+
+
+def test_motion_stats_forward_backward_and_history_view():
+    from mixermdm_b200.engine import MotionStats
+    from mixermdm_b200.modules import history_view
+    mean, std = np.linspace(-1, 1, 262, dtype=np.float32), np.linspace(0.5, 1.5, 262, dtype=np.float32)
+    n = MotionStats(mean, std)
+    x = torch.randn(2, 5, 262)
+    assert torch.allclose(n.backward(n.forward(x)), x, atol=1e-5)
+    assert torch.allclose(n.forward(x), (x - torch.from_numpy(mean)) / torch.from_numpy(std))
+    w = torch.rand(4, 5, 262)
+    assert history_view(w, 1).shape == (4, 5, 1) and history_view(w, 2).shape == (4, 5, 1)
+    assert history_view(w, 3).shape == (4, 5, 262) and history_view(w, 4) is w
+
+
+def test_missing_submodel_checkpoint_is_an_error():
+    from mixermdm_b200.mixermdm import AttrDict, MixerMDM
+    den = AttrDict(NAME="in2IN", NUM_LAYERS=1, NUM_HEADS=2, DROPOUT=0.1, INPUT_DIM=262, LATENT_DIM=128, FF_SIZE=256,
+                   ACTIVATION="gelu", CHECKPOINT="/nonexistent/in2in.ckpt", STRATEGY="ddim50")
+    ind = AttrDict(den, NAME="in2INind")
+    cfg = AttrDict(NAME="MixerMDM", MODEL1=ind, MODEL2=den, ACTIVATION="gelu", MOTION_REP="global", CFG_WEIGHT=3.5,
+                   MIXING_MODE=4, DIFFUSION_STEPS=1000, BETA_SCHEDULER="cosine", SAMPLER="uniform",
+                   FORCE_INFLUENCE_VAL=None, INPUT_DIM=262, LATENT_DIM=512, FF_SIZE=1024, NUM_LAYERS=1, NUM_HEADS=8,
+                   DROPOUT=0.1)
+    with pytest.raises(FileNotFoundError):
+        MixerMDM(cfg, normalizers=synth.normalizer_stats())
+    MixerMDM(cfg, normalizers=synth.normalizer_stats(), load_submodel_checkpoints=False)
+
+
+def test_last_error_is_per_thread_without_a_handle():
+    from mixermdm_b200 import _lib
+    lib = _lib.load()
+    assert lib.mmdm_mix_cfg_ddim(None, None) != 0                 # null argument: fails before touching a device
+    assert b"null argument" in lib.mmdm_last_error(None)
+    import threading
+    seen = []
+    t = threading.Thread(target=lambda: seen.append(lib.mmdm_last_error(None)))
+    t.start(); t.join()
+    assert seen == [b""]                                          # another thread has its own (empty) slot

@@ -39,7 +39,7 @@ def _inputs(meta):
 def test_library_is_the_product_path():
     from mixermdm_b200 import _lib
     lib = _lib.load()
-    assert lib.mmdm_abi_version() == 1
+    assert lib.mmdm_abi_version() == 2
 
 
 def test_denoiser_forward_vs_reference_golden(golden):

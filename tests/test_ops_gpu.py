@@ -123,7 +123,13 @@ def _ref_attention(q, k, v, scale):
 @pytest.mark.parametrize("T,H,hd,S,kv_xor", [(300, 8, 128, 4, 0), (300, 8, 64, 4, 0), (300, 2, 128, 4, 1),
                                              (77, 2, 64, 2, 0), (128, 2, 128, 2, 1), (255, 1, 64, 2, 0),
                                              (303, 2, 128, 2, 0), (303, 2, 64, 4, 1), (24, 4, 64, 100, 0), (159, 2, 128, 2, 0),
-                                             (160, 2, 64, 2, 1), (300, 8, 128, 40, 1), (300, 8, 64, 56, 0)])
+                                             (160, 2, 64, 2, 1), (300, 8, 128, 40, 1), (300, 8, 64, 56, 0),
+                                             # block / tile boundaries of the 64-key, 128-row tiling
+                                             (1, 2, 64, 2, 0), (63, 2, 128, 2, 0), (64, 2, 64, 2, 1), (127, 1, 128, 6, 0),
+                                             (191, 2, 64, 2, 0), (256, 2, 128, 2, 1), (319, 2, 128, 3, 0),
+                                             # longer than the resident K/V ring: blocks stream through it
+                                             (320, 2, 128, 2, 0), (400, 2, 64, 4, 1), (512, 2, 128, 2, 0),
+                                             (512, 8, 64, 40, 1), (700, 1, 128, 4, 0)])
 def test_attention_zero_sink(ops, T, H, hd, S, kv_xor):
     from mixermdm_b200._lib import EPI_BF16
     D = H * hd
@@ -153,6 +159,34 @@ def test_attention_zero_sink(ops, T, H, hd, S, kv_xor):
     ref = _ref_attention(q, k, v, 1.0 / math.sqrt(hd)).permute(0, 2, 1, 3).reshape(M, D)
     assert _relerr(out, ref) < 1e-2
     assert (out.float() - ref).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize("T,hd", [(300, 128), (300, 64), (512, 128)])
+def test_attention_online_rescale(ops, T, hd):
+    """Keys whose logits grow along the sequence: later 64-key blocks exceed the running maximum by far more than the
+    lazy-rescale threshold (2^8), so the in-place rescale of O and of the row sum is exercised in every row."""
+    S, H = 3, 2
+    D = H * hd
+    Tp = (T + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = (3.0 * torch.randn(S, T, H, hd, device="cuda", generator=g)).to(torch.bfloat16)
+    ramp = (0.1 + 4.0 * torch.arange(T, device="cuda") / T).view(1, T, 1, 1)
+    k = (torch.randn(S, T, H, hd, device="cuda", generator=g) * ramp).to(torch.bfloat16)
+    v = torch.randn(S, T, H, hd, device="cuda", generator=g).to(torch.bfloat16)
+    qk = torch.cat([q.reshape(S * T, D), k.reshape(S * T, D)], 1).contiguous()
+    vt = torch.zeros(S * H, hd, Tp, dtype=torch.bfloat16, device="cuda")
+    vt[..., :T] = v.permute(0, 2, 3, 1).reshape(S * H, hd, T)
+    out = torch.zeros(S * T, D, dtype=torch.bfloat16, device="cuda")
+    ops.attention(qk[:, :D], qk[:, D:], vt, out, S, T, H, hd, 0)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    logits = torch.einsum("shqd,shkd->shqk", qf, kf) / math.sqrt(hd)
+    blockmax = torch.stack([logits[..., i:i + 64].amax(-1) for i in range(0, T, 64)], -1).clamp_min(0)
+    jumps = (blockmax[..., 1:] - blockmax.cummax(-1).values[..., :-1]).amax(-1)
+    assert (jumps > 8 * math.log(2)).float().mean().item() > 0.5      # the rescale path really runs in most rows
+    ref = _ref_attention(qf, kf, vf, 1.0 / math.sqrt(hd)).permute(0, 2, 1, 3).reshape(S * T, D)
+    assert torch.isfinite(out.float()).all()
+    assert _relerr(out, ref) < 1e-2
 
 
 def test_small_linear(ops):

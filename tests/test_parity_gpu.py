@@ -418,13 +418,13 @@ def test_batched_generator_equals_one_prompt_per_call(golden):
     model.mixing.load_state_dict(synth.synthetic_state_dict(model.mixing.state_dict(), seed=meta["weights_seed"]), strict=True)
     model = model.to(DEV)
     g = torch.Generator().manual_seed(11)
-    lens, reps = [24, 17, 24, 24], [1, 2, 3, 1]
+    lens, reps = [24, 17, 24, 24, 17], [1, 2, 4, 1, 1]      # T=17: 2 + 1 = 3 rows, padded to 4 inside the generator
     reqs = [MotionRequest(torch.randn(6144, generator=g).to(DEV), T, r, torch.randn(r, T, 524, generator=g).to(DEV))
             for T, r in zip(lens, reps)]
     (m1, s1), _ = synth.normalizer_stats()
     gen = BatchedGenerator(model, max_length=32, normalizer=(m1, s1), max_batch=8)
     res = gen.generate(reqs)
-    assert gen.calls == 2                                   # lengths {24, 17}: two sampler calls for four prompts
+    assert gen.calls == 2                                   # lengths {24, 17}: two sampler calls for five prompts
     for r, got in zip(reqs, res):
         one = model.forward_test({"cond": r.cond.unsqueeze(0).expand(r.repeats, -1).contiguous(), "noise": r.noise.clone(),
                                   "motion_lens": torch.full((r.repeats,), r.motion_len, dtype=torch.long)})["output"]

@@ -38,24 +38,25 @@ qk = (torch.randn(M, 2 * D, device=dev, generator=g) * 0.5).to(torch.bfloat16)
 vt = (torch.randn(S * H, hd, Tp, device=dev, generator=g) * 0.5).to(torch.bfloat16)
 att = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
 lib = _lib.load()
-trace = torch.zeros(12 * 24 * 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(12 * 64 * 16, dtype=torch.int64, device=dev)
 for _ in range(3):
     ops.attention(qk[:, :D], qk[:, D:], vt, att, S, T, H, hd, 0)
 torch.cuda.synchronize()
 assert lib.mmdm_debug_attn_trace(C.c_void_p(trace.data_ptr())) == 0
 ops.attention(qk[:, :D], qk[:, D:], vt, att, S, T, H, hd, 0)
 torch.cuda.synchronize()
-tr = trace.cpu().view(12, 24, 16)
+tr = trace.cpu().view(12, 64, 16)
 t0 = int(tr[tr > 0].min())
-names = {
-    "sm": ["wait_S", "S_ready", "max_done", "S_released", "P_g0", "P_g1", "P_g2", "O_ready", "out_done", "-", "wait_O"],
-    8: ["K_issue", "Q_issue", "V_issue"],
-    9: ["early_begin", "early_issue", "early_commit", "pv_g0", "pv_g1", "pv_g2", "pv_commit", "-", "-", "late_commit"],
-}
-for j in range(0, 10):
-    print(f"--- job {j}")
+SM = ["blk_begin", "S_in_regs", "prefetch_tried", "exp_done", "P_published", "wait_O", "O_ready", "tile_done", "max_done", "exp_half", "mid_try_done", "end_try_done"]
+MMA = ["S_begin", "K_ok", "S_issued", "PV_begin", "P_ok", "V_ok", "PV_issued", "-"]
+NB = (T + 1 + 63) // 64
+print("per-warp S_in_regs / exp_done / P_published of blocks 1..8 (softmax warps 0-7)")
+for n in range(1, 9):
+    print(f"  block {n}: " + "  ".join(f"w{w}:{int(tr[w, n, 1]) - t0}/{int(tr[w, n, 3]) - t0}/{int(tr[w, n, 4]) - t0}" for w in range(8)))
+for n in range(0, 24):
+    print(f"--- block {n} (tile {n // NB} of the warpgroup, kb {n % NB})")
     for w in (0, 4, 8, 9):
-        nm = names["sm"] if w < 8 else names[w]
-        ev = [(int(tr[w, j, e]) - t0, nm[e]) for e in range(len(nm)) if tr[w, j, e] > 0]
+        nm = SM if w < 8 else MMA
+        ev = [(int(tr[w, n, e]) - t0, nm[e]) for e in range(len(nm)) if tr[w, n, e] > 0]
         ev.sort()
-        print(f"  warp {w}: " + "  ".join(f"{n}@{t}" for t, n in ev))
+        print(f"  warp {w}: " + "  ".join(f"{nn}@{tt}" for tt, nn in ev))

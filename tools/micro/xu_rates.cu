@@ -94,7 +94,7 @@ void run(const char* name, int warps_per_sm) {
   cudaFree(out);
 }
 int main() {
-  for (int w : {8, 16}) {
+  for (int w : {4, 8, 16}) {
     run<0>("ex2.approx.ftz.f32", w);
     run<1>("F2FP bf16x2 pack (+FADD)", w);
     run<2>("poly exp2 (FMA pipe)", w);

@@ -16,6 +16,8 @@
 // by more than 8 in the exponent (factor 256): the rescale of O is rare and done in place by the warpgroup itself.
 #include "attention.cuh"
 
+#include <stdlib.h>
+
 namespace mmdm {
 
 struct AttnParams {
@@ -25,6 +27,7 @@ struct AttnParams {
   int GS;        // tiles that share one pass over the K / V blocks (see "groups" below)
   int kv_xor, rev;
   int ldo, wide_store;   // output row pitch (elements); 32-byte stores allowed
+  int stagger;           // cycles the second warpgroup starts late
   __nv_bfloat16* out;
   float scale_log2, tau_raw;
 };
@@ -39,8 +42,8 @@ struct AttnCfg {
   static constexpr uint32_t NBAR = 18 + 4 * NSLOT;
   static constexpr uint32_t USED_BYTES = 2 * Q_BYTES + NSLOT * (KB_BYTES + VB_BYTES) + NBAR * 8 + 16;
   static constexpr size_t SMEM_BYTES = USED_BYTES + 1024;
-  // TMEM columns: warpgroup g owns [g*128, +128) as two 64-column S buffers (block m -> buffer m & 1; P(m), packed
-  // bf16, overwrites the first 32 columns of its own S once that is in registers) | O_g [256 + g*HD, +HD)
+  // TMEM columns: warpgroup g owns [g*128, +128): S [0,64) | P buffer 0 [64,96) | P buffer 1 [96,128) (packed bf16,
+  // block m -> buffer m & 1); O_g [256 + g*HD, +HD)
   static constexpr uint32_t SP_COL = 0, O_COL = 256;
   static constexpr int THREADS = 352;   // 8 softmax warps, 2 MMA warps (one per warpgroup), loader
 };
@@ -104,13 +107,14 @@ __device__ __forceinline__ void ring_next(RingPos& r) {
   }
 }
 
-// Barrier protocol (one CTA; g = softmax warpgroup, m = running block number of the warpgroup, b = m & 1). A barrier may
-// run ONE phase ahead of its waiter, never two (parity waits alias), which is why everything tied to the two S / P
-// buffers has one barrier per buffer.
-//   sfull[g,b] MMA commit      S(m) complete in buffer b. A commit covers ALL earlier MMAs of the issuing thread and the
-//                              issue order is P V(m - 2), S(m): S(m) complete => P V(m - 2) complete (its V block and,
-//                              trivially, its P are free) - the softmax warps release K and V ring slots from that.
-//   pfull[g,b] 4 softmax warps P(m) written over the first half of S(m)'s columns (so S(m) has been read, too)
+// Barrier protocol (one CTA; g = softmax warpgroup, m = running block number of the warpgroup). A barrier may run ONE
+// phase ahead of its waiter, never two (parity waits alias).
+//   sfull[g]   MMA commit      S(m) complete. A commit covers ALL earlier MMAs of the issuing thread and the issue order
+//                              is S(m+1), PV(m), S(m+2): S(m+2) complete => P V(m) complete, i.e. P buffer m & 1 and the
+//                              V block of m are free - the softmax warps release K and V ring slots from that.
+//   sfree[g]   4 softmax warps S(m) is in registers -> S(m+1) may be issued (long before P(m) exists: the tensor pipe
+//                              is never in the softmax warps' critical path)
+//   pfull[g,b] 4 softmax warps P(m) written to buffer b = m & 1
 //   flush[g]   MMA commit      once per tile behind P V(NB - 2): what S(m + 1) is for earlier blocks, for the rescale
 //                              path of the last block
 //   ofull[g]   MMA commit      last P V of the tile complete;   ofree[g]  4 warps: O_g read out
@@ -130,7 +134,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + C::NSLOT * C::VB_BYTES);
   uint64_t* qfull = bars;          // [2]
   uint64_t* qfree = bars + 2;      // [2]
-  uint64_t* sfull = bars + 4;      // [2][2]
+  uint64_t* sfull = bars + 4;      // [2]
+  uint64_t* sfree = bars + 6;      // [2]
   uint64_t* pfull = bars + 8;      // [2][2]
   uint64_t* ofull = bars + 12;     // [2]
   uint64_t* ofree = bars + 14;     // [2]
@@ -162,8 +167,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int g = 0; g < 2; ++g) {
       mbar_init(&qfull[g], 1);
       mbar_init(&qfree[g], 1);
-      mbar_init(&sfull[g * 2], 1);
-      mbar_init(&sfull[g * 2 + 1], 1);
+      mbar_init(&sfull[g], 1);
+      mbar_init(&sfree[g], 4);
       mbar_init(&ofull[g], 1);
       mbar_init(&ofree[g], 4);
       mbar_init(&flush[g], 1);
@@ -258,8 +263,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 8 || warp == 9) {
     // ---- MMA issuers, one per warpgroup -----------------------------------------------------------------------
-    // Issue order per tile: S(0), S(1), then for every block: P V(kb), S(kb + 2). S(kb + 2) lands in the buffer that
-    // P(kb) is read from by the MMA in front of it (the tensor pipe executes in issue order: no completion wait).
+    // Issue order per tile: S(0), then for every block kb: S(kb + 1) (as soon as S(kb) sits in the softmax warps'
+    // registers), P V(kb) (when P(kb) is published).
     const int g = warp - 8;
     if (elect_one()) {
       const uint32_t ids = umma_idesc_bf16(128, 64);
@@ -267,7 +272,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint64_t dq0 = umma_desc_k_sw128(smem_u32(Qs) + g * C::Q_BYTES);
       const uint64_t dk0 = umma_desc_k_sw128(smem_u32(Ks));
       const uint64_t dv0 = umma_desc_k_sw128(smem_u32(Vs));
-      const uint32_t spcol = tmem_base + C::SP_COL + (uint32_t)g * 128u;
+      const uint32_t scol = tmem_base + C::SP_COL + (uint32_t)g * 128u;
       const uint32_t ocol = tmem_base + C::O_COL + (uint32_t)g * HD;
       int m0 = 0;   // blocks of this warpgroup before the current tile
       int nt = 0;   // tiles of this warpgroup so far
@@ -281,10 +286,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         auto issue_s = [&](int kb) {
           const int m = m0 + kb;
           TR(warp, m, 0);
-          if (!seen) mbar_wait(&kfull[rs.slot], rs.ph & 1);
+          if (!seen) mbar_wait(&kfull[rs.slot], rs.ph & 1);   // (first: usually complete long before S(m - 1) is read)
+          if (m > 0) mbar_wait(&sfree[g], (m - 1) & 1);
           tc_fence_after();
           TR(warp, m, 1);
-          const uint32_t scol = spcol + (uint32_t)(m & 1) * 64u;
           uint64_t da = dq0;
           uint64_t db = dk0 + (uint64_t)launder(((uint32_t)rs.slot * C::KB_BYTES) >> 4);
 #pragma unroll
@@ -294,24 +299,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             da += wrap ? (uint64_t)(128 * 128 / 16 - 6) : 2u;
             db += wrap ? (uint64_t)(64 * 128 / 16 - 6) : 2u;
           }
-          umma_commit(&sfull[g * 2 + (m & 1)]);
+          umma_commit(&sfull[g]);
           if (kb == NB - 1) umma_commit(&qfree[g]);
           ring_next<C::NSLOT>(rs);
           TR(warp, m, 2);
         };
         mbar_wait(&qfull[g], nt & 1);
         issue_s(0);
-        if (NB > 1) issue_s(1);
         for (int kb = 0; kb < NB; ++kb) {
+          if (kb + 1 < NB) issue_s(kb + 1);
+          else if (NB > 1) umma_commit(&flush[g]);   // covers P V(NB - 2) for the rescale path of the last block
           const int m = m0 + kb, b = m & 1, u = m >> 1;
           TR(warp, m, 3);
-          mbar_wait(&pfull[g * 2 + b], u & 1);
-          TR(warp, m, 4);
           if (!seen) mbar_wait(&vfull[rv.slot], rv.ph & 1);
           if (kb == 0 && nt > 0) mbar_wait(&ofree[g], (nt - 1) & 1);   // the previous tile's O has been read out
+          mbar_wait(&pfull[g * 2 + b], u & 1);
           tc_fence_after();
           TR(warp, m, 5);
-          uint32_t pa = spcol + (uint32_t)b * 64u;
+          uint32_t pa = scol + 64u + (uint32_t)b * 32u;
           uint64_t db = dv0 + (uint64_t)launder(((uint32_t)rv.slot * C::VB_BYTES) >> 4);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {   // 16 keys per step
@@ -323,11 +328,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           // completion of P V(kb) through S(kb + 2), which these blocks do not have)
           if (kb + 2 >= NB)
             for (int r = 0; r <= p.GS - ti.gsize; ++r) umma_commit(&vfree[rv.slot]);
+          if (kb == NB - 1) umma_commit(&ofull[g]);
           ring_next<C::NSLOT>(rv);
           TR(warp, m, 6);
-          if (kb + 2 < NB) issue_s(kb + 2);
-          else if (kb + 2 == NB) umma_commit(&flush[g]);   // covers P V(NB - 2) for the rescale path of the last block
-          else umma_commit(&ofull[g]);
         }
         m0 += NB;
         nt++;
@@ -402,8 +405,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int m = m0 + kb, b = m & 1;
         TR(warp, m, 0);
         // S(kb) has completed: its key block is free; it was issued behind P V(kb - 2), so that V block is free too
-        mbar_wait(&sfull[g * 2 + b], (m >> 1) & 1);
+        mbar_wait(&sfull[g], m & 1);
         tc_fence_after();
+        if (m == 0 && g == 1 && p.stagger > 0) {
+          // The two warpgroups start in lock step (their first key block lands at the same moment) and, with equal work
+          // per block, stay there: both load from TMEM together, then both queue for the MUFU together. Half a block of
+          // delay, once, puts one warpgroup's exponentials under the other's TMEM reads and barrier traffic.
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger) {}
+        }
         if (lane == 0 && q == 0) {
           for (int r = 0; r < narr; ++r) mbar_arrive(&kfree[rk.slot]);
           if (kb >= 2)
@@ -413,75 +423,81 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (kb >= 2) ring_next<C::NSLOT>(rv);
         TR(warp, m, 1);
         if (rows_valid) {
-          const uint32_t scol = spcol + (uint32_t)b * 64u;
+          const uint32_t pcol = spcol + 64u + (uint32_t)b * 32u;
           const int key0 = kb * 64;
           const bool full = key0 + 64 <= p.T + 1;
-          uint32_t pk[32];
-          float s0 = 0.f, s1 = 0.f;
-          // exponentials of the 16 logits sv[0..16) of key group j -> pk[8j .. 8j+8), relative to the running maximum
-          auto exp16 = [&](const uint32_t* sv, int j, float moff) {
-            if (full) {
+          uint32_t sv[64];
+          tmem_ld_32x32b_x32(spcol, sv);
+          tmem_ld_32x32b_x32(spcol + 32u, sv + 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sfree[g]);   // S(kb) is in registers: S(kb + 1) may be issued
+          TR(warp, m, 2);
+          // running maximum of the row from this block's logits (keys beyond T are zero rows of K: logit 0, harmless
+          // below a maximum that is >= 0)
+          auto raise_max = [&]() -> float {
+            float m4[4] = {m_used, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float e0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -moff));
-                const float e1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -moff));
-                s0 += e0;
-                s1 += e1;
-                pk[8 * j + i] = pack_bf16x2(e0, e1);
-              }
-            } else if (key0 + 16 * j <= p.T) {   // key T is the zero-attention key, keys > T are padding
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float e0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -moff));
-                float e1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -moff));
-                e0 = (key0 + 16 * j + 2 * i <= p.T) ? e0 : 0.f;
-                e1 = (key0 + 16 * j + 2 * i + 1 <= p.T) ? e1 : 0.f;
-                s0 += e0;
-                s1 += e1;
-                pk[8 * j + i] = pack_bf16x2(e0, e1);
-              }
-            } else {   // a 16-key group entirely past T: no MUFU work
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pk[8 * j + i] = 0u;
-            }
-          };
-          // whole block at once: load the 64 logits, (optionally) raise the running maximum to theirs, exponentials
-          auto whole_block = [&](bool take_max) -> float {
-            uint32_t sv[64];
-            tmem_ld_32x32b_x32(scol, sv);
-            tmem_ld_32x32b_x32(scol + 32u, sv + 32);
-            tmem_ld_wait();
-            float f = 1.0f;
-            if (take_max) {
-              // (keys beyond T are zero rows of K: logit 0, harmless below a maximum that is >= 0)
-              float m4[4] = {m_used, 0.f, 0.f, 0.f};
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])));
-              const float bm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-              f = ex2_approx((m_used - bm) * c);
-              m_used = bm;
-            }
-            s0 = s1 = 0.f;
-            const float moff = m_used * c;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) exp16(sv + 16 * j, j, moff);
+            for (int i = 0; i < 32; ++i)
+              m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])));
+            const float bm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            const float f = ex2_approx((m_used - bm) * c);
+            m_used = bm;
             return f;
+          };
+          uint32_t pk[32];
+          float bsum;
+          auto exps = [&]() {   // pk <- packed bf16 probabilities relative to the running maximum, bsum <- their sum
+            const float moff = m_used * c;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (full) {
+#pragma unroll
+                for (int i = 8 * j; i < 8 * j + 8; ++i) {
+                  const float e0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -moff));
+                  const float e1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -moff));
+                  s0 += e0;
+                  s1 += e1;
+                  pk[i] = pack_bf16x2(e0, e1);
+                }
+              } else if (key0 + 16 * j <= p.T) {   // key T is the zero-attention key, keys > T are padding
+#pragma unroll
+                for (int i = 8 * j; i < 8 * j + 8; ++i) {
+                  float e0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -moff));
+                  float e1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -moff));
+                  e0 = (key0 + 2 * i <= p.T) ? e0 : 0.f;
+                  e1 = (key0 + 2 * i + 1 <= p.T) ? e1 : 0.f;
+                  s0 += e0;
+                  s1 += e1;
+                  pk[i] = pack_bf16x2(e0, e1);
+                }
+              } else {   // a 16-key group entirely past T: no MUFU work
+#pragma unroll
+                for (int i = 8 * j; i < 8 * j + 8; ++i) pk[i] = 0u;
+              }
+            }
+            bsum = s0 + s1;
           };
           // The first block sets the running maximum (nothing is accumulated yet, so adopting it is free). Later blocks
           // take no maximum pass: exp2 has 127 binades of headroom, a block that really outgrows the reference is
           // caught by its sum.
-          whole_block(kb == 0);
+          if (kb == 0) raise_max();
+          exps();
           // rare: the block outgrew the reference by more than 2^40 (or overflowed). Take its true maximum, rescale
           // this row's O and sum in place and redo the exponentials. P V(kb - 1) is complete once S(kb + 1), issued
           // behind it, is (the flush commit for the last block); nothing else touches O_g until P(kb) is published.
-          const bool grow = kb > 0 && !(s0 + s1 < 1.0995116e12f);
+          const bool grow = kb > 0 && !(bsum < 1.0995116e12f);
           if (__any_sync(0xffffffffu, grow)) {
             if (kb + 1 == NB) mbar_wait(&flush[g], nt & 1);
-            else mbar_wait(&sfull[g * 2 + (b ^ 1)], ((m + 1) >> 1) & 1);
+            else mbar_wait(&sfull[g], (m + 1) & 1);
             tc_fence_after();
-            // (every lane reloads: tcgen05.ld is warp-collective; lanes that do not grow recompute what they had)
-            const float f = whole_block(grow);
+            float f = 1.0f;
+            if (grow) {   // (register arithmetic only: the warp-collective TMEM accesses stay outside the branch)
+              f = raise_max();
+              exps();
+            }
 #pragma unroll 1
             for (int cc = 0; cc < HD / 16; ++cc) {
               uint32_t o[16];
@@ -494,12 +510,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tmem_st_wait();
             lsum *= f;
           }
-          lsum += s0 + s1;
+          lsum += bsum;
           TR(warp, m, 3);
-          // P(kb) goes over the first half of S(kb)'s own columns (all of S(kb) has been read)
-          tmem_st_32x32b_x16(scol, pk);
-          tmem_st_32x32b_x16(scol + 16u, pk + 16);
+          tmem_st_32x32b_x16(pcol, pk);
+          tmem_st_32x32b_x16(pcol + 16u, pk + 16);
           tmem_st_wait();
+        } else if (lane == 0) {
+          mbar_arrive(&sfree[g]);   // row groups past the sequence end only keep the barrier counts
         }
         tc_fence_before();
         __syncwarp();
@@ -560,6 +577,14 @@ static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat
   p.out = out;
   p.ldo = ldo;
   p.wide_store = ((reinterpret_cast<uintptr_t>(out) & 31) == 0 && (ldo % 16) == 0) ? 1 : 0;
+  {
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e = getenv("MMDM_ATTN_STAGGER");   // A/B measurements
+      stagger = e ? atoi(e) : 0;   // measured: no effect (94.3 - 95.5 us for 0 .. 1400 cycles), off by default
+    }
+    p.stagger = stagger;
+  }
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   p.tau_raw = 8.0f / p.scale_log2;
   const int items = S * H;

@@ -635,7 +635,10 @@ size_t mmdm_workspace_bytes(const mmdm_handle* h, int B, int T) {
 int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T) {
   return guarded(h, [&]() -> int {
     MMDM_REQUIRE(h && ws, "mmdm_bind_workspace: null argument");
-    MMDM_REQUIRE(T >= 1 && T <= 303, "mmdm_bind_workspace: T=%d outside [1,303]", T);
+    int tmax = 1 << 30;   // frames index the positional-encoding tables (reference: 5000 rows, models/utils/utils.py:25)
+    for (int i = 0; i < 3; ++i)
+      if (h->net[i].present) tmax = std::min(tmax, h->net[i].w.pe_rows);
+    MMDM_REQUIRE(T >= 1 && T <= tmax, "mmdm_bind_workspace: T=%d outside [1,%d] (positional-encoding table)", T, tmax);
     MMDM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
     size_t need = mmdm_workspace_bytes(h, B, T);
     MMDM_REQUIRE(bytes >= need, "workspace too small: %zu < %zu", bytes, need);

@@ -22,8 +22,44 @@ OUT = os.path.join(ROOT, "tests", "golden")
 B, T = 2, 24
 
 
+CHAIN_B, CHAIN_T = 1, 16
+
+
+def chain():
+    """tests/golden/reference_chain.npz: the reference's own 50-step trajectory for teacher-forced per-step parity.
+    After every ddim_sample the two state streams are rounded to fp16-representable values BEFORE they are fed to the
+    next step, so the stored fp16 tensors are exactly the inputs the reference saw (and every output is the next
+    input): x1[i], x2[i] = state entering DDIM index 49 - i (i = 0: the noise), x1[50], x2[50] = state after index 0,
+    final = pred_xstart2 of index 0 (the sampler's return value), fp32."""
+    dims = synth.SMALL_DIMS
+    cond, noise = synth.inputs(CHAIN_B, CHAIN_T, seed=3)
+    mix, diff, cfgm = ref_harness.build_reference(dims, mixing_mode=4, store_influence=False)
+    mix.load_state_dict(synth.synthetic_state_dict(mix.state_dict(), seed=0), strict=True)
+    q = lambda t: t.to(torch.float16).to(torch.float32)  # noqa: E731
+    x1 = x2 = q(noise)
+    xs1, xs2 = [x1.numpy().astype(np.float16)], [x2.numpy().astype(np.float16)]
+    final = None
+    with torch.no_grad(), ref_harness.reference_env():
+        for idx in range(diff.num_timesteps - 1, -1, -1):
+            tt = torch.full((CHAIN_B,), idx, dtype=torch.long)
+            o = diff.ddim_sample(cfgm, x1, x2, tt, clip_denoised=False, model_kwargs={"mask": None, "cond": cond})
+            x1, x2 = q(o["sample"]), q(o["sample2"])
+            xs1.append(x1.numpy().astype(np.float16))
+            xs2.append(x2.numpy().astype(np.float16))
+            if idx == 0:
+                final = o["pred_xstart2"].numpy()
+    np.savez_compressed(os.path.join(OUT, "reference_chain.npz"), x1=np.stack(xs1), x2=np.stack(xs2), final=final)
+    with open(os.path.join(OUT, "reference_chain.json"), "w") as f:
+        json.dump({"B": CHAIN_B, "T": CHAIN_T, "dims": dims, "weights_seed": 0, "inputs_seed": 3, "mixing_mode": 4,
+                   "generator": "oracle/make_goldens.py chain()", "torch": torch.__version__}, f, indent=1)
+    print("chain:", os.path.getsize(os.path.join(OUT, "reference_chain.npz")) // 1024, "KiB")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--chain-only" in sys.argv:
+        chain()
+        return
     dims = synth.SMALL_DIMS
     meta = {"B": B, "T": T, "dims": dims, "weights_seed": 0, "inputs_seed": 0,
             "generator": "oracle/make_goldens.py", "torch": torch.__version__}
@@ -86,6 +122,7 @@ def main():
     with open(os.path.join(OUT, "reference_small.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("wrote", len(arrays), "arrays;", os.path.getsize(os.path.join(OUT, "reference_small.npz")) // 1024, "KiB")
+    chain()
 
 
 if __name__ == "__main__":

@@ -126,3 +126,29 @@ def test_oracle_vs_live_reference_other_seed():
         o = orc.ddim_step(noise, 1.1 * noise, 12, cond)
     assert relerr(o["sample"], ref["sample"]) < 5e-5
     assert relerr(o["sample2"], ref["sample2"]) < 5e-5
+
+
+def test_oracle_follows_the_reference_chain_step_by_step():
+    """tests/golden/reference_chain.npz (the reference's own 50-step trajectory, oracle/make_goldens.py chain()):
+    the oracle, fed the reference's x_t, reproduces every step's x_{t-1} (golden stored as fp16: 5e-4)."""
+    import json
+    import os
+    from helpers import GOLDEN, build_mixer
+    ch = np.load(os.path.join(GOLDEN, "reference_chain.npz"))
+    with open(os.path.join(GOLDEN, "reference_chain.json")) as f:
+        meta = json.load(f)
+    B, T = meta["B"], meta["T"]
+    cond, _ = synth.inputs(B, T, seed=meta["inputs_seed"])
+    mix, sd = build_mixer(meta["dims"], mixing_mode=meta["mixing_mode"], seed=meta["weights_seed"])
+    orc = build_oracle(sd, meta["dims"], mixing_mode=meta["mixing_mode"])
+    x1s = torch.from_numpy(ch["x1"].astype(np.float32))
+    x2s = torch.from_numpy(ch["x2"].astype(np.float32))
+    assert x1s.shape == (51, B, T, 524)
+    with torch.no_grad():
+        for i in (0, 7, 23, 38, 48, 49):
+            idx = 49 - i
+            o = orc.ddim_step(x1s[i], x2s[i], idx, cond)
+            if idx > 0:
+                assert relerr(o["sample"], x1s[i + 1]) < 1e-3 and relerr(o["sample2"], x2s[i + 1]) < 1e-3, idx
+            else:
+                assert relerr(o["pred_xstart2"], ch["final"]) < 1e-4

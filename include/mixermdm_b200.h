@@ -44,7 +44,8 @@ enum mmdm_epilogue_mode {
   MMDM_EPI_EMBED_PE = 3,  /* out_f32  = acc + bias + pe[row % T]        motion_embed + PositionalEncoding   */
   MMDM_EPI_FINAL = 4,     /* out_f32  = (acc + bias) * std + mean       FinalLayer + normalizer.backward    */
   MMDM_EPI_F32 = 5,       /* out_f32  = acc + bias                      AdaLN.emb_layers[1]                 */
-  MMDM_EPI_SIGMOID_F32 = 6 /* out_f32 = sigmoid(acc + bias)              Influence.out + sigmoid            */
+  MMDM_EPI_SIGMOID_F32 = 6, /* out_f32 = sigmoid(acc + bias)             Influence.out + sigmoid            */
+  MMDM_EPI_QGELU_BF16 = 7  /* out_bf16 = x sigmoid(1.702 x), x = acc + bias   CLIP QuickGELU (text tower MLP) */
 };
 
 typedef struct mmdm_epilogue {
@@ -229,6 +230,51 @@ int mmdm_smooth_motion(const float* x, float* out, int B, int T, int F, const fl
  * i.e. the (B,max_length,2,nfeats) array the generators store. */
 int mmdm_format_motion(const float* x, float* out, int B, int T, int max_length, int nfeats, const float* mean,
                        const float* std_, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text conditioning, the step in front of the loop (reference: MixerMDM.text_process / generate_cond,
+ * models/mixermdm.py:283-356; in2IN.text_process, models/in2in.py:109-135): frozen CLIP ViT-L/14 text tower
+ * (OpenAI clip 1.0, clip/model.py) -> 2-layer post-norm nn.TransformerEncoder -> LayerNorm -> end-of-text row.
+ * All matrices bf16 in the nn.Linear (out, in) layout, everything else fp32, all device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mmdm_clip_block {            /* clip/model.py ResidualAttentionBlock */
+  const float* ln1_g; const float* ln1_b;   /* ln_1 */
+  const void* attn_in_w; const float* attn_in_b;    /* attn.in_proj_{weight,bias} (3W, W) */
+  const void* attn_out_w; const float* attn_out_b;  /* attn.out_proj (W, W) */
+  const float* ln2_g; const float* ln2_b;   /* ln_2 */
+  const void* fc_w; const float* fc_b;      /* mlp.c_fc (4W, W), QuickGELU behind it */
+  const void* proj_w; const float* proj_b;  /* mlp.c_proj (W, 4W) */
+} mmdm_clip_block;
+
+typedef struct mmdm_text_tower {
+  int32_t width, layers, heads, ctx, vocab; /* 768, 12, 12, 77, 49408 */
+  const float* tok_emb;                     /* token_embedding.weight (vocab, W) */
+  const float* pos_emb;                     /* positional_embedding (ctx, W) */
+  const mmdm_clip_block* blocks;            /* host array of `layers` entries */
+  const float* lnf_g; const float* lnf_b;   /* ln_final */
+} mmdm_text_tower;
+
+typedef struct mmdm_enc_layer {             /* nn.TransformerEncoderLayer(norm_first=False, activation="gelu") */
+  const void* in_w; const float* in_b;      /* self_attn.in_proj (3W, W) */
+  const void* out_w; const float* out_b;    /* self_attn.out_proj */
+  const float* norm1_g; const float* norm1_b;
+  const void* lin1_w; const float* lin1_b;  /* linear1 (ff, W) */
+  const void* lin2_w; const float* lin2_b;  /* linear2 (W, ff) */
+  const float* norm2_g; const float* norm2_b;
+} mmdm_enc_layer;
+
+typedef struct mmdm_text_encoder {
+  int32_t layers, heads, ff;                /* 2, 8, 2048 */
+  const mmdm_enc_layer* layers_;            /* host array */
+  const float* ln_g; const float* ln_b;     /* clip_ln / clip_ln_individual / clip_ln_interaction */
+} mmdm_text_encoder;
+
+size_t mmdm_text_workspace_bytes(int nseq, int ctx, int width, int ff_max);
+/* tokens: device (nseq, ctx) int32 (clip.tokenize output); eot: device (nseq) int32 = argmax of the token ids per row;
+ * cond_out: host array of n_enc device pointers, each (nseq, cond_ld >= width) fp32: one tower pass, n_enc encoders. */
+int mmdm_text_encode(const mmdm_text_tower* tower, const mmdm_text_encoder* encs, int n_enc, const int32_t* tokens,
+                     const int32_t* eot, int nseq, float* const* cond_out, int cond_ld, void* ws, size_t ws_bytes,
+                     void* stream);
 
 /* Test hook (host only, no GPU): the index arithmetic of the fused mix kernel's frame stream (csrc/mix_stream.cuh).
  * For item `item` of the stream of S samples x nfr frames (with or without a phase 2) in a ring of ring_slots <= nfr

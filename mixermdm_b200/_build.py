@@ -10,7 +10,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # MMDM_LIB_PATH: load an alternative build of the same library (instrumented builds from tools/attn_trace.py)
 LIB_PATH = os.environ.get("MMDM_LIB_PATH") or os.path.join(PKG_DIR, "libmixermdm_b200.so")
 
-SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "rowops.cu", "motion.cu", "engine.cu", "api.cu"]
+SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "rowops.cu", "motion.cu", "engine.cu", "text.cu", "api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -492,6 +492,8 @@ __device__ __forceinline__ uint32_t gelu_fast2_bf16(f32x2 x) {
   return pack_bf16x2(r0, r1);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// CLIP's QuickGELU: x * sigmoid(1.702 x) (OpenAI clip/model.py, class QuickGELU)
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

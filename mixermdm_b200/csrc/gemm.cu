@@ -73,8 +73,8 @@ __device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const Row
     if (j >= nvalid) break;
     const int n = col0 + j;
     const float x = v[j] + (ep.bias ? __ldg(ep.bias + n) : 0.f);
-    if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
-      const float o = (MODE == EPI_GELU_BF16) ? gelu_erf(x) : x;
+    if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16 || MODE == EPI_QGELU_BF16) {
+      const float o = (MODE == EPI_GELU_BF16) ? gelu_erf(x) : (MODE == EPI_QGELU_BF16) ? quick_gelu(x) : x;
       if (MODE == EPI_BF16 && ep.vt_col0 >= 0 && n >= ep.vt_col0) {
         const int nn = n - ep.vt_col0, h = nn / ep.hd, d = nn - h * ep.hd;
         ep.vt[((size_t)(rc.s * ep.H + h) * ep.hd + d) * ep.Tp + rc.t] = __float2bfloat16_rn(o);
@@ -124,6 +124,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& 
       pk.y = gelu_fast2_bf16(add2(pack2(v[8 * j + 2], v[8 * j + 3]), pack2(b[8 * j + 2], b[8 * j + 3])));
       pk.z = gelu_fast2_bf16(add2(pack2(v[8 * j + 4], v[8 * j + 5]), pack2(b[8 * j + 4], b[8 * j + 5])));
       pk.w = gelu_fast2_bf16(add2(pack2(v[8 * j + 6], v[8 * j + 7]), pack2(b[8 * j + 6], b[8 * j + 7])));
+      dst[j] = pk;
+    }
+  } else if (MODE == EPI_QGELU_BF16) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)rc.row * ep.ldo + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 pk;
+      pk.x = pack_bf16x2(quick_gelu(v[8 * j] + b[8 * j]), quick_gelu(v[8 * j + 1] + b[8 * j + 1]));
+      pk.y = pack_bf16x2(quick_gelu(v[8 * j + 2] + b[8 * j + 2]), quick_gelu(v[8 * j + 3] + b[8 * j + 3]));
+      pk.z = pack_bf16x2(quick_gelu(v[8 * j + 4] + b[8 * j + 4]), quick_gelu(v[8 * j + 5] + b[8 * j + 5]));
+      pk.w = pack_bf16x2(quick_gelu(v[8 * j + 6] + b[8 * j + 6]), quick_gelu(v[8 * j + 7] + b[8 * j + 7]));
       dst[j] = pk;
     }
   } else if (MODE == EPI_BF16) {
@@ -897,6 +908,7 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
     case EPI_FINAL: return launch_mode<EPI_FINAL>(A, lda, W, ldw, M, N, K, e2, stream);
     case EPI_F32: return launch_mode<EPI_F32>(A, lda, W, ldw, M, N, K, e2, stream);
     case EPI_SIGMOID_F32: return launch_mode<EPI_SIGMOID_F32>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_QGELU_BF16: return launch_mode<EPI_QGELU_BF16>(A, lda, W, ldw, M, N, K, e2, stream);
     default: break;
   }
   set_last_error("gemm: unknown epilogue mode %d", ep.mode);

@@ -13,6 +13,7 @@ enum EpiMode : int {
   EPI_FINAL = 4,      // out_f32  = (acc + bias) * std + mean, scattered to (B,T,2*nfeats) layout
   EPI_F32 = 5,        // out_f32  = acc + bias                         (AdaLN conditioning GEMM)
   EPI_SIGMOID_F32 = 6,  // out_f32 = sigmoid(acc + bias)               (Influence head, influence.py:120-125)
+  EPI_QGELU_BF16 = 7,   // out_bf16 = x * sigmoid(1.702 x), x = acc + bias (CLIP's QuickGELU: text tower MLP)
 };
 
 struct GemmEpi {

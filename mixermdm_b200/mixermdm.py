@@ -5,8 +5,10 @@ that reference checkpoints load with `load_state_dict(strict=True)` after the lo
 (scripts/infer/mixermdm.py:169-177), and so that callers find the attributes they read.
 
 Text conditioning: the reference tokenises with OpenAI `clip` and runs the frozen ViT-L/14@336 text tower plus three
-2-layer encoders once per batch. That path is outside this build's hot path; it runs here in plain PyTorch when the
-`clip` package (tokeniser) is importable, otherwise the caller passes the (B, 6144) condition as batch["cond"].
+2-layer encoders once per batch (models/mixermdm.py:283-356). Here the tower and the encoders run in the CUDA library
+(csrc/text.cu through text.TextEngine); the modules below only hold their parameters. Tokenisation is the one host
+step: `clip.tokenize` when the package is installed, or any callable set as `model.tokenizer`; a precomputed
+(B, 6144) condition can still be passed as batch["cond"].
 """
 import os
 from collections import OrderedDict
@@ -14,6 +16,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
+from . import text as text_engine
 from .diffusion import LossType, MixerDiffusion, ModelMeanType, ModelVarType, get_named_beta_schedule, space_timesteps
 from .modules import (ClassifierFreeSampleModelX2, FFN, Mixer, PositionalEncoding, TimestepEmbedder,
                       VanillaSelfAttention, in2INDenoiser)
@@ -50,12 +53,12 @@ def get_config(config_file):
 # parameter containers off the hot path
 # ------------------------------------------------------------------------------------------------
 class QuickGELU(nn.Module):
-    def forward(self, x):
-        return x * torch.sigmoid(1.702 * x)
+    """parameter-free placeholder that keeps the `mlp.gelu` slot of CLIP's block layout"""
 
 
 class _ClipResBlock(nn.Module):
-    """OpenAI CLIP ResidualAttentionBlock layout: attn / ln_1 / mlp.{c_fc,gelu,c_proj} / ln_2"""
+    """OpenAI CLIP ResidualAttentionBlock layout: attn / ln_1 / mlp.{c_fc,gelu,c_proj} / ln_2 (parameters only; the
+    arithmetic runs in csrc/text.cu)"""
 
     def __init__(self, d, heads):
         super().__init__()
@@ -64,24 +67,12 @@ class _ClipResBlock(nn.Module):
         self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d, 4 * d)), ("gelu", QuickGELU()), ("c_proj", nn.Linear(4 * d, d))]))
         self.ln_2 = nn.LayerNorm(d)
 
-    def forward(self, x, mask):
-        y = self.ln_1(x)
-        x = x + self.attn(y, y, y, need_weights=False, attn_mask=mask)[0]
-        return x + self.mlp(self.ln_2(x))
-
 
 class _ClipTextTransformer(nn.Module):
     def __init__(self, width=768, layers=12, heads=12):
         super().__init__()
         self.width, self.layers = width, layers
         self.resblocks = nn.Sequential(*[_ClipResBlock(width, heads) for _ in range(layers)])
-
-    def forward(self, x):   # LND, causal mask as in CLIP's text tower
-        n = x.shape[0]
-        mask = torch.full((n, n), float("-inf"), device=x.device, dtype=x.dtype).triu_(1)
-        for blk in self.resblocks:
-            x = blk(x, mask)
-        return x
 
 
 class _ClipTextTower:
@@ -93,22 +84,24 @@ class _ClipTextTower:
         self.positional_embedding = nn.Parameter(torch.empty(77, 768).normal_(std=0.01))
         self.ln_final = nn.LayerNorm(768)
         self.dtype = torch.float32
+        self.tokenizer = None          # callable(list[str]) -> (B, 77) ints; default: clip.tokenize(..., truncate=True)
         for m in (self.token_embedding, self.clip_transformer, self.ln_final):
             for p in m.parameters():
                 p.requires_grad = False
 
-    def _clip_features(self, raw_text):
-        try:
-            import clip  # tokeniser only
-        except ImportError as e:
-            raise RuntimeError("text prompts need the `clip` tokenizer; pass a precomputed batch['cond'] (B, 6144) "
-                               "instead") from e
+    def _tokens(self, raw_text):
+        tok = self.tokenizer or text_engine.default_tokenizer
+        return torch.as_tensor(tok(raw_text))
+
+    def _encode_text(self, key, encoders, tokens):
+        """run the CUDA text path: this object's CLIP tower, then `encoders` [(TransformerEncoder, LayerNorm), ...]"""
+        cache = self.__dict__.setdefault("_text_engines", {})
         device = self.positional_embedding.device
-        with torch.no_grad():
-            text = clip.tokenize(raw_text, truncate=True).to(device)
-            x = self.token_embedding(text).type(self.dtype) + self.positional_embedding.type(self.dtype)
-            x = self.clip_transformer(x.permute(1, 0, 2)).permute(1, 0, 2)
-            return self.ln_final(x).type(self.dtype), text
+        eng = cache.get(key)
+        if eng is None or eng.device != device or eng.stale():
+            cache[key] = None
+            eng = cache[key] = text_engine.TextEngine(self, encoders, device)
+        return eng.encode(tokens)
 
 
 def _text_encoder():
@@ -146,12 +139,16 @@ class in2IN(nn.Module, _ClipTextTower):
             self.clipTransEncoder_individual, self.clip_ln_individual = _text_encoder()
         self._build_clip()
 
+    def _text_encoders(self, mode):
+        if mode == "individual":
+            return [(self.clipTransEncoder_individual, self.clip_ln_individual)]
+        if mode == "interaction":
+            return [(self.clipTransEncoder_interaction, self.clip_ln_interaction)]
+        raise ValueError("Mode not recognized")
+
     def text_process(self, batch, mode, text_name="text", out_name="cond"):
-        clip_out, text = self._clip_features(batch[text_name])
-        enc, ln = ((self.clipTransEncoder_individual, self.clip_ln_individual) if mode == "individual"
-                   else (self.clipTransEncoder_interaction, self.clip_ln_interaction))
-        out = ln(enc(clip_out))
-        batch[out_name] = out[torch.arange(out.shape[0]), text.argmax(dim=-1)]
+        """reference models/in2in.py:109-135: CLIP tower -> this sub-model's text encoder -> end-of-text row"""
+        batch[out_name] = self._encode_text(mode, self._text_encoders(mode), self._tokens(batch[text_name]))[0]
         return batch
 
 
@@ -262,9 +259,9 @@ class MixerMDM(nn.Module, _ClipTextTower):
 
     # -- conditioning -----------------------------------------------------------------------------
     def text_process(self, batch, text_name="text", out_name="cond"):
-        clip_out, text = self._clip_features(batch[text_name])
-        out = self.clip_ln(self.clipTransEncoder(clip_out))
-        batch[out_name] = out[torch.arange(out.shape[0]), text.argmax(dim=-1)]
+        """reference models/mixermdm.py:283-317: CLIP tower -> clipTransEncoder -> clip_ln -> end-of-text row"""
+        batch[out_name] = self._encode_text("mixer", [(self.clipTransEncoder, self.clip_ln)],
+                                            self._tokens(batch[text_name]))[0]
         return batch
 
     def generate_cond(self, batch):
@@ -273,14 +270,28 @@ class MixerMDM(nn.Module, _ClipTextTower):
         if "cond" in batch and torch.is_tensor(batch["cond"]):
             return batch["cond"]
         inter = "text_interaction" if "text_interaction" in batch else "text"
-        self.cond_pre_func1(batch, "individual", "text_individual1", "cond_individual_individual1")
-        self.cond_pre_func1(batch, "individual", "text_individual2", "cond_individual_individual2")
-        self.cond_pre_func2(batch, "interaction", "text_individual1", "cond_interaction_individual1")
-        self.cond_pre_func2(batch, "interaction", "text_individual2", "cond_interaction_individual2")
-        self.cond_pre_func2(batch, "interaction", inter, "cond_interaction")
-        self.text_process(batch, "text_individual1", "cond_influence_individual1")
-        self.text_process(batch, "text_individual2", "cond_influence_individual2")
-        self.text_process(batch, inter, "cond_influence_interaction")
+        # The reference makes eight text_process calls (five through the sub-models, three of its own), i.e. eight CLIP
+        # tower passes. Sequences are independent and model2 shares the tower with this module (mixermdm.py:229-233), so
+        # the same eight vectors come from two calls: model1's tower on [individual1; individual2] with its encoder, and
+        # the shared tower on [individual1; individual2; interaction] feeding model2's encoder and clipTransEncoder
+        # (three calls if model2's own positional_embedding parameter differs from this module's).
+        tok = self.tokenizer or text_engine.default_tokenizer
+        t1, t2, tI = (torch.as_tensor(tok(batch[k])) for k in ("text_individual1", "text_individual2", inter))
+        B = t1.shape[0]
+        self.model1.tokenizer = self.model2.tokenizer = self.tokenizer
+        (ind,) = self.model1._encode_text("individual", self.model1._text_encoders("individual"), torch.cat([t1, t2]))
+        t3 = torch.cat([t1, t2, tI])
+        if torch.equal(self.model2.positional_embedding, self.positional_embedding):
+            inter_out, mix_out = self._encode_text(
+                "generate_cond", self.model2._text_encoders("interaction") + [(self.clipTransEncoder, self.clip_ln)], t3)
+        else:   # model2 keeps its own positional_embedding parameter: if it differs, its tower input differs too
+            (inter_out,) = self.model2._encode_text("interaction", self.model2._text_encoders("interaction"), t3)
+            (mix_out,) = self._encode_text("mixer", [(self.clipTransEncoder, self.clip_ln)], t3)
+        batch["cond_individual_individual1"], batch["cond_individual_individual2"] = ind[:B], ind[B:]
+        batch["cond_interaction_individual1"], batch["cond_interaction_individual2"] = inter_out[:B], inter_out[B:2 * B]
+        batch["cond_interaction"] = inter_out[2 * B:]
+        batch["cond_influence_individual1"], batch["cond_influence_individual2"] = mix_out[:B], mix_out[B:2 * B]
+        batch["cond_influence_interaction"] = mix_out[2 * B:]
         return torch.cat([batch[k] for k in ("cond_interaction", "cond_interaction_individual1",
                                              "cond_interaction_individual2", "cond_individual_individual1",
                                              "cond_individual_individual2", "cond_influence_interaction",

@@ -55,10 +55,67 @@ def chain():
     print("chain:", os.path.getsize(os.path.join(OUT, "reference_chain.npz")) // 1024, "KiB")
 
 
+TEXT_PROMPTS = {
+    "text": ["two people greet each other and shake hands", "one person pushes the other who stumbles backwards"],
+    "text_individual1": ["a person walks forward and extends the right hand", "a person steps in and pushes with both arms"],
+    "text_individual2": ["a person stands still then raises an arm to shake hands", "a person is pushed and takes three steps back"],
+}
+
+
+def build_text_reference(seed=0):
+    """Holder objects carrying the reference's own text methods (MixerMDM.generate_cond / text_process,
+    in2IN.text_process - imported, unmodified) over the restated CLIP modules of oracle/text_oracle.py, with the
+    attribute names (= state-dict keys) of the real model. Returns (mixermdm_holder, state_dict)."""
+    from torch import nn
+    from oracle import text_oracle as to
+    with ref_harness.reference_env():
+        import clip as clip_stub
+        clip_stub.tokenize = to.stub_tokenize
+        from models.in2in import in2IN
+        from models.mixermdm import MixerMDM
+
+    def holder(cls):
+        obj = cls.__new__(cls)
+        nn.Module.__init__(obj)
+        return obj
+    m = holder(MixerMDM)
+    m.model1, m.model2 = holder(in2IN), holder(in2IN)
+    to.attach_clip(m.model1)
+    m.model1.clipTransEncoder_individual, m.model1.clip_ln_individual = to.text_encoder_pair()
+    to.attach_clip(m)
+    m.model2.token_embedding, m.model2.clip_transformer = m.token_embedding, m.clip_transformer
+    # (like the reference, models/mixermdm.py:229-233: model2 borrows the token table, the blocks and ln_final but keeps
+    #  its own positional_embedding parameter)
+    m.model2.positional_embedding = nn.Parameter(torch.zeros(to.CTX, to.WIDTH))
+    m.model2.ln_final, m.model2.dtype = m.ln_final, m.dtype
+    m.model2.clipTransEncoder_interaction, m.model2.clip_ln_interaction = to.text_encoder_pair()
+    m.clipTransEncoder, m.clip_ln = to.text_encoder_pair()
+    m.cond_pre_func1, m.cond_pre_func2 = m.model1.text_process, m.model2.text_process
+    sd = to.text_state_dict(m.state_dict(), seed=seed)
+    m.load_state_dict(sd, strict=True)
+    return m.eval(), sd
+
+
+def text():
+    """tests/golden/reference_text.npz: the (B, 6144) condition the reference's generate_cond builds from prompts"""
+    m, _ = build_text_reference(seed=0)
+    batch = {k: list(v) for k, v in TEXT_PROMPTS.items()}
+    with torch.no_grad(), ref_harness.reference_env():
+        cond = m.generate_cond(batch)
+    np.savez_compressed(os.path.join(OUT, "reference_text.npz"), cond=cond.numpy())
+    with open(os.path.join(OUT, "reference_text.json"), "w") as f:
+        json.dump({"prompts": TEXT_PROMPTS, "weights_seed": 0, "tokenizer": "oracle.text_oracle.stub_tokenize",
+                   "generator": "oracle/make_goldens.py text()", "torch": torch.__version__}, f, indent=1)
+    print("text:", cond.shape, float(cond.abs().mean()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--chain-only" in sys.argv:
         chain()
+        return
+    if "--text-only" in sys.argv:
+        text()
         return
     dims = synth.SMALL_DIMS
     meta = {"B": B, "T": T, "dims": dims, "weights_seed": 0, "inputs_seed": 0,
@@ -123,6 +180,7 @@ def main():
         json.dump(meta, f, indent=1)
     print("wrote", len(arrays), "arrays;", os.path.getsize(os.path.join(OUT, "reference_small.npz")) // 1024, "KiB")
     chain()
+    text()
 
 
 if __name__ == "__main__":

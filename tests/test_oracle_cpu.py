@@ -152,3 +152,23 @@ def test_oracle_follows_the_reference_chain_step_by_step():
                 assert relerr(o["sample"], x1s[i + 1]) < 1e-3 and relerr(o["sample2"], x2s[i + 1]) < 1e-3, idx
             else:
                 assert relerr(o["pred_xstart2"], ch["final"]) < 1e-4
+
+
+def test_text_oracle_matches_reference_generate_cond_golden():
+    """tests/golden/reference_text.npz was produced by the reference's unmodified generate_cond / text_process on
+    synthetic weights with a stub tokenizer (oracle/make_goldens.py text()); the oracle's restatement of that path
+    (oracle/text_oracle.py) reproduces it."""
+    import json
+    import os
+    from helpers import GOLDEN
+    from oracle import text_oracle
+    gold = np.load(os.path.join(GOLDEN, "reference_text.npz"))["cond"]
+    with open(os.path.join(GOLDEN, "reference_text.json")) as f:
+        meta = json.load(f)
+    m, _ = text_oracle.build_text_oracle(seed=meta["weights_seed"])
+    cond = text_oracle.generate_cond(m, meta["prompts"])
+    assert cond.shape == gold.shape == (2, 6144)
+    assert relerr(cond, gold) < 1e-5
+    tok = text_oracle.stub_tokenize(["a b c", " ".join(["w"] * 200)])
+    assert tok.shape == (2, 77) and tok[0, 0] == text_oracle.SOT and tok[0, 4] == text_oracle.EOT and tok[0, 5] == 0
+    assert tok[1, 76] == text_oracle.EOT                       # truncated prompts still end in <eot>

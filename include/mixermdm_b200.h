@@ -197,7 +197,8 @@ int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream);
  * replaces MixerDiffusion.ddim_sample (gaussian_diffusion.py:1902-1965) */
 int mmdm_step(mmdm_handle* h, float* final_out /* (B,T,524) guided prediction of the step (the sample when the index is 0), or NULL */, void* stream);
 /* whole loop from noise; result = pred_xstart2 of the last step (gaussian_diffusion.py:1769-1820).
- * use_graph != 0 replays one captured step graph nsteps times. hist_i1/hist_i2: optional
+ * use_graph != 0 replays one captured step graph nsteps times (graphs are cached per batch / frame count, so
+ * re-binding the same workspace to another motion length and back does not capture again). hist_i1/hist_i2: optional
  * (nsteps, 2B, T, 262) fp32 device buffers receiving the expanded Mixer weights, or NULL.
  * hist_out1/out2/mix: optional (nsteps, 2B, T, 524) buffers with the aligned predictions and out_influenced of
  * every step (Mixer mode "eval", mixermdm.py:805-809); all three or none; forces the eager (non-graph) loop. */
@@ -294,6 +295,8 @@ typedef struct mmdm_profile_entry {
 } mmdm_profile_entry;
 int mmdm_profile_read(mmdm_handle* h, mmdm_profile_entry* entries, int max_entries);
 int64_t mmdm_launch_count(const mmdm_handle* h);
+/* step graphs captured so far by mmdm_sample (one per distinct workspace / batch / frame count, cached) */
+int64_t mmdm_graph_captures(const mmdm_handle* h);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,8 @@ struct mmdm_handle {
   int device = 0;            // ordinal the handle was created on; every entry point makes it current
   std::string last_error;    // message of the last failed call on this handle (mmdm_last_error(h))
   int step_host = -1;        // host mirror of the device-side DDIM index (-1: no state set)
+  bool cond_ready = false;   // the text-embedding tables hold the sampler's condition (mmdm_set_condition); the
+                             // explicit-batch entry points (mixer / denoiser forward) and a re-bind overwrite them
   mmdm_config cfg;
   Net net[3];
   std::vector<int32_t> timestep_map;
@@ -122,10 +124,15 @@ struct mmdm_handle {
   int B = 0, T = 0, Bx = 0;   // bound un-doubled batch, frames, rows fed to the networks (2B)
   int Tp = 0;
   bool temb_ready = false;
-  cudaGraphExec_t graph = nullptr;
+  // One captured step graph per (workspace, batch, frames, history buffers): a caller that alternates between motion
+  // lengths (the evaluation generators: T = motion_lens[0] per prompt) re-binds the workspace without re-capturing.
+  struct GraphEntry {
+    void* ws_base; int B, T; float *h1, *h2;
+    cudaGraphExec_t exec; long long step_launches; long long stamp;
+  };
+  std::vector<GraphEntry> graphs;
+  long long graph_stamp = 0, graph_captures = 0;
   cudaStream_t cap_stream = nullptr;   // capture happens here: the legacy default stream cannot be captured
-  long long graph_step_launches = 0;
-  float *graph_h1 = nullptr, *graph_h2 = nullptr;
   Profiler prof;
   long long launches = 0;
   // Serpentine traversal: every big launch (LN, GEMM, attention) walks its rows in the direction opposite to the
@@ -544,9 +551,10 @@ static int ensure_temb(mmdm_handle* h, cudaStream_t st) {
   return 0;
 }
 
-static void drop_graph(mmdm_handle* h) {
-  if (h->graph) cudaGraphExecDestroy(h->graph);
-  h->graph = nullptr;
+constexpr size_t kMaxCachedGraphs = 8;
+static void drop_graphs(mmdm_handle* h) {
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
 }
 
 const char* get_last_error();
@@ -618,7 +626,7 @@ int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_han
 void mmdm_destroy(mmdm_handle* h) {
   if (!h) return;
   DeviceGuard dg(h->device);
-  drop_graph(h);
+  drop_graphs(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   h->prof.flush();
   for (auto e : h->prof.pool) cudaEventDestroy(e);
@@ -642,10 +650,11 @@ int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T) {
     MMDM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
     size_t need = mmdm_workspace_bytes(h, B, T);
     MMDM_REQUIRE(bytes >= need, "workspace too small: %zu < %zu", bytes, need);
-    drop_graph(h);
+    if (ws != h->ws_base) drop_graphs(h);   // cached graphs hold pointers into the old workspace
     carve(h, B, T, ws, &h->ws, nullptr);
     h->ws_base = ws; h->ws_bytes = bytes; h->B = B; h->T = T; h->Bx = 2 * B; h->Tp = (T + 7) / 8 * 8;
     h->temb_ready = false;
+    h->cond_ready = false;
     return 0;
   });
 }
@@ -660,6 +669,7 @@ int mmdm_set_condition(mmdm_handle* h, const float* cond, void* stream) {
     MMDM_TRY(run_text(h, 0, cond, ld, h->B, COL_IND, 2, st));
     MMDM_TRY(run_text(h, 1, cond, ld, h->B, COL_INTER, 3, st));
     MMDM_TRY(run_text(h, 2, cond, ld, h->B, COL_MIX, 3, st));
+    h->cond_ready = true;
     return 0;
   });
 }
@@ -701,6 +711,8 @@ int mmdm_step(mmdm_handle* h, float* final_out, void* stream) {
     // the DDIM index lives on the device (graph replays); the host mirror only guards against stepping past index 0,
     // which would read the coefficient / embedding tables out of bounds
     MMDM_REQUIRE(h->step_host >= 0, "mmdm_step: no step left (set a state first; the DDIM index ran past 0)");
+    MMDM_REQUIRE(h->cond_ready, "mmdm_step: no condition set (mmdm_set_condition; a mixer / denoiser forward or a re-bind "
+                                "in between overwrites the conditioning tables)");
     MMDM_TRY(ensure_temb(h, st));
     MMDM_TRY(step_body(h, final_out, nullptr, nullptr, st));
     h->step_host -= 1;
@@ -719,14 +731,23 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
     const bool eval_hist = hist_out1 || hist_out2 || hist_mix;
     if (eval_hist) MMDM_REQUIRE(hist_out1 && hist_out2 && hist_mix, "mmdm_sample: the three eval-mode history buffers come together");
     if (use_graph && !h->prof.on && !eval_hist) {
-      if (h->graph && (h->graph_h1 != hist_i1 || h->graph_h2 != hist_i2)) drop_graph(h);
-      if (!h->graph) {
+      mmdm_handle::GraphEntry* ge = nullptr;
+      for (auto& g : h->graphs)
+        if (g.ws_base == h->ws_base && g.B == h->B && g.T == h->T && g.h1 == hist_i1 && g.h2 == hist_i2) ge = &g;
+      if (!ge) {
+        if (h->graphs.size() >= kMaxCachedGraphs) {   // evict the least recently used entry
+          size_t lru = 0;
+          for (size_t i = 1; i < h->graphs.size(); ++i)
+            if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+          cudaGraphExecDestroy(h->graphs[lru].exec);
+          h->graphs.erase(h->graphs.begin() + lru);
+        }
         cudaGraph_t g = nullptr;
         if (!h->cap_stream) MMDM_CHECK_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
         MMDM_CHECK_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
         const long long before = h->launches;
         int rc = step_body(h, nullptr, hist_i1, hist_i2, h->cap_stream);
-        h->graph_step_launches = h->launches - before;
+        const long long step_launches = h->launches - before;
         h->launches = before;   // capturing enqueues nothing; replays are counted below
         cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
         if (rc != 0) {
@@ -734,12 +755,16 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
           return rc;
         }
         MMDM_CHECK_CUDA(e);
-        MMDM_CHECK_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
+        cudaGraphExec_t exec = nullptr;
+        MMDM_CHECK_CUDA(cudaGraphInstantiate(&exec, g, 0));
         cudaGraphDestroy(g);
-        h->graph_h1 = hist_i1; h->graph_h2 = hist_i2;
+        h->graphs.push_back({h->ws_base, h->B, h->T, hist_i1, hist_i2, exec, step_launches, 0});
+        h->graph_captures++;
+        ge = &h->graphs.back();
       }
-      for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_CHECK_CUDA(cudaGraphLaunch(h->graph, st));
-      h->launches += h->graph_step_launches * h->cfg.nsteps;
+      ge->stamp = ++h->graph_stamp;
+      for (int i = 0; i < h->cfg.nsteps; ++i) MMDM_CHECK_CUDA(cudaGraphLaunch(ge->exec, st));
+      h->launches += ge->step_launches * h->cfg.nsteps;
     } else {
       EvalHist eh;
       eh.out1 = hist_out1; eh.out2 = hist_out2; eh.mix = hist_mix;
@@ -765,6 +790,7 @@ int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const i
     MMDM_TRY(ensure_temb(h, st));
     Workspace& ws = h->ws;
     const int ld = 8 * h->cfg.text_dim;
+    h->cond_ready = false;
     MMDM_TRY(run_text(h, 0, cond, ld, Bx, COL_IND, 2, st));
     MMDM_TRY(run_text(h, 1, cond, ld, Bx, COL_INTER, 3, st));
     MMDM_TRY(run_text(h, 2, cond, ld, Bx, COL_MIX, 3, st));
@@ -822,6 +848,7 @@ int mmdm_denoiser_forward(mmdm_handle* h, int which, const float* x, const int64
     MMDM_TRY(ensure_temb(h, st));
     Workspace& ws = h->ws;
     const int nsl = which == MMDM_NET_INTERACTION ? 3 : 1;
+    h->cond_ready = false;
     MMDM_TRY(run_text(h, which, cond, nsl * h->cfg.text_dim, Bx, 0, nsl, st));
     MMDM_TRY(run_time_embed(h, which, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
     MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, Bx * persons, persons, Bx, 0, nsl, which == MMDM_NET_INTERACTION ? 1 : 0, st));
@@ -914,6 +941,7 @@ int mmdm_profile_read(mmdm_handle* h, mmdm_profile_entry* entries, int max_entri
 }
 
 int64_t mmdm_launch_count(const mmdm_handle* h) { return h ? h->launches : 0; }
+int64_t mmdm_graph_captures(const mmdm_handle* h) { return h ? h->graph_captures : 0; }
 
 const char* mmdm_last_error(const mmdm_handle* h) {
   return (h && !h->last_error.empty()) ? h->last_error.c_str() : mmdm::get_last_error();

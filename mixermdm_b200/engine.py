@@ -252,6 +252,10 @@ class _Handle:
     def launches(self):
         return int(self.lib.mmdm_launch_count(self.h))
 
+    def graph_captures(self):
+        self.lib.mmdm_graph_captures.restype = C.c_int64
+        return int(self.lib.mmdm_graph_captures(self.h))
+
     def profile(self, on):
         self.call("mmdm_profile_enable", int(on))
 
@@ -268,6 +272,14 @@ class _Handle:
                 self.h = C.c_void_p()
         except Exception:
             pass
+
+
+def canonical_device(device):
+    """torch.device with an explicit index ("cuda" and "cuda:0" must not look like two devices to the engine caches)"""
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
 
 
 def _f32c(t, device):
@@ -301,7 +313,7 @@ class MixerEngine:
     """engine for one `Mixer` module (both denoisers + Influence + fused mix / sampler step)"""
 
     def __init__(self, mixer, device, sched=None, cfg_scale=3.5, center=True):
-        device = torch.device(device)
+        device = canonical_device(device)
         pk = _Packer(device)
         nets = [pk.pack_net(NET_INDIVIDUAL, mixer.denoiser1, mixer.denoiser1.blocks, True),
                 pk.pack_net(NET_INTERACTION, mixer.denoiser2, mixer.denoiser2.blocks, True),
@@ -459,7 +471,7 @@ class StandaloneDenoiser:
     """engine holding a single in2INDenoiser (direct module.forward calls, BASELINE config 3)"""
 
     def __init__(self, den, x):
-        device = x.device
+        device = canonical_device(x.device)
         pk = _Packer(device)
         self.kind = NET_INTERACTION if den.mode == "interaction" else NET_INDIVIDUAL
         nets = [_absent_net(0), _absent_net(1), _absent_net(2)]
@@ -480,7 +492,7 @@ class StandaloneDenoiser:
         self.T = 0
 
     def matches(self, den, x):
-        return x.device == self.device and weights_fingerprint(den) == self.fingerprint
+        return canonical_device(x.device) == self.device and weights_fingerprint(den) == self.fingerprint
 
     def forward(self, x, timesteps, cond):
         Bx, T = x.shape[0], x.shape[1]

@@ -12,11 +12,13 @@ import torch
 
 from . import _lib
 
-MotionRequest = collections.namedtuple("MotionRequest", "cond motion_len repeats noise", defaults=(1, None))
+MotionRequest = collections.namedtuple("MotionRequest", "cond motion_len repeats noise text text_individual1 text_individual2",
+                                      defaults=(1, None, None, None, None))
 MotionRequest.__doc__ = """One prompt of the evaluation loop.
-cond: (6144,) or (repeats, 6144) condition vector(s) (`MixerMDM.generate_cond`); motion_len: frames to generate
-(`motion_lens[0]`); repeats: copies of the prompt (`mm_num_repeats` for MultiModality samples, else 1);
-noise: optional (repeats, motion_len, 524) initial noise (otherwise the model draws it)."""
+cond: (6144,) or (repeats, 6144) condition vector(s) (`MixerMDM.generate_cond`), or None when the prompt is given as
+text (`text`, and for the extended data sets `text_individual1` / `text_individual2`: the model encodes them);
+motion_len: frames to generate (`motion_lens[0]`); repeats: copies of the prompt (`mm_num_repeats` for MultiModality
+samples, else 1); noise: optional (repeats, motion_len, 524) initial noise (otherwise the model draws it)."""
 
 
 def format_generated(output, max_length, mean=None, std=None):
@@ -89,28 +91,46 @@ class BatchedGenerator:
         mean, std = self.normalizer if self.normalizer is not None else (None, None)
         for T, idxs in plan_batches(requests, self.max_batch):
             conds, noises, have_noise = [], [], [requests[i].noise is not None for i in idxs]
+            have_cond = [requests[i].cond is not None for i in idxs]
             if any(have_noise) and not all(have_noise):
                 raise ValueError("either every request of a batch carries its initial noise or none does")
+            if any(have_cond) and not all(have_cond):
+                raise ValueError("either every request of a batch carries its condition vector or every one its text")
+            texts = {"text": [], "text_individual1": [], "text_individual2": []}
             for i in idxs:
                 r = requests[i]
-                c = r.cond if r.cond.dim() == 2 else r.cond.unsqueeze(0).expand(r.repeats, -1)
-                if c.shape[0] != r.repeats:
-                    raise ValueError(f"request {i}: cond has {c.shape[0]} rows for {r.repeats} repeats")
-                conds.append(c)
+                if r.cond is not None:
+                    c = r.cond if r.cond.dim() == 2 else r.cond.unsqueeze(0).expand(r.repeats, -1)
+                    if c.shape[0] != r.repeats:
+                        raise ValueError(f"request {i}: cond has {c.shape[0]} rows for {r.repeats} repeats")
+                    conds.append(c)
+                else:
+                    if r.text is None:
+                        raise ValueError(f"request {i}: neither a condition vector nor a text prompt")
+                    # not extended data sets carry one description: like the reference's non-extended callers, it
+                    # stands for the individual ones too
+                    for k in texts:
+                        texts[k] += [getattr(r, k) if getattr(r, k) is not None else r.text] * r.repeats
                 if r.noise is not None:
                     if tuple(r.noise.shape[:2]) != (r.repeats, T):
                         raise ValueError(f"request {i}: noise must be (repeats, motion_len, 524)")
                     noises.append(r.noise)
-            cond = torch.cat(conds, dim=0)
+            cond = torch.cat(conds, dim=0) if conds else None
             noise = torch.cat(noises, dim=0) if noises else None
-            rows = cond.shape[0]
-            if rows == 3:
+            rows = cond.shape[0] if cond is not None else len(texts["text"])
+            pad = 1 if rows == 3 else 0
+            if pad:
                 # a sampler call on exactly 3 rows is refused (the reference's center_motion mixes the samples of a
                 # batch of 3, engine.MixerEngine._check_batch): samples are independent, so one repeated row is added
                 # and dropped again
-                cond = torch.cat([cond, cond[-1:]], dim=0)
+                cond = torch.cat([cond, cond[-1:]], dim=0) if cond is not None else None
                 noise = torch.cat([noise, noise[-1:]], dim=0) if noise is not None else None
-            batch = {"cond": cond, "motion_lens": torch.full((cond.shape[0],), T, dtype=torch.long)}
+                texts = {k: v + v[-1:] for k, v in texts.items()}
+            batch = {"motion_lens": torch.full((rows + pad,), T, dtype=torch.long)}
+            if cond is not None:
+                batch["cond"] = cond
+            else:
+                batch.update(texts)
             if noise is not None:
                 batch["noise"] = noise
             out = self.model.forward_test(batch)["output"][:rows]
@@ -121,3 +141,36 @@ class BatchedGenerator:
                 results[i] = formatted[row:row + requests[i].repeats]
                 row += requests[i].repeats
         return results
+
+
+def generate_evaluation_set(model, items, mm_idxs=(), mm_num_repeats=1, max_length=300, normalizer=None, extended=False,
+                            max_batch=32, formatter=format_generated):
+    """The generation loop of `EvaluationDatasetInterHuman.__init__` (reference evaluation/datasets.py:64-160) with
+    request batching. items: what its DataLoader(batch_size=1) yields - (name, text, motion1, motion2, motion_lens
+    [, text_individual1, text_individual2]) with 1-tuples of strings and a (1,) length tensor; the ground-truth motions
+    are ignored. mm_idxs: indices generated `mm_num_repeats` times for the MultiModality metric. Returns
+    (generated_motions, mm_generated_motions): lists of dicts with the reference's keys, motions as numpy arrays
+    (max_length, 262) / (repeats, max_length, 2, 262), `normalizer` = (mean, std) for its normalize=True."""
+    mm = set(int(i) for i in mm_idxs)
+    reqs, meta = [], []
+    for i, data in enumerate(items):
+        text, lens = data[1], data[4]
+        ti1, ti2 = (data[5], data[6]) if extended else (None, None)
+        T = int(lens[0])
+        reqs.append(MotionRequest(None, T, mm_num_repeats if i in mm else 1, None, text[0],
+                                  ti1[0] if extended else None, ti2[0] if extended else None))
+        meta.append((text[0], lens[0], ti1[0] if extended else None, ti2[0] if extended else None, i in mm))
+    outs = BatchedGenerator(model, max_length=max_length, normalizer=normalizer, max_batch=max_batch,
+                            formatter=formatter).generate(reqs)
+    generated, mm_generated = [], []
+    for (text, length, ti1, ti2, is_mm), out in zip(meta, outs):
+        arr = out.detach().cpu().numpy()
+        sub = {"motion1": arr[0, :, 0], "motion2": arr[0, :, 1], "motion_lens": length, "text": text}
+        mm_sub = {"mm_motions": arr, "motion_lens": length, "text": text}
+        if extended:
+            for d in (sub, mm_sub):
+                d["text_individual1"], d["text_individual2"] = ti1, ti2
+        generated.append(sub)
+        if is_mm:
+            mm_generated.append(mm_sub)
+    return generated, mm_generated

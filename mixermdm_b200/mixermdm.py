@@ -96,7 +96,8 @@ class _ClipTextTower:
     def _encode_text(self, key, encoders, tokens):
         """run the CUDA text path: this object's CLIP tower, then `encoders` [(TransformerEncoder, LayerNorm), ...]"""
         cache = self.__dict__.setdefault("_text_engines", {})
-        device = self.positional_embedding.device
+        from .engine import canonical_device
+        device = canonical_device(self.positional_embedding.device)
         eng = cache.get(key)
         if eng is None or eng.device != device or eng.stale():
             cache[key] = None

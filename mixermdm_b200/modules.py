@@ -216,7 +216,8 @@ class Mixer(nn.Module):
         """the CUDA engine bound to a workspace for `batch_rows` network rows (CFG-doubled batch) of `frames`;
         rebuilt when a sampler asks for another schedule / guidance scale / centring flag"""
         eng = self._engine
-        stale = (eng is None or eng.device != torch.device(device) or
+        device = _engine.canonical_device(device)
+        stale = (eng is None or eng.device != device or
                  eng.fingerprint != _engine.weights_fingerprint(self))   # live parameters changed since packing
         if eng is not None and not stale:
             stale = ((sched is not None and not eng.sched.same_as(sched)) or

@@ -70,7 +70,8 @@ class TextEngine:
         encoders: list of (nn.TransformerEncoder container, nn.LayerNorm container)"""
         from .engine import weights_fingerprint
         self.lib = _lib.load()
-        self.device = torch.device(device)
+        from .engine import canonical_device
+        self.device = canonical_device(device)
         if self.device.type != "cuda":
             raise MmdmError("the text path runs on CUDA devices only (sm_100a); there is no CPU path")
         pk = _Pack(self.device)

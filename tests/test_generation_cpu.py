@@ -78,3 +78,41 @@ def test_gpu_formatter_refuses_cpu_tensors():
     from mixermdm_b200.generation import format_generated
     with pytest.raises(_lib.MmdmError):
         format_generated(torch.zeros(1, 4, 524), 8)
+
+
+class _StubTextModel:
+    """forward_test on text batches: output[b] = hash of the three prompts of row b (so rows are traceable)"""
+
+    def __init__(self):
+        self.calls = []
+
+    def forward_test(self, batch):
+        T = int(batch["motion_lens"][0])
+        rows = len(batch["text"])
+        assert len(batch["text_individual1"]) == rows == len(batch["text_individual2"]) == batch["motion_lens"].shape[0]
+        assert rows != 3                                     # the generator never issues a 3-row sampler call
+        self.calls.append((rows, T))
+        tag = torch.tensor([float(len(a) + 10 * len(b) + 100 * len(c)) for a, b, c in
+                            zip(batch["text"], batch["text_individual1"], batch["text_individual2"])])
+        return {"output": tag[:, None, None] + torch.zeros(rows, T, 524)}
+
+
+def test_evaluation_set_adapter_follows_the_reference_contract():
+    """evaluation/datasets.py:64-160: DataLoader(batch_size=1) items in, the reference's dict lists out"""
+    from mixermdm_b200.generation import generate_evaluation_set
+    items = []
+    for i, (T, txt) in enumerate([(24, "aa"), (17, "bbbb"), (24, "c"), (24, "dddddd"), (17, "ee")]):
+        items.append((("name%d" % i,), (txt,), None, None, torch.tensor([T]), (txt + "1",), (txt + "22",)))
+    model = _StubTextModel()
+    generated, mm = generate_evaluation_set(model, items, mm_idxs=[1], mm_num_repeats=2, max_length=32,
+                                            extended=True, max_batch=8, formatter=_cpu_formatter)
+    assert sorted(model.calls) == [(4, 17), (4, 24)]      # T=17: 2 + 1 = 3 rows padded to 4; T=24: 3 prompts + ... = 3 -> 4
+    assert len(generated) == 5 and len(mm) == 1
+    for it, g in zip(items, generated):
+        txt = it[1][0]
+        tag = len(txt) + 10 * (len(txt) + 1) + 100 * (len(txt) + 2)
+        T = int(it[4][0])
+        assert g["text"] == txt and g["text_individual1"] == txt + "1" and int(g["motion_lens"]) == T
+        assert g["motion1"].shape == (32, 262) and g["motion2"].shape == (32, 262)
+        assert (g["motion1"][:T] == tag).all() and (g["motion1"][T:] == 0).all()
+    assert mm[0]["mm_motions"].shape == (2, 32, 2, 262) and mm[0]["text"] == "bbbb"

@@ -66,6 +66,13 @@ def test_stepping_past_the_schedule_is_an_error(golden):
         eng.step()
     # the message is the handle's own
     assert b"no step left" in eng.lib.mmdm_last_error(eng.hd.h)
+    # an explicit-batch forward in between re-uses the conditioning tables: stepping without a new set_condition is refused
+    eng.set_state(x1, x2, 5)
+    mix(torch.cat([x1, x1]), torch.cat([t, t]), cond=torch.cat([cond, cond]), mask=None, x2=torch.cat([x2, x2]))
+    with pytest.raises(MmdmError, match="no condition set"):
+        eng.step()
+    eng.set_condition(cond)
+    eng.step()
 
 
 def test_wrong_shapes_raise_instead_of_reading_out_of_bounds(golden):

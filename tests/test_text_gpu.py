@@ -86,3 +86,39 @@ def test_forward_test_from_prompts(text_model):
     out2 = model.forward_test({"cond": cond, "motion_lens": batch["motion_lens"], "noise": noise.clone()})["output"]
     torch.cuda.synchronize()
     assert out.shape == (2, 20, 524) and torch.isfinite(out).all() and torch.equal(out, out2)
+
+
+def test_evaluation_set_from_prompts_mixed_lengths_and_graph_cache(text_model):
+    """The evaluation generators' contract (evaluation/datasets.py:64-160) on the real model: prompts of different
+    lengths are packed per length, every motion equals what one forward_test per prompt gives, and alternating
+    between lengths re-uses the cached step graphs instead of capturing again."""
+    from mixermdm_b200.generation import BatchedGenerator, MotionRequest, generate_evaluation_set
+    model, meta = text_model
+    P = meta["prompts"]
+    items = []
+    for i, T in enumerate([20, 28, 20, 28]):
+        j = i % 2
+        items.append((("n",), (P["text"][j],), None, None, torch.tensor([T]), (P["text_individual1"][j],),
+                      (P["text_individual2"][j],)))
+    gen, mm = generate_evaluation_set(model, items, mm_idxs=[0], mm_num_repeats=2, max_length=32, extended=True)
+    assert len(gen) == 4 and len(mm) == 1 and mm[0]["mm_motions"].shape == (2, 32, 2, 262)
+    assert gen[1]["motion1"].shape == (32, 262) and np.isfinite(gen[1]["motion1"]).all()
+    assert (gen[0]["motion1"][20:] == 0).all() and (gen[1]["motion2"][28:] == 0).all()
+    # bitwise: one request with fixed noise through the batched path == the same prompt alone through forward_test
+    g = torch.Generator().manual_seed(5)
+    reqs = [MotionRequest(None, T, 1, torch.randn(1, T, 524, generator=g).to(DEV), P["text"][j],
+                          P["text_individual1"][j], P["text_individual2"][j]) for T, j in [(20, 0), (28, 1), (20, 1)]]
+    eng = model.mixing.engine(4, 20, torch.device(DEV))
+    outs = BatchedGenerator(model, max_length=32, max_batch=8).generate(reqs)
+    before = eng.hd.graph_captures()
+    for r, got in zip(reqs, outs):
+        one = model.forward_test({"text": [r.text], "text_individual1": [r.text_individual1],
+                                  "text_individual2": [r.text_individual2], "noise": r.noise.clone(),
+                                  "motion_lens": torch.tensor([r.motion_len])})["output"]
+        torch.cuda.synchronize()
+        assert torch.equal(got[0, :r.motion_len].reshape(r.motion_len, 524), one[0])
+    again = BatchedGenerator(model, max_length=32, max_batch=8).generate(reqs)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(outs, again))
+    eng2 = model.mixing.engine(4, 20, torch.device(DEV))
+    assert eng2 is eng and eng.hd.graph_captures() - before <= 2      # B=1 x {20, 28} captured once each, then re-used

@@ -2,7 +2,7 @@
 denoising loop of pabloruizponce/MixerMDM. It is the checker for the CUDA path (tests/, __graft_entry__.smoke,
 bench.py's cpu_baseline / --impl reference legs) and is never imported by the product package.
 
-Pinned against the unmodified reference: tests/test_oracle_vs_reference.py runs both on identical weights and
+Pinned against the unmodified reference: tests/test_oracle_cpu.py runs both on identical weights and
 inputs (reference imported from /root/reference through oracle/ref_harness.py) and tests/golden/*.npz hold
 outputs of the reference itself (oracle/make_goldens.py). The reference ships no tests or golden vectors of its
 own, so those two are the pin.

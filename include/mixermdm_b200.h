@@ -196,6 +196,12 @@ int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream);
 /* one DDIM step: CFG-doubled Mixer.forward + process_xstart + DDIM update; decrements the device step index.
  * replaces MixerDiffusion.ddim_sample (gaussian_diffusion.py:1902-1965) */
 int mmdm_step(mmdm_handle* h, float* final_out /* (B,T,524) guided prediction of the step (the sample when the index is 0), or NULL */, void* stream);
+/* state += scale * noise on both streams (noise1 / noise2: device (B,T,524) fp32, may be the same buffer): the
+ * sigma_t * z term of an ancestral (DDPM) update, GaussianDiffusion.p_sample (gaussian_diffusion.py:683-691). With the
+ * handle's coefficient table set to the posterior-mean form (schedule.py: ddpm_coefficients) a DDPM step is
+ * mmdm_step followed by this call; the reference's own MixerDiffusion cannot run p_sample (SURVEY 8a note 2), so the
+ * parity of this variant is formula-level. */
+int mmdm_add_state_noise(mmdm_handle* h, const float* noise1, const float* noise2, float scale, void* stream);
 /* whole loop from noise; result = pred_xstart2 of the last step (gaussian_diffusion.py:1769-1820).
  * use_graph != 0 replays one captured step graph nsteps times (graphs are cached per batch / frame count, so
  * re-binding the same workspace to another motion length and back does not capture again). hist_i1/hist_i2: optional

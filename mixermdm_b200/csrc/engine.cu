@@ -703,6 +703,16 @@ int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream) {
   });
 }
 
+int mmdm_add_state_noise(mmdm_handle* h, const float* noise1, const float* noise2, float scale, void* stream) {
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base && noise1 && noise2, "mmdm_add_state_noise: handle not bound / null noise");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Scope sc(h, "state_noise", st);
+    MMDM_TRY(launch_add_state_noise(h->ws.x1, h->ws.x2, noise1, noise2, (long long)h->B * h->T, 2 * h->cfg.nfeats, scale, st));
+    return 0;
+  });
+}
+
 int mmdm_step(mmdm_handle* h, float* final_out, void* stream) {
   return guarded(h, [&]() -> int {
     MMDM_REQUIRE(h && h->ws_base, "mmdm_step: handle not bound");

@@ -276,4 +276,34 @@ int launch_add_int(int* p, int v, cudaStream_t stream) {
   return 0;
 }
 
+// x1 += scale * n1, x2 += scale * n2 on the interleaved state rows (x1 | x2, 2 * rowf floats per frame): the noise term of
+// an ancestral (DDPM) update, reference GaussianDiffusion.p_sample (gaussian_diffusion.py:683-691). float4 per thread.
+__global__ void add_state_noise_kernel(float* __restrict__ x1, float* __restrict__ x2, const float* __restrict__ n1,
+                                       const float* __restrict__ n2, long long nrows, int row4, float scale) {
+  const long long total = nrows * row4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row4;
+    const int c = (int)(i - r * row4);
+    const float4 a = reinterpret_cast<const float4*>(n1)[i], b = reinterpret_cast<const float4*>(n2)[i];
+    float4* p1 = reinterpret_cast<float4*>(x1) + r * 2 * row4 + c;
+    float4* p2 = reinterpret_cast<float4*>(x2) + r * 2 * row4 + c;
+    float4 u = *p1, v = *p2;
+    u.x = fmaf(scale, a.x, u.x); u.y = fmaf(scale, a.y, u.y); u.z = fmaf(scale, a.z, u.z); u.w = fmaf(scale, a.w, u.w);
+    v.x = fmaf(scale, b.x, v.x); v.y = fmaf(scale, b.y, v.y); v.z = fmaf(scale, b.z, v.z); v.w = fmaf(scale, b.w, v.w);
+    *p1 = u;
+    *p2 = v;
+  }
+}
+int launch_add_state_noise(float* x1, float* x2, const float* n1, const float* n2, long long nrows, int rowf, float scale,
+                           cudaStream_t stream) {
+  MMDM_REQUIRE(rowf % 4 == 0 && ((uintptr_t)x1 % 16 == 0) && ((uintptr_t)x2 % 16 == 0) && ((uintptr_t)n1 % 16 == 0) &&
+               ((uintptr_t)n2 % 16 == 0), "add_state_noise: rows must be float4-aligned");
+  const long long total = nrows * (rowf / 4);
+  const long long want = (total + 255) / 256, cap = (long long)device_sm_count() * 16;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  add_state_noise_kernel<<<grid, 256, 0, stream>>>(x1, x2, n1, n2, nrows, rowf / 4, scale);
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace mmdm

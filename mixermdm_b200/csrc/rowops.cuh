@@ -28,5 +28,7 @@ int launch_pack_state(const float* x, int B, int T, int nf, int kpad, int person
 
 int launch_set_int(int* p, int v, cudaStream_t stream);
 int launch_add_int(int* p, int v, cudaStream_t stream);
+int launch_add_state_noise(float* x1, float* x2, const float* n1, const float* n2, long long nrows, int rowf, float scale,
+                           cudaStream_t stream);
 
 }  // namespace mmdm

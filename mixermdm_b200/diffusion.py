@@ -65,6 +65,34 @@ class MixerDiffusion:
         eng = mixer.engine(2 * B, T, device, sched=self.schedule, cfg_scale=float(model.s), center=self.align)
         return mixer, eng
 
+    def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                      model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                      randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,
+                      generator=None, step_noise=None):
+        """Ancestral (DDPM) sampling over the same two-stream step (GaussianDiffusion.p_sample_loop's signature,
+        gaussian_diffusion.py:694-760; update of p_sample :683-691: mean = coef1 x0 + coef2 x_t, + sigma_t z for
+        t != 0). The reference's MixerDiffusion inherits p_sample but cannot run it (its p_mean_variance override takes
+        the second stream, SURVEY 8a note 2), so this variant is derived and its parity is formula-level (tested)."""
+        if dump_steps is not None or const_noise or skip_timesteps or init_image is not None:
+            raise NotImplementedError()
+        if clip_denoised or denoised_fn is not None or cond_fn is not None or cond_fn_with_grad or randomize_class:
+            raise NotImplementedError("clip_denoised=False, no denoised_fn/cond_fn: the MixerMDM inference path")
+        model_kwargs = model_kwargs or {}
+        if model_kwargs.get("mask") is not None:
+            raise NotImplementedError("mask=None is the only masking the MixerMDM sampler uses")
+        cond = model_kwargs["cond"]
+        if device is None:
+            device = cond.device if noise is None else noise.device
+        B, T, D = shape
+        assert D == 524
+        if noise is None:
+            noise = torch.randn(*shape, device=device, generator=generator)
+        var = {ModelVarType.FIXED_SMALL: "fixed_small", ModelVarType.FIXED_LARGE: "fixed_large"}.get(self.model_var_type)
+        if var is None:
+            raise NotImplementedError("MixerDiffusion.p_sample_loop: fixed variances only")
+        _, eng = self._engine_for(model, B, T, torch.device(device))
+        return eng.sample_ddpm(cond, noise, step_noise=step_noise, generator=generator, var_type=var)
+
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                          model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None,
                          randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,

@@ -334,8 +334,9 @@ class MixerEngine:
         tmap = (C.c_int32 * cfg.nsteps)(*self.sched.timestep_map)
         pk.keep.append(tmap)
         cfg.timestep_map = C.cast(tmap, C.POINTER(C.c_int32))
-        self.coef = pk.f32(torch.from_numpy(self.sched.ddim_coefficients()))
+        self.coef = pk.f32(torch.from_numpy(self.sched.ddim_coefficients()))   # rewritten in place by set_sampler()
         cfg.coef = pk.p(self.coef)
+        self.sampler, self.sigma = "ddim", None
         self.head_w, self.head_b = pk.bf16(mixer.influence.out.weight), pk.f32(mixer.influence.out.bias)
         cfg.head_w, cfg.head_b = pk.p(self.head_w), pk.p(self.head_b)
         n1, n2 = mixer.normalizer_model1, mixer.normalizer_model2
@@ -396,6 +397,58 @@ class MixerEngine:
             self._check_state(final_out, "final_out")
         self._check_batch(self.hd.B)
         self.hd.call("mmdm_step", ptr(final_out), self.hd.stream())
+
+    def set_sampler(self, kind, var_type="fixed_small"):
+        """"ddim" (eta = 0, the reference's inference path) or "ddpm" (ancestral update): swaps the per-step coefficient
+        table the fused step reads on the device; captured step graphs stay valid (same pointer)."""
+        key = (kind, var_type if kind == "ddpm" else None)
+        if key == (self.sampler, getattr(self, "_var_type", None)):
+            return
+        if kind == "ddim":
+            table, self.sigma = self.sched.ddim_coefficients(), None
+        elif kind == "ddpm":
+            table, self.sigma = self.sched.ddpm_coefficients(var_type)
+        else:
+            raise ValueError(f"sampler must be 'ddim' or 'ddpm', got {kind!r}")
+        with torch.cuda.device(self.device):
+            self.coef.copy_(torch.from_numpy(table).to(self.device))
+            torch.cuda.current_stream().synchronize()
+        self.sampler, self._var_type = key
+
+    def add_state_noise(self, noise1, noise2, scale):
+        """state += scale * noise on both streams (the sigma_t z term of a DDPM step)"""
+        for n in (noise1, noise2):
+            self._check_state(n, "noise")
+            _expect(n, (self.hd.B, self.hd.T, 2 * NFEATS), "noise")
+        self.hd.call("mmdm_add_state_noise", ptr(noise1), ptr(noise2), C.c_float(float(scale)), self.hd.stream())
+
+    def sample_ddpm(self, cond, noise, step_noise=None, generator=None, var_type="fixed_small"):
+        """whole ancestral (DDPM) loop: the fused step with posterior-mean coefficients + sigma_t z after every step but
+        the last. step_noise: optional (nsteps - 1, B, T, 524) tensor of the z's (index i is used after DDIM-table
+        index nsteps - 1 - i); otherwise drawn with torch.randn(generator=...). Both state streams receive the same z,
+        as they start from the same noise. Returns the last step's prediction like sample()."""
+        B, T = noise.shape[0], noise.shape[1]
+        _expect(noise, (B, T, 2 * NFEATS), "noise")
+        _expect(cond, (B, 8 * TEXT_DIM), "cond")
+        self._check_batch(B)
+        self.bind(B, T)
+        prev = (self.sampler, getattr(self, "_var_type", None))
+        self.set_sampler("ddpm", var_type)
+        try:
+            noise = _f32c(noise, self.device)
+            self.set_condition(cond)
+            self.set_state(noise, noise, self.nsteps - 1)
+            out = torch.empty(B, T, 2 * NFEATS, device=self.device)
+            for i in range(self.nsteps - 1, -1, -1):
+                self.step(out if i == 0 else None)
+                if i > 0:
+                    k = self.nsteps - 1 - i
+                    z = (_f32c(step_noise[k], self.device) if step_noise is not None else
+                         torch.randn(B, T, 2 * NFEATS, device=self.device, generator=generator))
+                    self.add_state_noise(z, z, float(self.sigma[i]))
+        finally:
+            self.set_sampler(prev[0], prev[1] or "fixed_small")
+        return out
 
     def sample(self, cond, noise, out=None, store_influence=False, use_graph=True, store_outputs=False):
         """whole DDIM loop; cond (B,6144), noise (B,T,524) device fp32 -> (B,T,524) real-space prediction.

@@ -89,3 +89,23 @@ class SpacedSchedule:
         c[:, 2] = np.sqrt(ab_prev)
         c[:, 3] = np.sqrt(np.float32(1.0) - ab_prev - np.float32(0.0))
         return c
+
+    def ddpm_coefficients(self, var_type="fixed_small"):
+        """Ancestral (DDPM) update x_{t-1} = coef1 x0 + coef2 x_t + sigma_t z in the kernels' table format
+        (reference GaussianDiffusion.q_posterior_mean_variance :452-478, p_mean_variance :520-538, p_sample :683-691).
+        The fused step forms A = c2 - c3 / c1 and B = c3 / c1 * c0 from its row (c0, c1, c2, c3) and applies
+        x_prev = A x0 + B x_t, so the row (1, 1, coef1 + coef2, coef2) gives A = coef1, B = coef2.
+        Returns ((nsteps, 4) fp32 table, (nsteps,) float64 sigma_t = exp(0.5 log variance); sigma is unused at t = 0)."""
+        c = np.zeros((self.num_timesteps, 4), dtype=np.float32)
+        c[:, 0] = 1.0
+        c[:, 1] = 1.0
+        c[:, 3] = self.posterior_mean_coef2.astype(np.float32)
+        # (the kernel forms c2 - c3 in double: it gets coef1 back to half an fp32 ulp of coef1 + coef2 <= 1)
+        c[:, 2] = (self.posterior_mean_coef1.astype(np.float32).astype(np.float64) + c[:, 3].astype(np.float64))
+        if var_type == "fixed_small":
+            logvar = self.posterior_log_variance_clipped
+        elif var_type == "fixed_large":
+            logvar = np.log(np.append(self.posterior_variance[1], self.betas[1:]))
+        else:
+            raise NotImplementedError("learned variances are not on the MixerMDM path")
+        return c, np.exp(0.5 * logvar)

@@ -109,8 +109,21 @@ def text():
     print("text:", cond.shape, float(cond.abs().mean()))
 
 
+def schedule_tables():
+    """tests/golden/reference_schedule.npz: the posterior tables of the reference's re-spaced diffusion object (the
+    DDPM side of GaussianDiffusion.__init__, gaussian_diffusion.py:355-382), float64"""
+    _, diff, _ = ref_harness.build_reference(synth.SMALL_DIMS, mixing_mode=4, store_influence=False)
+    names = ("betas", "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+             "posterior_mean_coef2")
+    np.savez_compressed(os.path.join(OUT, "reference_schedule.npz"), **{n: np.asarray(getattr(diff, n)) for n in names})
+    print("schedule:", {n: np.asarray(getattr(diff, n)).shape for n in names})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--schedule-only" in sys.argv:
+        schedule_tables()
+        return
     if "--chain-only" in sys.argv:
         chain()
         return
@@ -181,6 +194,7 @@ def main():
     print("wrote", len(arrays), "arrays;", os.path.getsize(os.path.join(OUT, "reference_small.npz")) // 1024, "KiB")
     chain()
     text()
+    schedule_tables()
 
 
 if __name__ == "__main__":

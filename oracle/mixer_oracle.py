@@ -323,6 +323,22 @@ class Oracle:
         n2 = p2 * ca + ce * ((cr * x2 - p2) / crm1)
         return dict(sample=n1, sample2=n2, pred_xstart=p1, pred_xstart2=p2, guided=g)
 
+    def ddpm_step(self, x1, x2, i, cond, z):
+        """Ancestral update of GaussianDiffusion.p_sample (models/utils/gaussian_diffusion.py:632-692) over the two-stream
+        prediction: mean = coef1 x0 + coef2 x_t (q_posterior_mean_variance :452-478), + exp(0.5 logvar) z for t != 0,
+        FIXED_SMALL variance (:520-538). The reference's MixerDiffusion cannot execute p_sample (SURVEY 8a note 2), so
+        this restates the inherited formula on MixerDiffusion.p_mean_variance's two pred_xstart streams."""
+        B = x1.shape[0]
+        t = torch.full((B,), int(self.sched.timestep_map[i]), dtype=torch.long)
+        g = self.guided(x1, x2, t, cond)
+        p1, p2 = self.process_xstart(g, last=(i == 0))
+        c1 = torch.tensor(float(self.sched.posterior_mean_coef1[i]), dtype=torch.float32)
+        c2 = torch.tensor(float(self.sched.posterior_mean_coef2[i]), dtype=torch.float32)
+        sg = torch.tensor(float(np.exp(0.5 * self.sched.posterior_log_variance_clipped[i])), dtype=torch.float32)
+        nz = 0.0 if i == 0 else 1.0
+        return dict(sample=c1 * p1 + c2 * x1 + nz * sg * z, sample2=c1 * p2 + c2 * x2 + nz * sg * z,
+                    pred_xstart=p1, pred_xstart2=p2, guided=g)
+
     def sample(self, noise, cond, steps=None, trace=None):
         """models/utils/gaussian_diffusion.py:1769-1899 — both streams start from the same noise"""
         x1, x2 = noise.clone(), noise.clone()

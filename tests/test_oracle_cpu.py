@@ -42,6 +42,27 @@ def test_schedule_tables_match_reference_golden(golden):
     np.testing.assert_array_equal(c[:, 2], np.sqrt(arr["alphas_cumprod_prev"].astype(np.float32)))
 
 
+def test_ddpm_tables_match_reference_golden():
+    """posterior tables of the reference's diffusion object (bit exact, float64) and the kernel-format DDPM row:
+    A = c2 - c3 / c1, B = c3 / c1 * c0 (what the fused step forms) give back coef1 / coef2"""
+    import os
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_schedule.npz"))
+    s = default_schedule()
+    for name in ("betas", "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+                 "posterior_mean_coef2"):
+        np.testing.assert_array_equal(getattr(s, name), ref[name])
+    c, sigma = s.ddpm_coefficients()
+    assert c.dtype == np.float32 and c.shape == (50, 4)
+    c = c.astype(np.float64)
+    A, B = c[:, 2] - c[:, 3] / c[:, 1], c[:, 3] / c[:, 1] * c[:, 0]
+    np.testing.assert_allclose(A, ref["posterior_mean_coef1"], rtol=0, atol=1.2e-7)
+    np.testing.assert_allclose(B, ref["posterior_mean_coef2"], rtol=1e-7, atol=0)
+    np.testing.assert_array_equal(sigma, np.exp(0.5 * ref["posterior_log_variance_clipped"]))
+    assert A[0] == 1.0 and B[0] == 0.0          # t = 0: the sample is the prediction itself
+    large = s.ddpm_coefficients("fixed_large")[1]
+    np.testing.assert_allclose(large[1:] ** 2, ref["betas"][1:], rtol=1e-12)
+
+
 def test_motion_math_matches_reference_golden(golden):
     arr, _ = golden
     a, b, c = [torch.from_numpy(arr[k]) for k in ("unit_in_a", "unit_in_b", "unit_in_c")]

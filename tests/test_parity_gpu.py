@@ -384,6 +384,63 @@ def test_every_ddim_step_teacher_forced_vs_reference_chain():
     report("worst per-step state vs the reference chain", worst["state"])
 
 
+def test_ddpm_step_formula_level(golden):
+    """The DDPM variant of the fused update (north star: "DDIM/DDPM update"). The reference's MixerDiffusion cannot run
+    p_sample, so parity is formula-level: (1) against the oracle's restatement of p_sample on the two-stream prediction
+    (bf16 networks: guided-state tolerance); (2) exactly, against the x0 implied by this engine's own DDIM update of the
+    same state: x_ddpm = coef1 x0 + coef2 x_t + sigma z (fp32: 1e-4); (3) the loop entry point is reproducible."""
+    arr, meta = golden
+    cond, noise, t, x1, x2 = _inputs(meta)
+    mix, sd = build_mixer(meta["dims"])
+    mix = mix.to(DEV)
+    sched = default_schedule()
+    eng = mix.engine(2 * meta["B"], meta["T"], torch.device(DEV), sched=sched, cfg_scale=3.5, center=True)
+    idx = 30
+    eng.set_condition(cond)
+    eng.set_state(x1, x2, idx)
+    eng.step()
+    d1, d2 = eng.get_state()
+    eng.set_sampler("ddpm")
+    eng.set_state(x1, x2, idx)
+    eng.step()
+    m1, m2 = eng.get_state()
+    z = torch.randn(x1.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    sigma = float(eng.sigma[idx])
+    eng.add_state_noise(z, z, sigma)
+    s1, s2 = eng.get_state()
+    eng.set_sampler("ddim")
+    torch.cuda.synchronize()
+    # (2) exact relation between the two updates of the same prediction
+    cr, crm1, ca, ce = [float(v) for v in sched.ddim_coefficients()[idx]]
+    A, Bc = ca - ce / crm1, ce / crm1 * cr
+    c1, c2 = float(sched.posterior_mean_coef1[idx]), float(sched.posterior_mean_coef2[idx])
+    for d, m, s_, x in ((d1, m1, s1, x1), (d2, m2, s2, x2)):
+        x0 = (d.double() - Bc * x.double()) / A
+        want = c1 * x0 + c2 * x.double()
+        assert report("ddpm mean vs own ddim x0", relerr(m, want.float())) < 1e-4
+        assert report("ddpm noise term", relerr(s_ - m, sigma * z)) < 1e-5
+    # (1) oracle restatement of p_sample
+    orc = build_oracle(sd, meta["dims"])
+    orc.sched = sched
+    o = orc.ddpm_step(x1.cpu(), x2.cpu(), idx, cond.cpu(), z.cpu())
+    assert report("ddpm step stream1 vs oracle", relerr(s1, o["sample"])) < TOL_GUIDED_STATE
+    assert report("ddpm step stream2 vs oracle", relerr(s2, o["sample2"])) < TOL_GUIDED_STATE
+    # (3) loop entry point: reproducible with given noises, ends on the last step's prediction, leaves DDIM selected
+    from mixermdm_b200.diffusion import MixerDiffusion, get_named_beta_schedule, space_timesteps
+    from mixermdm_b200.modules import ClassifierFreeSampleModelX2
+    diff = MixerDiffusion(use_timesteps=space_timesteps(1000, "ddim50"), betas=get_named_beta_schedule("cosine", 1000))
+    zs = torch.randn(49, *noise.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    kw = dict(noise=noise.clone(), clip_denoised=False, model_kwargs={"mask": None, "cond": cond}, step_noise=zs)
+    cfgm = ClassifierFreeSampleModelX2(mix, 3.5)
+    a = diff.p_sample_loop(cfgm, tuple(noise.shape), **kw)
+    b = diff.p_sample_loop(cfgm, tuple(noise.shape), **kw)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    ref = diff.ddim_sample_loop(cfgm, tuple(noise.shape), noise=noise.clone(), clip_denoised=False,
+                                model_kwargs={"mask": None, "cond": cond})
+    assert report("ddim loop after a ddpm loop", relerr(ref, arr["loop_mode4"])) < LOOP_TOL
+    assert not torch.equal(a, ref)
+
+
 def test_long_sequences_stream_through_the_attention_ring(golden):
     """T > 319: the K/V blocks of a sequence no longer fit the attention kernel's shared-memory ring and stream
     through it (the round-1 kernel stopped at T = 303; the reference's positional table goes to 5000)."""

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MMDM_ABI_VERSION 2
+#define MMDM_ABI_VERSION 3
 
 typedef struct mmdm_handle mmdm_handle;
 
@@ -85,6 +85,13 @@ int mmdm_ln_modulate(const float* h, int M, int D, int T, const float* mod0, int
  * replaces nn.MultiheadAttention(add_zero_attn=True) core (reference models/utils/layers.py:33-45,74-88) */
 int mmdm_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int Tp, void* out, int ldo,
                    int S, int T, int H, int hd, int kv_xor, void* stream);
+/* the same with a key-padding mask (key_padding_mask of nn.MultiheadAttention, layers.py:36-44): words from
+ * mmdm_build_key_mask, [S][ceil((T+1)/64)] uint64, indexed by the sequence the keys come from */
+int mmdm_attention_masked(const void* q, int ldq, const void* k, int ldk, const void* vt, int Tp, void* out, int ldo,
+                          int S, int T, int H, int hd, int kv_xor, const uint64_t* key_mask_words, void* stream);
+/* mask: device (rows, T) fp32, frame attendable where > 0.5 (reference: key_padding_mask = ~(mask > 0.5),
+ * in2in.py:433-435); sequence s of nseq reads mask row (s / persons) % rows; the zero-attention key stays attendable */
+int mmdm_build_key_mask(const float* mask, int rows, int nseq, int T, int persons, uint64_t* words, void* stream);
 
 /* fp32 out[r,n] = act(a[r,:].w[n,:] + b[n]) (act 0: none, 1: SiLU); text_embed / time_embed (utils.py:41-55) */
 int mmdm_small_linear(const float* a, int lda, const float* w, const float* b, float* out, int ldo, int R,
@@ -190,6 +197,12 @@ int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T);
 
 /* text_embed of the 8 condition slices for the bound batch (cond: device (B, 6144) fp32); once per batch */
 int mmdm_set_condition(mmdm_handle* h, const float* cond, void* stream);
+/* frame mask for every attention of the following forwards / steps on this handle (in2INDenoiser / Influence
+ * `mask` argument, in2in.py:410-435, influence.py:107-116): device (rows, T) fp32, frame kept where > 0.5; network
+ * batch row bx reads mask row bx % rows (so the sampler's B rows serve both CFG halves). NULL clears it. Cleared by
+ * mmdm_bind_workspace. The Mixer entry points refuse it with cfg.align (the reference's masked alignment does not run,
+ * alignment.py:86-89); the denoiser entry point takes it always. */
+int mmdm_set_key_mask(mmdm_handle* h, const float* mask, int rows, void* stream);
 /* state streams x1 (individual space) / x2 (interaction space), device (B,T,524) fp32, and the DDIM index */
 int mmdm_set_state(mmdm_handle* h, const float* x1, const float* x2, int step_index, void* stream);
 int mmdm_get_state(mmdm_handle* h, float* x1, float* x2, void* stream);

@@ -5,7 +5,7 @@ import os
 from . import _build
 
 _LIB = None
-ABI_VERSION = 2   # MMDM_ABI_VERSION of include/mixermdm_b200.h
+ABI_VERSION = 3   # MMDM_ABI_VERSION of include/mixermdm_b200.h
 
 
 class MmdmError(RuntimeError):

@@ -63,6 +63,20 @@ int mmdm_attention(const void* q, int ldq, const void* k, int ldk, const void* v
                           ldo, S, T, H, hd, kv_xor, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mmdm_attention_masked(const void* q, int ldq, const void* k, int ldk, const void* vt, int Tp, void* out, int ldo,
+                          int S, int T, int H, int hd, int kv_xor, const uint64_t* key_mask_words, void* stream) {
+  MMDM_REQUIRE(q && k && vt && out, "mmdm_attention_masked: null argument");
+  return launch_attention(reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(k),
+                          ldk, reinterpret_cast<const __nv_bfloat16*>(vt), Tp, reinterpret_cast<__nv_bfloat16*>(out),
+                          ldo, S, T, H, hd, kv_xor, reinterpret_cast<cudaStream_t>(stream), 0,
+                          reinterpret_cast<const unsigned long long*>(key_mask_words));
+}
+
+int mmdm_build_key_mask(const float* mask, int rows, int nseq, int T, int persons, uint64_t* words, void* stream) {
+  return build_key_mask(mask, rows, nseq, T, persons, reinterpret_cast<unsigned long long*>(words),
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
 int mmdm_small_linear(const float* a, int lda, const float* w, const float* b, float* out, int ldo, int R,
                       int N, int K, int act, void* stream) {
   MMDM_REQUIRE(a && w && out, "mmdm_small_linear: null argument");

@@ -29,6 +29,7 @@ struct AttnParams {
   int ldo, wide_store;   // output row pitch (elements); 32-byte stores allowed
   int stagger;           // cycles the second warpgroup starts late
   __nv_bfloat16* out;
+  const unsigned long long* kmask;   // optional key-padding mask: [S][NB] words, bit j of word kb = key kb*64+j attendable
   float scale_log2, tau_raw;
 };
 
@@ -121,7 +122,7 @@ __device__ __forceinline__ void ring_next(RingPos& r) {
 //   qfull[g]   TMA             Q tile landed;                   qfree[g]  MMA commit: last S of the tile complete
 //   kfull/vfull[slot] TMA;     kfree/vfree[slot]  one arrival per tile of the group (a softmax warp that has seen the
 //                              covering S complete, or an MMA commit for the last two V blocks of a tile)
-template <int HD>
+template <int HD, bool MASKED>
 __global__ void __launch_bounds__(AttnCfg<HD>::THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -401,6 +402,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       RingPos rv = rk;                                      // V block whose P V completion is observed next
       float m_used = 0.f;    // the zero-attention key contributes logit 0: the maximum never drops below it
       float lsum = 0.f;
+      const unsigned long long* kmrow = nullptr;   // key-padding words of the sequence the keys come from
+      if constexpr (MASKED) {
+        int s_, h_;
+        item_sh(ti.k, s_, h_);
+        kmrow = p.kmask + (size_t)(s_ ^ p.kv_xor) * NB;
+      }
       for (int kb = 0; kb < NB; ++kb) {
         const int m = m0 + kb, b = m & 1;
         TR(warp, m, 0);
@@ -424,8 +431,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         TR(warp, m, 1);
         if (rows_valid) {
           const uint32_t pcol = spcol + 64u + (uint32_t)b * 32u;
+          // attendable keys of the block: keys 0..T-1, key T = the zero-attention key, nothing beyond. MASKED: minus
+          // the caller's padding mask, as a bit word (the zero key stays attendable: torch pads the mask with False)
           const int key0 = kb * 64;
-          const bool full = key0 + 64 <= p.T + 1;
+          unsigned long long kw = 0ull;
+          bool full;
+          if constexpr (MASKED) {
+            kw = __ldg(kmrow + kb);
+            full = kw == ~0ull;
+          } else {
+            full = key0 + 64 <= p.T + 1;
+          }
+          auto attendable = [&](int j) -> bool {   // j: key inside the block (compile-time after unrolling)
+            if constexpr (MASKED) return ((kw >> j) & 1ull) != 0ull;
+            else return key0 + j <= p.T;
+          };
           uint32_t sv[64];
           tmem_ld_32x32b_x32(spcol, sv);
           tmem_ld_32x32b_x32(spcol + 32u, sv + 32);
@@ -438,9 +458,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           // below a maximum that is >= 0)
           auto raise_max = [&]() -> float {
             float m4[4] = {m_used, 0.f, 0.f, 0.f};
+            if (!MASKED || full) {   // (keys beyond T are zero rows of K: logit 0, harmless below a maximum >= 0)
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])));
+              for (int i = 0; i < 32; ++i)
+                m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])));
+            } else {   // masked keys must not set the reference: everything attendable could underflow below them
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float a0 = attendable(2 * i) ? __uint_as_float(sv[2 * i]) : 0.f;
+                const float a1 = attendable(2 * i + 1) ? __uint_as_float(sv[2 * i + 1]) : 0.f;
+                m4[i & 3] = fmaxf(m4[i & 3], fmaxf(a0, a1));
+              }
+            }
             const float bm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             const float f = ex2_approx((m_used - bm) * c);
             m_used = bm;
@@ -462,18 +491,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                   s1 += e1;
                   pk[i] = pack_bf16x2(e0, e1);
                 }
-              } else if (key0 + 16 * j <= p.T) {   // key T is the zero-attention key, keys > T are padding
+              } else if (MASKED ? (((uint32_t)(kw >> (16 * j)) & 0xffffu) != 0u) : (key0 + 16 * j <= p.T)) {
+                // some keys of the 16-key group attendable
 #pragma unroll
                 for (int i = 8 * j; i < 8 * j + 8; ++i) {
                   float e0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -moff));
                   float e1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -moff));
-                  e0 = (key0 + 2 * i <= p.T) ? e0 : 0.f;
-                  e1 = (key0 + 2 * i + 1 <= p.T) ? e1 : 0.f;
+                  e0 = attendable(2 * i) ? e0 : 0.f;
+                  e1 = attendable(2 * i + 1) ? e1 : 0.f;
                   s0 += e0;
                   s1 += e1;
                   pk[i] = pack_bf16x2(e0, e1);
                 }
-              } else {   // a 16-key group entirely past T: no MUFU work
+              } else {   // a 16-key group without attendable keys (past T, or padding): no MUFU work
 #pragma unroll
                 for (int i = 8 * j; i < 8 * j + 8; ++i) pk[i] = 0u;
               }
@@ -544,7 +574,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 template <int HD>
-static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk,
+static int launch_attention_t(const unsigned long long* kmask, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk,
                               const __nv_bfloat16* vt, int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H,
                               int kv_xor, int rev, cudaStream_t stream) {
   using C = AttnCfg<HD>;
@@ -575,6 +605,7 @@ static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat
   p.kv_xor = kv_xor;
   p.rev = rev;
   p.out = out;
+  p.kmask = kmask;
   p.ldo = ldo;
   p.wide_store = ((reinterpret_cast<uintptr_t>(out) & 31) == 0 && (ldo % 16) == 0) ? 1 : 0;
   {
@@ -589,7 +620,8 @@ static int launch_attention_t(const __nv_bfloat16* q, int ldq, const __nv_bfloat
   p.tau_raw = 8.0f / p.scale_log2;
   const int items = S * H;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  attention_kernel<HD><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  if (kmask != nullptr) attention_kernel<HD, true><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  else attention_kernel<HD, false><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -603,23 +635,52 @@ extern "C" int mmdm_debug_attn_trace(long long* dev_ptr) {
 int attention_init() {   // kernel attributes are per device
   static PerDeviceFlag attr;
   if (!attr.first()) return 0;
-  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)AttnCfg<128>::SMEM_BYTES));
-  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)AttnCfg<64>::SMEM_BYTES));
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)AttnCfg<128>::SMEM_BYTES));
+  MMDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)AttnCfg<64>::SMEM_BYTES));
+  return 0;
+}
+
+// one thread per (sequence, word): 64 mask values -> bits; bit T = zero-attention key, nothing beyond
+__global__ void build_key_mask_kernel(const float* __restrict__ mask, int rows, int nseq, int T, int persons, int NB,
+                                      unsigned long long* __restrict__ words) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseq * NB) return;
+  const int s = i / NB, kb = i - s * NB;
+  const float* row = mask + (size_t)((s / persons) % rows) * T;
+  unsigned long long w = 0ull;
+  for (int j = 0; j < 64; ++j) {
+    const int key = kb * 64 + j;
+    const bool on = key < T ? row[key] > 0.5f : key == T;
+    w |= (unsigned long long)on << j;
+  }
+  words[i] = w;
+}
+
+int build_key_mask(const float* mask, int rows, int nseq, int T, int persons, unsigned long long* words,
+                   cudaStream_t stream) {
+  MMDM_REQUIRE(mask && words && rows >= 1 && nseq >= 1 && T >= 1 && persons >= 1, "build_key_mask: bad argument");
+  const int NB = (T + 1 + 63) / 64, n = nseq * NB;
+  build_key_mask_kernel<<<(n + 127) / 128, 128, 0, stream>>>(mask, rows, nseq, T, persons, NB, words);
+  MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
                      int Tp, __nv_bfloat16* out, int ldo, int S, int T, int H, int hd, int kv_xor,
-                     cudaStream_t stream, int rev) {
+                     cudaStream_t stream, int rev, const unsigned long long* key_mask) {
   MMDM_REQUIRE(attention_init() == 0, "attention: kernel attribute setup failed");
   MMDM_REQUIRE(T >= 1 && S >= 1 && H >= 1, "attention: empty problem S=%d T=%d H=%d", S, T, H);
   MMDM_REQUIRE(hd == 64 || hd == 128, "attention: head dim %d not in {64,128}", hd);
   MMDM_REQUIRE((ldq % 8) == 0 && (ldk % 8) == 0 && (Tp % 8) == 0 && (ldo % 8) == 0 && Tp >= T,
                "attention: pitches must be multiples of 8 elements");
-  if (hd == 128) return launch_attention_t<128>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, rev, stream);
-  return launch_attention_t<64>(q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, rev, stream);
+  if (hd == 128) return launch_attention_t<128>(key_mask, q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, rev, stream);
+  return launch_attention_t<64>(key_mask, q, ldq, k, ldk, vt, Tp, out, ldo, S, T, H, kv_xor, rev, stream);
 }
 
 }  // namespace mmdm

@@ -103,6 +103,8 @@ struct Workspace {
   float* final = nullptr;               // result of the last step (B, T, 524); copied to the caller's buffer
   int* step = nullptr;
   int* ts_idx = nullptr;    // (nsteps) int: timestep_map on device
+  unsigned long long* kmask1 = nullptr;   // key-padding words, one sequence per batch row   [Bx][NB]
+  unsigned long long* kmask2 = nullptr;   // ... two sequences (persons) per batch row        [2 Bx][NB]
 };
 
 }  // namespace mmdm
@@ -113,6 +115,8 @@ struct mmdm_handle {
   int device = 0;            // ordinal the handle was created on; every entry point makes it current
   std::string last_error;    // message of the last failed call on this handle (mmdm_last_error(h))
   int step_host = -1;        // host mirror of the device-side DDIM index (-1: no state set)
+  bool mask_on = false;      // key-padding words in ws.kmask1 / kmask2 are live (mmdm_set_key_mask)
+  int seq_persons = 2;       // sequences per batch row of the network pass being enqueued (selects kmask1 / kmask2)
   bool cond_ready = false;   // the text-embedding tables hold the sampler's condition (mmdm_set_condition); the
                              // explicit-batch entry points (mixer / denoiser forward) and a re-bind overwrite them
   mmdm_config cfg;
@@ -127,7 +131,7 @@ struct mmdm_handle {
   // One captured step graph per (workspace, batch, frames, history buffers): a caller that alternates between motion
   // lengths (the evaluation generators: T = motion_lens[0] per prompt) re-binds the workspace without re-capturing.
   struct GraphEntry {
-    void* ws_base; int B, T; float *h1, *h2;
+    void* ws_base; int B, T; float *h1, *h2; bool masked;
     cudaGraphExec_t exec; long long step_launches; long long stamp;
   };
   std::vector<GraphEntry> graphs;
@@ -231,6 +235,11 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
   ws.final = c.take<float>((size_t)B * T * nf2);
   ws.step = c.take<int>(4);
   ws.ts_idx = c.take<int>(h->cfg.nsteps);
+  {
+    const size_t NB = (size_t)(T + 1 + 63) / 64;
+    ws.kmask1 = c.take<unsigned long long>((size_t)Bx * NB);
+    ws.kmask2 = c.take<unsigned long long>((size_t)2 * Bx * NB);
+  }
   if (w) *w = ws;
   if (total) *total = align_up(c.off, 1024);
 }
@@ -308,8 +317,9 @@ static int attention(mmdm_handle* h, const Net& n, int S, int T, int kv_xor, cud
   Workspace& ws = h->ws;
   const int D = n.w.D;
   Scope sc(h, "attention", st, 4.0 * S * n.w.H * (double)T * (T + 1) * n.hd());
+  const unsigned long long* km = h->mask_on ? (h->seq_persons == 2 ? ws.kmask2 : ws.kmask1) : nullptr;
   return launch_attention(ws.qk, 2 * D, ws.qk + D, 2 * D, ws.vt, h->Tp, ws.att, D, S, T, n.w.H, n.hd(), kv_xor, st,
-                          next_dir(h));
+                          next_dir(h), km);
 }
 
 static int ln(mmdm_handle* h, const float* src, int M, int D, int T, const float* m0, int ld0, bf16* o0,
@@ -385,6 +395,7 @@ static int run_denoiser(mmdm_handle* h, int ni, const float* x, int Bu, int dup,
   const int Bx = dup ? 2 * Bu : Bu;
   const int S = Bx * persons;
   const int Mu = Bu * persons * T, M = S * T;
+  h->seq_persons = persons;
   MMDM_TRY(run_conditioning(h, ni, S, temb, step_ptr, st));
   {
     Scope sc(h, "pack_state", st);
@@ -441,6 +452,9 @@ static int run_mixer_nets(mmdm_handle* h, const float* x1, const float* x2, int 
   const int T = h->T, nf = h->cfg.nfeats, kpad = h->cfg.kpad;
   const int Bx = dup ? 2 * Bu : Bu, S = 2 * Bx, M = S * T;
   const int Bt = Bu;
+  MMDM_REQUIRE(!(h->mask_on && h->cfg.align),
+               "frame masks need Mixer(align=False): the reference's masked trajectory alignment does not run "
+               "(utils/alignment.py:86-89 indexes one frame per batch row with a (B, 2) length tensor)");
   // individual denoiser on both persons (text slices: cond1_1, cond1_2)
   MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bt, dup, 2, 0, st));
   MMDM_TRY(run_denoiser(h, 0, x1, Bu, dup, 2, temb[0], step_ptr, ws.out1, h->cfg.std1, h->cfg.mean1, st, x_pitch));
@@ -455,6 +469,7 @@ static int run_mixer_nets(mmdm_handle* h, const float* x1, const float* x2, int 
   }
   Net& n = h->net[2];
   const int D = n.w.D;
+  h->seq_persons = 2;
   MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bt, dup, 3, 1, st));
   MMDM_TRY(run_conditioning(h, 2, S, temb[2], step_ptr, st));
   GemmEpi ee;
@@ -655,6 +670,7 @@ int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T) {
     h->ws_base = ws; h->ws_bytes = bytes; h->B = B; h->T = T; h->Bx = 2 * B; h->Tp = (T + 7) / 8 * 8;
     h->temb_ready = false;
     h->cond_ready = false;
+    h->mask_on = false;
     return 0;
   });
 }
@@ -670,6 +686,23 @@ int mmdm_set_condition(mmdm_handle* h, const float* cond, void* stream) {
     MMDM_TRY(run_text(h, 1, cond, ld, h->B, COL_INTER, 3, st));
     MMDM_TRY(run_text(h, 2, cond, ld, h->B, COL_MIX, 3, st));
     h->cond_ready = true;
+    return 0;
+  });
+}
+
+int mmdm_set_key_mask(mmdm_handle* h, const float* mask, int rows, void* stream) {
+  return guarded(h, [&]() -> int {
+    MMDM_REQUIRE(h && h->ws_base, "mmdm_set_key_mask: handle not bound");
+    if (mask == nullptr) {
+      h->mask_on = false;
+      return 0;
+    }
+    MMDM_REQUIRE(rows >= 1 && rows <= h->Bx, "mmdm_set_key_mask: %d mask rows for a workspace of %d batch rows", rows, h->Bx);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MMDM_TRY(build_key_mask(mask, rows, h->Bx, h->T, 1, h->ws.kmask1, st));
+    MMDM_TRY(build_key_mask(mask, rows, 2 * h->Bx, h->T, 2, h->ws.kmask2, st));
+    h->launches += 2;
+    h->mask_on = true;
     return 0;
   });
 }
@@ -743,7 +776,9 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
     if (use_graph && !h->prof.on && !eval_hist) {
       mmdm_handle::GraphEntry* ge = nullptr;
       for (auto& g : h->graphs)
-        if (g.ws_base == h->ws_base && g.B == h->B && g.T == h->T && g.h1 == hist_i1 && g.h2 == hist_i2) ge = &g;
+        if (g.ws_base == h->ws_base && g.B == h->B && g.T == h->T && g.h1 == hist_i1 && g.h2 == hist_i2 &&
+            g.masked == h->mask_on)
+          ge = &g;
       if (!ge) {
         if (h->graphs.size() >= kMaxCachedGraphs) {   // evict the least recently used entry
           size_t lru = 0;
@@ -768,7 +803,7 @@ int mmdm_sample(mmdm_handle* h, const float* cond, const float* noise, float* ou
         cudaGraphExec_t exec = nullptr;
         MMDM_CHECK_CUDA(cudaGraphInstantiate(&exec, g, 0));
         cudaGraphDestroy(g);
-        h->graphs.push_back({h->ws_base, h->B, h->T, hist_i1, hist_i2, exec, step_launches, 0});
+        h->graphs.push_back({h->ws_base, h->B, h->T, hist_i1, hist_i2, h->mask_on, exec, step_launches, 0});
         h->graph_captures++;
         ge = &h->graphs.back();
       }

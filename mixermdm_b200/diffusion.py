@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from . import schedule
+from .modules import _check_mask
 from .schedule import get_named_beta_schedule, space_timesteps  # noqa: F401  (re-exported, reference names)
 
 
@@ -78,8 +79,7 @@ class MixerDiffusion:
         if clip_denoised or denoised_fn is not None or cond_fn is not None or cond_fn_with_grad or randomize_class:
             raise NotImplementedError("clip_denoised=False, no denoised_fn/cond_fn: the MixerMDM inference path")
         model_kwargs = model_kwargs or {}
-        if model_kwargs.get("mask") is not None:
-            raise NotImplementedError("mask=None is the only masking the MixerMDM sampler uses")
+        mask = model_kwargs.get("mask")
         cond = model_kwargs["cond"]
         if device is None:
             device = cond.device if noise is None else noise.device
@@ -90,8 +90,9 @@ class MixerDiffusion:
         var = {ModelVarType.FIXED_SMALL: "fixed_small", ModelVarType.FIXED_LARGE: "fixed_large"}.get(self.model_var_type)
         if var is None:
             raise NotImplementedError("MixerDiffusion.p_sample_loop: fixed variances only")
-        _, eng = self._engine_for(model, B, T, torch.device(device))
-        return eng.sample_ddpm(cond, noise, step_noise=step_noise, generator=generator, var_type=var)
+        mixer, eng = self._engine_for(model, B, T, torch.device(device))
+        _check_mask(mixer, mask)
+        return eng.sample_ddpm(cond, noise, step_noise=step_noise, generator=generator, var_type=var, mask=mask)
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                          model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None,
@@ -105,8 +106,7 @@ class MixerDiffusion:
         if eta != 0.0 or skip_timesteps or init_image is not None or x_start is not None:
             raise NotImplementedError("eta=0, full schedule, no inpainting: the MixerMDM inference path")
         model_kwargs = model_kwargs or {}
-        if model_kwargs.get("mask") is not None:
-            raise NotImplementedError("mask=None is the only masking the MixerMDM sampler uses")
+        mask = model_kwargs.get("mask")
         cond = model_kwargs["cond"]
         if device is None:
             device = cond.device if noise is None else noise.device
@@ -115,8 +115,9 @@ class MixerDiffusion:
         if noise is None:
             noise = torch.randn(*shape, device=device)
         mixer, eng = self._engine_for(model, B, T, torch.device(device))
+        _check_mask(mixer, mask)
         want_out = (mixer.mode == "eval")
-        res = eng.sample(cond, noise, store_influence=mixer.store_influence, store_outputs=want_out)
+        res = eng.sample(cond, noise, store_influence=mixer.store_influence, store_outputs=want_out, mask=mask)
         if not (mixer.store_influence or want_out):
             return res
         res = list(res)

@@ -232,6 +232,19 @@ class _Handle:
         """invoke handle entry point `name`(h, *args); the C side makes the handle's device current for the call"""
         check(getattr(self.lib, name)(self.h, *args), name, self.h)
 
+    def set_key_mask(self, mask, frames=None):
+        """frame mask for the attention layers of the following calls (reference: the `mask` argument of
+        in2INDenoiser / Influence, (B, T, P) float with 1 = real frame; they read mask[..., 0]). None clears it."""
+        if mask is None:
+            self.call("mmdm_set_key_mask", None, 0, self.stream())
+            return
+        m = mask[..., 0] if mask.dim() == 3 else mask
+        if m.dim() != 2 or (frames is not None and m.shape[1] != frames):
+            raise ValueError(f"mask: expected (B, {frames}) or (B, {frames}, P), got {tuple(mask.shape)}")
+        m = m.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.call("mmdm_set_key_mask", ptr(m), int(m.shape[0]), self.stream())
+        self._mask_keep = m   # (the words are built on the stream: keep the source alive until then)
+
     def stream(self):
         """the caller's current torch stream ON THE HANDLE'S DEVICE (not on whatever device happens to be current)"""
         return cur_stream(self.device)
@@ -292,7 +305,7 @@ def _expect(t, shape, name):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
 
 
-def _denoiser_call(hd, which, x, timesteps, cond):
+def _denoiser_call(hd, which, x, timesteps, cond, mask=None):
     """in2INDenoiser.forward through the handle. Like the reference (models/in2in.py:414-424, slices of cond) a cond
     wider than the network's 768 / 2304 columns is accepted and its leading columns are used."""
     Bx, T = x.shape[0], x.shape[1]
@@ -305,6 +318,7 @@ def _denoiser_call(hd, which, x, timesteps, cond):
     x, cond = _f32c(x, hd.device), _f32c(cond[:, :ncond], hd.device)
     ts = timesteps.detach().to(device=hd.device, dtype=torch.int64).contiguous()
     out = torch.empty_like(x)
+    hd.set_key_mask(mask, T)
     hd.call("mmdm_denoiser_forward", which, ptr(x), ptr(ts), ptr(cond), ptr(out), Bx, hd.stream())
     return out
 
@@ -422,7 +436,7 @@ class MixerEngine:
             _expect(n, (self.hd.B, self.hd.T, 2 * NFEATS), "noise")
         self.hd.call("mmdm_add_state_noise", ptr(noise1), ptr(noise2), C.c_float(float(scale)), self.hd.stream())
 
-    def sample_ddpm(self, cond, noise, step_noise=None, generator=None, var_type="fixed_small"):
+    def sample_ddpm(self, cond, noise, step_noise=None, generator=None, var_type="fixed_small", mask=None):
         """whole ancestral (DDPM) loop: the fused step with posterior-mean coefficients + sigma_t z after every step but
         the last. step_noise: optional (nsteps - 1, B, T, 524) tensor of the z's (index i is used after DDIM-table
         index nsteps - 1 - i); otherwise drawn with torch.randn(generator=...). Both state streams receive the same z,
@@ -436,6 +450,7 @@ class MixerEngine:
         self.set_sampler("ddpm", var_type)
         try:
             noise = _f32c(noise, self.device)
+            self.hd.set_key_mask(mask, T)
             self.set_condition(cond)
             self.set_state(noise, noise, self.nsteps - 1)
             out = torch.empty(B, T, 2 * NFEATS, device=self.device)
@@ -450,7 +465,7 @@ class MixerEngine:
             self.set_sampler(prev[0], prev[1] or "fixed_small")
         return out
 
-    def sample(self, cond, noise, out=None, store_influence=False, use_graph=True, store_outputs=False):
+    def sample(self, cond, noise, out=None, store_influence=False, use_graph=True, store_outputs=False, mask=None):
         """whole DDIM loop; cond (B,6144), noise (B,T,524) device fp32 -> (B,T,524) real-space prediction.
         store_influence: also return the per-step expanded weights, 2 x (nsteps, 2B, T, 262).
         store_outputs:   also return out1 / out2 / out_influenced of every step, 3 x (nsteps, 2B, T, 524)."""
@@ -472,6 +487,7 @@ class MixerEngine:
             h2 = torch.empty(self.nsteps, 2 * B, T, NFEATS, device=self.device)
         if store_outputs:
             o1, o2, om = [torch.empty(self.nsteps, 2 * B, T, 2 * NFEATS, device=self.device) for _ in range(3)]
+        self.hd.set_key_mask(mask, T)
         self.hd.call("mmdm_sample", ptr(cond), ptr(noise), ptr(out), ptr(h1), ptr(h2), ptr(o1), ptr(o2), ptr(om),
                      int(use_graph), self.hd.stream())
         res = [out]
@@ -483,7 +499,7 @@ class MixerEngine:
 
     # -- module-level entry points ------------------------------------------------------------------
     def mixer_forward(self, x1, x2, timesteps, cond, want_aux=False, want_influence=False, cfg_combine=False,
-                      cfg_scale=None):
+                      cfg_scale=None, mask=None):
         Bx, T = x1.shape[0], x1.shape[1]
         _expect(x1, (Bx, T, 2 * NFEATS), "x1")
         _expect(x2, (Bx, T, 2 * NFEATS), "x2")
@@ -497,27 +513,28 @@ class MixerEngine:
         o2 = torch.empty(Bx, T, 2 * NFEATS, device=self.device) if want_aux else None
         w1 = torch.empty(Bx, T, NFEATS, device=self.device) if want_influence else None
         w2 = torch.empty(Bx, T, NFEATS, device=self.device) if want_influence else None
+        self.hd.set_key_mask(mask, T)
         self.hd.call("mmdm_mixer_forward", ptr(x1), ptr(x2), ptr(ts), ptr(cond), ptr(out), ptr(o1), ptr(o2), ptr(w1),
                      ptr(w2), Bx, int(cfg_combine), C.c_float(self.cfg_scale if cfg_scale is None else cfg_scale),
                      self.hd.stream())
         return out, o1, o2, w1, w2
 
-    def cfg_forward(self, x, x2, timesteps, cond, scale, store_influence=False, owner=None):
+    def cfg_forward(self, x, x2, timesteps, cond, scale, store_influence=False, owner=None, mask=None):
         """ClassifierFreeSampleModelX2.forward: doubled batch, zero condition for the second half, guidance."""
         xx = torch.cat([x, x], 0)
         xx2 = torch.cat([x2, x2], 0)
         tt = torch.cat([timesteps, timesteps], 0)
         cc = torch.cat([cond, torch.zeros_like(cond)], 0)
         out, _, _, w1, w2 = self.mixer_forward(xx, xx2, tt, cc, want_influence=store_influence, cfg_combine=True,
-                                               cfg_scale=scale)
+                                               cfg_scale=scale, mask=mask)   # (mask rows serve both halves: bx % B)
         if store_influence and owner is not None:
             from .modules import history_view
             owner.history_influence_i1.append(history_view(w1, self.mixing_mode))
             owner.history_influence_i2.append(history_view(w2, self.mixing_mode))
         return out
 
-    def denoiser_forward(self, which, x, timesteps, cond):
-        return _denoiser_call(self.hd, which, x, timesteps, cond)
+    def denoiser_forward(self, which, x, timesteps, cond, mask=None):
+        return _denoiser_call(self.hd, which, x, timesteps, cond, mask)
 
 
 class StandaloneDenoiser:
@@ -547,9 +564,9 @@ class StandaloneDenoiser:
     def matches(self, den, x):
         return canonical_device(x.device) == self.device and weights_fingerprint(den) == self.fingerprint
 
-    def forward(self, x, timesteps, cond):
+    def forward(self, x, timesteps, cond, mask=None):
         Bx, T = x.shape[0], x.shape[1]
         if Bx > self.rows or T != self.T:
             self.hd.bind((Bx + 1) // 2, T)
             self.rows, self.T = 2 * ((Bx + 1) // 2), T
-        return _denoiser_call(self.hd, self.kind, x, timesteps, cond)
+        return _denoiser_call(self.hd, self.kind, x, timesteps, cond, mask)

@@ -149,12 +149,10 @@ class in2INDenoiser(nn.Module):
     def forward(self, x, timesteps, mask=None, cond=None):
         """x: (B,T,262) [individual] or (B,T,524) [interaction]; timesteps: (B,) original-scale indices into the
         PE table; cond: (B,768) / (B,2304). Returns the normalised-space x0 prediction, same shape as x."""
-        if mask is not None:
-            raise NotImplementedError("key-padding masks are not part of the MixerMDM sampling path (mask=None)")
         if self._standalone is None or not self._standalone.matches(self, x):
             self._standalone = None   # parameters changed (load_state_dict, in-place update, .to()): repack
             self._standalone = _engine.StandaloneDenoiser(self, x)
-        return self._standalone.forward(x, timesteps, cond)
+        return self._standalone.forward(x, timesteps, cond, mask)   # mask: (B, T, P) float, mask[..., 0] > 0.5 = real frame
 
     def __getstate__(self):   # the engine holds ctypes pointers: copies / pickles rebuild it on first use
         d = dict(self.__dict__)
@@ -248,12 +246,11 @@ class Mixer(nn.Module):
     def forward(self, x1, timesteps, cond=None, mask=None, x2=None):
         """x1/x2: (Be,T,524) state in individual / interaction space, timesteps (Be,), cond (Be,6144).
         eval modes return out_influenced (Be,T,524); train mode returns (out_influenced, out1, out2)."""
-        if mask is not None:
-            raise NotImplementedError("mask=None is the only masking the MixerMDM sampler uses")
+        _check_mask(self, mask)
         eng = self.engine(x1.shape[0], x1.shape[1], x1.device)
         out, out1, out2, w1, w2 = eng.mixer_forward(x1, x2, timesteps, cond,
                                                     want_aux=(self.mode != "eval_intermediate"),
-                                                    want_influence=self.store_influence)
+                                                    want_influence=self.store_influence, mask=mask)
         if self.store_influence:
             self.history_influence_i1.append(history_view(w1, self.mixing_mode))
             self.history_influence_i2.append(history_view(w2, self.mixing_mode))
@@ -266,6 +263,16 @@ class Mixer(nn.Module):
         return out
 
 
+def _check_mask(mixer, mask):
+    """Frame masks reach the three networks' attention layers (in2in.py:433-435, influence.py:107-116). With
+    Mixer(align=True) the reference hands the (B, T, 2) mask to align_trajectories, which builds a (B, 2) length tensor
+    and indexes one frame per batch row with it (utils/alignment.py:86-89): a shape error for B != 2. There is nothing
+    to be identical to, so that combination raises here too."""
+    if mask is not None and mixer.align:
+        raise NotImplementedError("mask with Mixer(align=True): the reference's masked trajectory alignment does not run "
+                                  "(utils/alignment.py:86-89); use align=False or mask=None")
+
+
 class ClassifierFreeSampleModelX2(nn.Module):
     """CFG wrapper for the two-stream sampler (reference models/utils/cfg_sampler.py:31-56):
     s * model(cond) + (1 - s) * model(cond = 0) on a doubled batch."""
@@ -276,9 +283,8 @@ class ClassifierFreeSampleModelX2(nn.Module):
         self.s = cfg_scale
 
     def forward(self, x, x2, timesteps, cond=None, mask=None):
-        if mask is not None:
-            raise NotImplementedError("mask=None is the only masking the MixerMDM sampler uses")
+        _check_mask(self.model, mask)
         B = x.shape[0]
         eng = self.model.engine(2 * B, x.shape[1], x.device)
         return eng.cfg_forward(x, x2, timesteps, cond, self.s, store_influence=self.model.store_influence,
-                               owner=self.model)
+                               owner=self.model, mask=mask)

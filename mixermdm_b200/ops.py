@@ -63,13 +63,24 @@ def ln_modulate(h, T, mod0, out0=None, mod1=None, out1=None):
     return (out0, out1) if mod1 is not None else out0
 
 
-def attention(q, k, vt, out, S, T, H, hd, kv_xor=0):
-    """q/k: 2-D bf16 views (rows = s*T+t) whose columns are the H*hd projected features; vt: (S*H, hd, Tp)."""
+def attention(q, k, vt, out, S, T, H, hd, kv_xor=0, key_mask=None, persons=1):
+    """q/k: 2-D bf16 views (rows = s*T+t) whose columns are the H*hd projected features; vt: (S*H, hd, Tp).
+    key_mask: optional (rows, T) float tensor, > 0.5 = key attendable; sequence s reads row (s // persons) % rows."""
     lib = _lib.load()
     with torch.cuda.device(q.device):
-        check(lib.mmdm_attention(ptr(q), C.c_int(q.stride(0)), ptr(k), C.c_int(k.stride(0)), ptr(vt),
-                                 C.c_int(vt.stride(1)), ptr(out), C.c_int(out.stride(0)), S, T, H, hd, kv_xor,
-                                 cur_stream()), "mmdm_attention")
+        if key_mask is None:
+            check(lib.mmdm_attention(ptr(q), C.c_int(q.stride(0)), ptr(k), C.c_int(k.stride(0)), ptr(vt),
+                                     C.c_int(vt.stride(1)), ptr(out), C.c_int(out.stride(0)), S, T, H, hd, kv_xor,
+                                     cur_stream()), "mmdm_attention")
+            return out
+        m = key_mask.detach().to(device=q.device, dtype=torch.float32).contiguous()
+        assert m.dim() == 2 and m.shape[1] == T
+        words = torch.empty(S, (T + 64) // 64, dtype=torch.int64, device=q.device)
+        check(lib.mmdm_build_key_mask(ptr(m), int(m.shape[0]), S, T, persons, ptr(words), cur_stream()),
+              "mmdm_build_key_mask")
+        check(lib.mmdm_attention_masked(ptr(q), C.c_int(q.stride(0)), ptr(k), C.c_int(k.stride(0)), ptr(vt),
+                                        C.c_int(vt.stride(1)), ptr(out), C.c_int(out.stride(0)), S, T, H, hd, kv_xor,
+                                        ptr(words), cur_stream()), "mmdm_attention_masked")
     return out
 
 

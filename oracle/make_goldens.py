@@ -109,6 +109,46 @@ def text():
     print("text:", cond.shape, float(cond.abs().mean()))
 
 
+MASK_LENS = (24, 15)
+
+
+def masked():
+    """tests/golden/reference_masked.npz: the three networks with a frame mask (generate_src_mask's (B, T, 2) layout,
+    models/mixermdm.py:358-372): both denoisers alone and Mixer.forward with align=False in modes 2 and 4 (with
+    align=True the reference's masked trajectory alignment raises, utils/alignment.py:86-89)."""
+    dims = synth.SMALL_DIMS
+    cond, noise = synth.inputs(B, T, seed=0)
+    t_mid = torch.full((B,), 500, dtype=torch.long)
+    x1, x2 = noise, 0.9 * noise.flip(0)
+    mask = torch.ones(B, T, 2)
+    for i, n in enumerate(MASK_LENS):
+        mask[i, n:] = 0
+    arrays = {"mask": mask.numpy()}
+    for mode in (2, 4):
+        mix, _, _ = ref_harness.build_reference(dims, mixing_mode=mode, store_influence=True)
+        mix.load_state_dict(synth.synthetic_state_dict(mix.state_dict(), seed=0), strict=True)
+        mix.align = False
+        with torch.no_grad(), ref_harness.reference_env():
+            arrays[f"mixer_out_mode{mode}"] = mix(x1, t_mid, cond=cond, mask=mask, x2=x2).numpy()
+            arrays[f"mixer_w1_mode{mode}"] = mix.history_influence_i1[-1].expand(B, T, 262).numpy().copy()
+            if mode == 4:
+                arrays["den_individual"] = mix.denoiser1(x1[..., :262], t_mid, mask=mask, cond=cond[:, 2304:3072]).numpy()
+                arrays["den_interaction"] = mix.denoiser2(x2, t_mid, mask=mask, cond=cond[:, :2304]).numpy()
+                try:
+                    mix.align = True
+                    mix(torch.cat([x1, x1]), torch.cat([t_mid, t_mid]), cond=torch.cat([cond, cond]),
+                        mask=torch.cat([mask, mask]), x2=torch.cat([x2, x2]))
+                    arrays["align_with_mask_runs"] = np.array(1)
+                except Exception as e:   # noqa: BLE001  (recorded: the reason masks need align=False)
+                    arrays["align_with_mask_runs"] = np.array(0)
+                    print("reference Mixer(align=True) with a mask:", type(e).__name__, str(e)[:120])
+    np.savez_compressed(os.path.join(OUT, "reference_masked.npz"), **arrays)
+    with open(os.path.join(OUT, "reference_masked.json"), "w") as f:
+        json.dump({"B": B, "T": T, "dims": dims, "weights_seed": 0, "inputs_seed": 0, "lens": list(MASK_LENS),
+                   "generator": "oracle/make_goldens.py masked()", "torch": torch.__version__}, f, indent=1)
+    print("masked:", sorted(arrays))
+
+
 def schedule_tables():
     """tests/golden/reference_schedule.npz: the posterior tables of the reference's re-spaced diffusion object (the
     DDPM side of GaussianDiffusion.__init__, gaussian_diffusion.py:355-382), float64"""
@@ -123,6 +163,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if "--schedule-only" in sys.argv:
         schedule_tables()
+        return
+    if "--masked-only" in sys.argv:
+        masked()
         return
     if "--chain-only" in sys.argv:
         chain()
@@ -195,6 +238,7 @@ def main():
     chain()
     text()
     schedule_tables()
+    masked()
 
 
 if __name__ == "__main__":

@@ -28,10 +28,11 @@ def ada_ln(sd, pre, h, emb):
     return F.layer_norm(h, (h.shape[-1],), eps=1e-6) * (1 + scale[:, None]) + shift[:, None]
 
 
-def mha_zero_attn(sd, pre, q_in, kv_in, heads):
-    """nn.MultiheadAttention(batch_first, add_zero_attn=True) with no masks (models/utils/layers.py:33-45,74-88;
+def mha_zero_attn(sd, pre, q_in, kv_in, heads, pad=None):
+    """nn.MultiheadAttention(batch_first, add_zero_attn=True) (models/utils/layers.py:33-45,74-88;
     torch F.multi_head_attention_forward): packed in-projection, one extra key/value row of zeros appended
-    AFTER the projection, logits scaled by 1/sqrt(hd), out-projection."""
+    AFTER the projection, logits scaled by 1/sqrt(hd), out-projection. pad: optional key_padding_mask (B, Tk) bool,
+    True = ignore the key; torch pads it with False for the zero key, so a fully padded row attends to that key."""
     w, b = sd[pre + "in_proj_weight"], sd[pre + "in_proj_bias"]
     D = q_in.shape[-1]
     q = F.linear(q_in, w[:D], b[:D])
@@ -46,7 +47,11 @@ def mha_zero_attn(sd, pre, q_in, kv_in, heads):
     zeros = torch.zeros(B, heads, 1, hd, dtype=q.dtype)
     k = torch.cat([k, zeros], dim=2)
     v = torch.cat([v, zeros], dim=2)
-    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1) @ v
+    logits = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    if pad is not None:
+        padz = torch.cat([pad, torch.zeros(B, 1, dtype=torch.bool)], dim=1)
+        logits = logits.masked_fill(padz[:, None, None, :], float("-inf"))
+    att = torch.softmax(logits, dim=-1) @ v
     att = att.transpose(1, 2).reshape(B, Tq, D)
     return F.linear(att, sd[pre + "out_proj.weight"], sd[pre + "out_proj.bias"])
 
@@ -58,15 +63,15 @@ def ffn(sd, pre, h, emb):
     return F.linear(x, sd[pre + "linear2.weight"], sd[pre + "linear2.bias"])
 
 
-def block(sd, pre, x, y, emb_sa, emb_ca, emb_ffn, heads, cross):
+def block(sd, pre, x, y, emb_sa, emb_ca, emb_ffn, heads, cross, pad=None):
     """models/utils/blocks.py:49-63 and models/utils/influence.py:36-48 (they differ only in which embedding
     feeds the FFN's AdaLN)"""
     xs = ada_ln(sd, pre + "sa_block.norm.", x, emb_sa)
-    h = x + mha_zero_attn(sd, pre + "sa_block.attention.", xs, xs, heads)
+    h = x + mha_zero_attn(sd, pre + "sa_block.attention.", xs, xs, heads, pad)
     if cross:
         qn = ada_ln(sd, pre + "ca_block.norm.", h, emb_ca)
         kn = ada_ln(sd, pre + "ca_block.xf_norm.", y, emb_ca)
-        h = h + mha_zero_attn(sd, pre + "ca_block.attention.", qn, kn, heads)
+        h = h + mha_zero_attn(sd, pre + "ca_block.attention.", qn, kn, heads, pad)
     return h + ffn(sd, pre + "ffn.", h, emb_ffn)
 
 
@@ -81,9 +86,15 @@ def n_layers(sd, pre):
     return 1 + max(int(k[len(pre + "blocks."):].split(".")[0]) for k in sd if k.startswith(pre + "blocks."))
 
 
-def denoiser(sd, pre, mode, x, t, cond, heads):
+def _pad_of(mask):
+    """models/in2in.py:410-411,433-435 / influence.py:107-116: mask (B, T, P) float, frame kept where mask[..., 0] > 0.5"""
+    return None if mask is None else ~(mask[..., 0] > 0.5)
+
+
+def denoiser(sd, pre, mode, x, t, cond, heads, mask=None):
     """models/in2in.py:401-462 — both streams read the PREVIOUS layer's states; weights shared between streams"""
     T = x.shape[1]
+    pad = _pad_of(mask)
     te = time_embed(sd, pre, t)
     text = lambda c: F.linear(c, sd[pre + "text_embed.weight"], sd[pre + "text_embed.bias"])  # noqa: E731
     pe = sd[pre + "sequence_pos_encoder.pe"][:T]
@@ -93,7 +104,7 @@ def denoiser(sd, pre, mode, x, t, cond, heads):
         e1 = te + text(cond[:, :768])
         h = embed(x[..., :NF])
         for l in range(L):
-            h = block(sd, f"{pre}blocks.{l}.", h, None, e1, None, e1, heads, cross=False)
+            h = block(sd, f"{pre}blocks.{l}.", h, None, e1, None, e1, heads, cross=False, pad=pad)
         return F.linear(h, sd[pre + "out.linear.weight"], sd[pre + "out.linear.bias"])
     e = te + text(cond[:, :768])
     e1 = te + text(cond[:, 768:1536])
@@ -101,18 +112,19 @@ def denoiser(sd, pre, mode, x, t, cond, heads):
     ha, hb = embed(x[..., :NF]), embed(x[..., NF:])
     for l in range(L):
         p = f"{pre}blocks.{l}."
-        na = block(sd, p, ha, hb, e1, e, e1, heads, cross=True)
-        nb = block(sd, p, hb, ha, e2, e, e2, heads, cross=True)
+        na = block(sd, p, ha, hb, e1, e, e1, heads, cross=True, pad=pad)
+        nb = block(sd, p, hb, ha, e2, e, e2, heads, cross=True, pad=pad)
         ha, hb = na, nb
     out = lambda h: F.linear(h, sd[pre + "out.linear.weight"], sd[pre + "out.linear.bias"])  # noqa: E731
     return torch.cat([out(ha), out(hb)], dim=-1)
 
 
-def influence(sd, pre, m_i, m_I, cond_i, cond_I, heads, mode):
-    """models/utils/influence.py:93-126"""
+def influence(sd, pre, m_i, m_I, cond_i, cond_I, heads, mode, mask=None):
+    """models/utils/influence.py:93-126 (the time pooling of modes 1 / 3 runs over padded frames too)"""
     h = m_i
+    pad = _pad_of(mask)
     for l in range(n_layers(sd, pre)):
-        h = block(sd, f"{pre}blocks.{l}.", h, m_I, cond_i, cond_I, cond_I, heads, cross=True)
+        h = block(sd, f"{pre}blocks.{l}.", h, m_I, cond_i, cond_I, cond_I, heads, cross=True, pad=pad)
     if mode in (1, 3):
         h = h.mean(dim=1)
     return torch.sigmoid(F.linear(h, sd[pre + "out.weight"], sd[pre + "out.bias"]))
@@ -263,16 +275,20 @@ class Oracle:
         self.mode, self.align, self.center, self.s, self.force = mixing_mode, align, center, cfg_scale, force
         self.sched = sched
 
-    def mixer(self, x1, x2, t, cond, detail=False):
-        """models/mixermdm.py:660-811 (eval_intermediate): returns out_influenced (Be,T,524)"""
+    def mixer(self, x1, x2, t, cond, detail=False, mask=None):
+        """models/mixermdm.py:660-811 (eval_intermediate): returns out_influenced (Be,T,524). mask: (Be, T, 2) float
+        frame mask handed to the three networks; the reference's align_trajectories cannot take it (mask.squeeze().sum(dim=1)
+        is (B, 2) for this mask and is then used as one index per batch row, utils/alignment.py:86-89: shape error for
+        B != 2), so a mask requires align=False here as it does there."""
+        assert mask is None or not self.align
         sd = self.sd
         T = x1.shape[1]
         te = time_embed(sd, "", t)
         tx = lambda c: F.linear(c, sd["text_embed.weight"], sd["text_embed.bias"])  # noqa: E731
         cI, ci1, ci2 = te + tx(cond[:, 3840:4608]), te + tx(cond[:, 4608:5376]), te + tx(cond[:, 5376:6144])
-        o11 = denoiser(sd, "denoiser1.", "individual", x1[..., :NF], t, cond[:, 2304:3072], self.h_den)
-        o12 = denoiser(sd, "denoiser1.", "individual", x1[..., NF:], t, cond[:, 3072:3840], self.h_den)
-        o2 = denoiser(sd, "denoiser2.", "interaction", x2, t, cond[:, :2304], self.h_den)
+        o11 = denoiser(sd, "denoiser1.", "individual", x1[..., :NF], t, cond[:, 2304:3072], self.h_den, mask)
+        o12 = denoiser(sd, "denoiser1.", "individual", x1[..., NF:], t, cond[:, 3072:3840], self.h_den, mask)
+        o2 = denoiser(sd, "denoiser2.", "interaction", x2, t, cond[:, :2304], self.h_den, mask)
         o11, o12 = o11 * self.s1 + self.m1, o12 * self.s1 + self.m1
         o21, o22 = o2[..., :NF] * self.s2 + self.m2, o2[..., NF:] * self.s2 + self.m2
         raw = (torch.cat([o11, o12], -1), torch.cat([o21, o22], -1))
@@ -281,8 +297,8 @@ class Oracle:
             o22, o12 = align_pair(o22, o12)
         pe = sd["sequence_pos_encoder.pe"][:T]
         emb = lambda m: F.linear(m, sd["motion_embed.weight"], sd["motion_embed.bias"]) + pe  # noqa: E731
-        w1 = influence(sd, "influence.", emb(o11), emb(o21), ci1, cI, self.h_mix, self.mode)
-        w2 = influence(sd, "influence.", emb(o12), emb(o22), ci2, cI, self.h_mix, self.mode)
+        w1 = influence(sd, "influence.", emb(o11), emb(o21), ci1, cI, self.h_mix, self.mode, mask)
+        w2 = influence(sd, "influence.", emb(o12), emb(o22), ci2, cI, self.h_mix, self.mode, mask)
         w1, w2 = expand_weights(w1, T, self.mode), expand_weights(w2, T, self.mode)
         if self.force is not None:
             w1, w2 = torch.ones_like(w1) * self.force, torch.ones_like(w2) * self.force
@@ -293,11 +309,12 @@ class Oracle:
                         w2=w2.expand(-1, T, NF) if w2.shape[-1] == 1 else w2, raw1=raw[0], raw2=raw[1])
         return out
 
-    def guided(self, x1, x2, t, cond):
+    def guided(self, x1, x2, t, cond, mask=None):
         """models/utils/cfg_sampler.py:38-56"""
         B = x1.shape[0]
         out = self.mixer(torch.cat([x1, x1]), torch.cat([x2, x2]), torch.cat([t, t]),
-                         torch.cat([cond, torch.zeros_like(cond)]))
+                         torch.cat([cond, torch.zeros_like(cond)]),
+                         mask=None if mask is None else torch.cat([mask, mask]))
         return self.s * out[:B] + (1 - self.s) * out[B:]
 
     def process_xstart(self, g, last):
@@ -311,11 +328,11 @@ class Oracle:
         x2 = torch.cat([(g[..., :NF] - self.m2) / self.s2, (g[..., NF:] - self.m2) / self.s2], dim=-1)
         return x1, x2
 
-    def ddim_step(self, x1, x2, i, cond):
+    def ddim_step(self, x1, x2, i, cond, mask=None):
         """models/utils/gaussian_diffusion.py:1902-1965 with eta = 0; i = index into the re-spaced schedule"""
         B = x1.shape[0]
         t = torch.full((B,), int(self.sched.timestep_map[i]), dtype=torch.long)
-        g = self.guided(x1, x2, t, cond)
+        g = self.guided(x1, x2, t, cond, mask)
         p1, p2 = self.process_xstart(g, last=(i == 0))
         c = self.sched.ddim_coefficients()[i]
         cr, crm1, ca, ce = [torch.tensor(float(v), dtype=torch.float32) for v in c]

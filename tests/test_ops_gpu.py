@@ -112,9 +112,11 @@ def test_ln_modulate(ops, D):
     assert _relerr(o1, r1.reshape(-1, D)) < 4e-3
 
 
-def _ref_attention(q, k, v, scale):
-    # q,k,v: (S,H,T,hd) fp32; zero-attention sink appended (logit 0, value 0)
+def _ref_attention(q, k, v, scale, pad=None):
+    # q,k,v: (S,H,T,hd) fp32; zero-attention sink appended (logit 0, value 0); pad: (S,T) bool, True = key ignored
     logits = torch.einsum("shqd,shkd->shqk", q, k) * scale
+    if pad is not None:
+        logits = logits.masked_fill(pad[:, None, None, :], float("-inf"))
     zeros = torch.zeros(*logits.shape[:-1], 1, device=q.device)
     p = torch.softmax(torch.cat([logits, zeros], -1), -1)[..., :-1]
     return torch.einsum("shqk,shkd->shqd", p, v)
@@ -159,6 +161,53 @@ def test_attention_zero_sink(ops, T, H, hd, S, kv_xor):
     ref = _ref_attention(q, k, v, 1.0 / math.sqrt(hd)).permute(0, 2, 1, 3).reshape(M, D)
     assert _relerr(out, ref) < 1e-2
     assert (out.float() - ref).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize("T,H,hd,S,kv_xor,kind", [(300, 2, 128, 6, 0, "prefix"), (300, 2, 64, 6, 1, "prefix"),
+                                                  (300, 2, 128, 4, 1, "random"), (77, 2, 64, 4, 0, "random"),
+                                                  (400, 1, 128, 4, 0, "prefix"), (130, 2, 64, 4, 0, "edge")])
+def test_attention_key_padding_mask(ops, T, H, hd, S, kv_xor, kind):
+    """key_padding_mask of nn.MultiheadAttention(add_zero_attn=True) (reference models/utils/layers.py:36-44): masked
+    keys get no weight, the zero-attention key always does - so a row whose keys are all masked returns exactly 0.
+    Masked keys carry large logits here: they must neither leak nor set the softmax reference. Two sequences (persons)
+    share a mask row, as in the engine."""
+    D = H * hd
+    Tp = (T + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.randn(S, T, H, hd, device="cuda", generator=g).to(torch.bfloat16)
+    k = torch.randn(S, T, H, hd, device="cuda", generator=g).to(torch.bfloat16)
+    v = torch.randn(S, T, H, hd, device="cuda", generator=g).to(torch.bfloat16)
+    rows = S // 2
+    keep = torch.ones(rows, T, device="cuda")
+    if kind == "prefix":
+        lens = [T, 1, T // 2, 65, 0, 64][:rows]
+        for r, n in enumerate(lens):
+            keep[r, n:] = 0
+    elif kind == "random":
+        keep = (torch.rand(rows, T, device="cuda", generator=g) > 0.4).float()
+        keep[0] = 0                      # everything masked: only the zero key is left
+    else:
+        keep[0, 63:65] = 0               # holes across a 64-key block boundary
+        keep[1, :64] = 0                 # the whole first block masked (it normally sets the running maximum)
+    pad_rows = ~(keep > 0.5)
+    pad = pad_rows.repeat_interleave(2, dim=0)            # sequence s -> mask row s // 2
+    k = torch.where(pad[:, :, None, None], 6.0 * k.float(), k.float()).to(torch.bfloat16)   # masked keys: big logits
+    qk = torch.cat([q.reshape(S * T, D), k.reshape(S * T, D)], 1).contiguous()
+    vt = torch.zeros(S * H, hd, Tp, dtype=torch.bfloat16, device="cuda")
+    vt[..., :T] = v.permute(0, 2, 3, 1).reshape(S * H, hd, T)
+    out = torch.full((S * T, D), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.attention(qk[:, :D], qk[:, D:], vt, out, S, T, H, hd, kv_xor, key_mask=keep, persons=2)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    if kv_xor:
+        idx = torch.arange(S, device="cuda") ^ kv_xor
+        kf, vf = kf[idx], vf[idx]                         # (the partner sequence belongs to the same mask row)
+    ref = _ref_attention(qf, kf, vf, 1.0 / math.sqrt(hd), pad).permute(0, 2, 1, 3).reshape(S * T, D)
+    assert torch.isfinite(out.float()).all()
+    assert _relerr(out, ref) < 1e-2
+    dead = pad.all(dim=1)
+    if dead.any():
+        assert out.view(S, T, D)[dead].abs().max().item() == 0.0
 
 
 @pytest.mark.parametrize("T,hd", [(300, 128), (300, 64), (512, 128)])

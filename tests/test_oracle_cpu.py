@@ -105,6 +105,34 @@ def test_oracle_mixer_forward_vs_golden(golden, small_sd, mode):
     assert relerr(d["w1"], arr[f"mixer_w1_mode{mode}"]) < 2e-5
 
 
+@pytest.mark.parametrize("mode", [2, 4])
+def test_oracle_with_frame_mask_vs_reference_golden(golden, small_sd, mode):
+    """key-padding masks: both denoisers and Mixer.forward(align=False) against the unmodified reference"""
+    import os
+    arr, meta = golden
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_masked.npz"))
+    assert int(ref["align_with_mask_runs"]) == 0      # why masks require align=False: the reference raises there
+    cond, noise, t, x1, x2 = _inputs(meta)
+    mask = torch.from_numpy(ref["mask"])
+    sd = dict(small_sd)
+    nw = 1 if mode in (1, 2) else 23
+    sd.update(synth.synthetic_state_dict({"influence.out.weight": torch.zeros(nw, 512),
+                                          "influence.out.bias": torch.zeros(nw)}, seed=meta["weights_seed"]))
+    orc = build_oracle(sd, meta["dims"], mixing_mode=mode, align=False)
+    with torch.no_grad():
+        d = orc.mixer(x1, x2, t, cond, detail=True, mask=mask)
+        assert relerr(d["out"], ref[f"mixer_out_mode{mode}"]) < 2e-5
+        assert relerr(d["w1"], ref[f"mixer_w1_mode{mode}"]) < 2e-5
+        if mode == 4:
+            a = mixer_oracle.denoiser(orc.sd, "denoiser1.", "individual", x1[..., :262], t, cond[:, 2304:3072],
+                                      orc.h_den, mask)
+            b = mixer_oracle.denoiser(orc.sd, "denoiser2.", "interaction", x2, t, cond[:, :2304], orc.h_den, mask)
+            assert relerr(a, ref["den_individual"]) < 2e-5
+            assert relerr(b, ref["den_interaction"]) < 2e-5
+            # the mask matters: the unmasked golden differs
+            assert relerr(b, arr["den_interaction"]) > 1e-3
+
+
 def test_oracle_denoisers_and_step_vs_golden(golden, small_sd):
     arr, meta = golden
     cond, noise, t, x1, x2 = _inputs(meta)

@@ -384,6 +384,56 @@ def test_every_ddim_step_teacher_forced_vs_reference_chain():
     report("worst per-step state vs the reference chain", worst["state"])
 
 
+@pytest.mark.parametrize("mode", [2, 4])
+def test_frame_mask_vs_reference_golden(golden, mode):
+    """key-padding masks (in2in.py:410-435, influence.py:107-116) through the engine: both denoisers, Mixer.forward with
+    align=False and the CFG wrapper, against outputs of the unmodified reference; align=True + mask raises as the
+    reference does; a later unmasked call is unaffected (the mask is per call)."""
+    import os
+    from mixermdm_b200.modules import ClassifierFreeSampleModelX2
+    arr, meta = golden
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_masked.npz"))
+    cond, noise, t, x1, x2 = _inputs(meta)
+    mask = torch.from_numpy(ref["mask"]).to(DEV)
+    mix, sd = build_mixer(meta["dims"], mixing_mode=mode, align=False, store_influence=True)
+    mix = mix.to(DEV)
+    out = mix(x1, t, cond=cond, mask=mask, x2=x2)
+    torch.cuda.synchronize()
+    assert report(f"masked mixer mode {mode}", relerr(out, ref[f"mixer_out_mode{mode}"])) < TOL_BF16
+    w1 = mix.history_influence_i1[-1].expand(meta["B"], meta["T"], 262)
+    assert report(f"masked weights mode {mode}", relerr(w1, ref[f"mixer_w1_mode{mode}"])) < TOL_BF16
+    if mode == 4:
+        a = mix.denoiser1(x1[..., :262], t, mask=mask, cond=cond[:, 2304:3072])
+        b = mix.denoiser2(x2, t, mask=mask, cond=cond[:, :2304])
+        assert report("masked individual denoiser", relerr(a, ref["den_individual"])) < TOL_BF16
+        assert report("masked interaction denoiser", relerr(b, ref["den_interaction"])) < TOL_BF16
+        b0 = mix.denoiser2(x2, t, mask=None, cond=cond[:, :2304])          # the mask does not stick to the handle
+        assert report("unmasked call after a masked one", relerr(b0, arr["den_interaction"])) < TOL_BF16
+        # CFG wrapper: doubled batch, one mask row per sample
+        orc = build_oracle(sd, meta["dims"], mixing_mode=mode, align=False)
+        g = ClassifierFreeSampleModelX2(mix, 3.5)(x1, x2, t, cond=cond, mask=mask)
+        want = 3.5 * orc.mixer(x1.cpu(), x2.cpu(), t.cpu(), cond.cpu(), mask=mask.cpu()) - \
+            2.5 * orc.mixer(x1.cpu(), x2.cpu(), t.cpu(), torch.zeros_like(cond).cpu(), mask=mask.cpu())
+        assert report("masked CFG wrapper", relerr(g, want)) < 2 * TOL_BF16
+        aligned, _ = build_mixer(meta["dims"], mixing_mode=mode, align=True)
+        with pytest.raises(NotImplementedError):
+            aligned.to(DEV)(x1, t, cond=cond, mask=mask, x2=x2)
+        # sampler: one masked DDIM step against the oracle, and the graph-replayed masked loop == eager masked steps
+        orc.sched = default_schedule()
+        eng = mix.engine(2 * meta["B"], meta["T"], torch.device(DEV), sched=orc.sched, cfg_scale=3.5, center=True)
+        eng.hd.set_key_mask(mask, meta["T"])
+        eng.set_condition(cond)
+        eng.set_state(x1, x2, 30)
+        eng.step()
+        s1, s2 = eng.get_state()
+        o = orc.ddim_step(x1.cpu(), x2.cpu(), 30, cond.cpu(), mask=mask.cpu())
+        assert report("masked ddim step stream2", relerr(s2, o["sample2"])) < TOL_BF16
+        loop_g = eng.sample(cond, noise, mask=mask).clone()
+        loop_e = eng.sample(cond, noise, mask=mask, use_graph=False).clone()
+        loop_0 = eng.sample(cond, noise)
+        assert torch.equal(loop_g, loop_e) and not torch.equal(loop_g, loop_0)
+
+
 def test_ddpm_step_formula_level(golden):
     """The DDPM variant of the fused update (north star: "DDIM/DDPM update"). The reference's MixerDiffusion cannot run
     p_sample, so parity is formula-level: (1) against the oracle's restatement of p_sample on the two-stream prediction

@@ -43,8 +43,9 @@ struct AttnCfg {
   static constexpr uint32_t NBAR = 18 + 4 * NSLOT;
   static constexpr uint32_t USED_BYTES = 2 * Q_BYTES + NSLOT * (KB_BYTES + VB_BYTES) + NBAR * 8 + 16;
   static constexpr size_t SMEM_BYTES = USED_BYTES + 1024;
-  // TMEM columns: warpgroup g owns [g*128, +128): S [0,64) | P buffer 0 [64,96) | P buffer 1 [96,128) (packed bf16,
-  // block m -> buffer m & 1); O_g [256 + g*HD, +HD)
+  // TMEM columns: warpgroup g owns [g*128, +128) as two 64-column S buffers (block m -> buffer m & 1); P(m), packed
+  // bf16, overwrites the first 32 columns of its own S buffer once the row's logits are in registers; O_g at
+  // [256 + g*HD, +HD)
   static constexpr uint32_t SP_COL = 0, O_COL = 256;
   static constexpr int THREADS = 352;   // 8 softmax warps, 2 MMA warps (one per warpgroup), loader
 };
@@ -110,12 +111,14 @@ __device__ __forceinline__ void ring_next(RingPos& r) {
 
 // Barrier protocol (one CTA; g = softmax warpgroup, m = running block number of the warpgroup). A barrier may run ONE
 // phase ahead of its waiter, never two (parity waits alias).
-//   sfull[g]   MMA commit      S(m) complete. A commit covers ALL earlier MMAs of the issuing thread and the issue order
-//                              is S(m+1), PV(m), S(m+2): S(m+2) complete => P V(m) complete, i.e. P buffer m & 1 and the
-//                              V block of m are free - the softmax warps release K and V ring slots from that.
-//   sfree[g]   4 softmax warps S(m) is in registers -> S(m+1) may be issued (long before P(m) exists: the tensor pipe
-//                              is never in the softmax warps' critical path)
-//   pfull[g,b] 4 softmax warps P(m) written to buffer b = m & 1
+//   sfull[g,b] MMA commit      S(m) complete in buffer b = m & 1. A commit covers ALL earlier MMAs of the issuing thread
+//                              and the issue order is S(0), S(1), then P V(m), S(m+2) for every m: S runs up to two blocks
+//                              ahead of the softmax (its round trip through the MMA warp and the in-order pipe, 1300-1900
+//                              cycles, is off the critical path), S(m+2) complete => P V(m) complete, i.e. the V block of
+//                              m is free - the softmax warps release K and V ring slots from that. S(m+2) may overwrite
+//                              buffer b because it is issued behind P V(m), the reader of P(m), and P(m) was published
+//                              after the warpgroup pulled S(m) out.
+//   pfull[g,b] 4 softmax warps P(m) written over the head of S buffer b = m & 1
 //   flush[g]   MMA commit      once per tile behind P V(NB - 2): what S(m + 1) is for earlier blocks, for the rescale
 //                              path of the last block
 //   ofull[g]   MMA commit      last P V of the tile complete;   ofree[g]  4 warps: O_g read out
@@ -135,8 +138,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + C::NSLOT * C::VB_BYTES);
   uint64_t* qfull = bars;          // [2]
   uint64_t* qfree = bars + 2;      // [2]
-  uint64_t* sfull = bars + 4;      // [2]
-  uint64_t* sfree = bars + 6;      // [2]
+  uint64_t* sfull = bars + 4;      // [2 warpgroups][2 buffers]
   uint64_t* pfull = bars + 8;      // [2][2]
   uint64_t* ofull = bars + 12;     // [2]
   uint64_t* ofree = bars + 14;     // [2]
@@ -168,8 +170,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int g = 0; g < 2; ++g) {
       mbar_init(&qfull[g], 1);
       mbar_init(&qfree[g], 1);
-      mbar_init(&sfull[g], 1);
-      mbar_init(&sfree[g], 4);
+      mbar_init(&sfull[g * 2], 1);
+      mbar_init(&sfull[g * 2 + 1], 1);
       mbar_init(&ofull[g], 1);
       mbar_init(&ofree[g], 4);
       mbar_init(&flush[g], 1);
@@ -287,29 +289,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         auto issue_s = [&](int kb) {
           const int m = m0 + kb;
           TR(warp, m, 0);
-          if (!seen) mbar_wait(&kfull[rs.slot], rs.ph & 1);   // (first: usually complete long before S(m - 1) is read)
-          if (m > 0) mbar_wait(&sfree[g], (m - 1) & 1);
+          if (!seen) mbar_wait(&kfull[rs.slot], rs.ph & 1);
           tc_fence_after();
           TR(warp, m, 1);
           uint64_t da = dq0;
           uint64_t db = dk0 + (uint64_t)launder(((uint32_t)rs.slot * C::KB_BYTES) >> 4);
 #pragma unroll
           for (int kk = 0; kk < HD / 16; ++kk) {   // 16 elements = 32 B per step, next 64-wide atom after four steps
-            umma_bf16_ss(scol, da, db, ids, kk > 0 ? 1u : 0u);
+            umma_bf16_ss(scol + (uint32_t)(m & 1) * 64u, da, db, ids, kk > 0 ? 1u : 0u);
             const bool wrap = (kk & 3) == 3;
             da += wrap ? (uint64_t)(128 * 128 / 16 - 6) : 2u;
             db += wrap ? (uint64_t)(64 * 128 / 16 - 6) : 2u;
           }
-          umma_commit(&sfull[g]);
+          umma_commit(&sfull[g * 2 + (m & 1)]);
           if (kb == NB - 1) umma_commit(&qfree[g]);
           ring_next<C::NSLOT>(rs);
           TR(warp, m, 2);
         };
         mbar_wait(&qfull[g], nt & 1);
         issue_s(0);
+        if (NB > 1) issue_s(1);
         for (int kb = 0; kb < NB; ++kb) {
-          if (kb + 1 < NB) issue_s(kb + 1);
-          else if (NB > 1) umma_commit(&flush[g]);   // covers P V(NB - 2) for the rescale path of the last block
           const int m = m0 + kb, b = m & 1, u = m >> 1;
           TR(warp, m, 3);
           if (!seen) mbar_wait(&vfull[rv.slot], rv.ph & 1);
@@ -317,7 +317,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&pfull[g * 2 + b], u & 1);
           tc_fence_after();
           TR(warp, m, 5);
-          uint32_t pa = scol + 64u + (uint32_t)b * 32u;
+          uint32_t pa = scol + (uint32_t)b * 64u;
           uint64_t db = dv0 + (uint64_t)launder(((uint32_t)rv.slot * C::VB_BYTES) >> 4);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {   // 16 keys per step
@@ -332,6 +332,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (kb == NB - 1) umma_commit(&ofull[g]);
           ring_next<C::NSLOT>(rv);
           TR(warp, m, 6);
+          if (kb + 2 < NB) issue_s(kb + 2);                      // into the buffer whose P this P V has just consumed
+          else if (kb + 2 == NB) umma_commit(&flush[g]);   // covers P V(NB - 2) for the rescale path of the last block
         }
         m0 += NB;
         nt++;
@@ -412,9 +414,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int m = m0 + kb, b = m & 1;
         TR(warp, m, 0);
         // S(kb) has completed: its key block is free; it was issued behind P V(kb - 2), so that V block is free too
-        mbar_wait(&sfull[g], m & 1);
+        mbar_wait(&sfull[g * 2 + b], (m >> 1) & 1);
         tc_fence_after();
-        if (m == 0 && g == 1 && p.stagger > 0) {
+        if (kb == 0 && g == 1 && p.stagger > 0) {
           // The two warpgroups start in lock step (their first key block lands at the same moment) and, with equal work
           // per block, stay there: both load from TMEM together, then both queue for the MUFU together. Half a block of
           // delay, once, puts one warpgroup's exponentials under the other's TMEM reads and barrier traffic.
@@ -430,7 +432,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (kb >= 2) ring_next<C::NSLOT>(rv);
         TR(warp, m, 1);
         if (rows_valid) {
-          const uint32_t pcol = spcol + 64u + (uint32_t)b * 32u;
+          const uint32_t sbuf = spcol + (uint32_t)b * 64u;   // S(kb); P(kb) goes over its first 32 columns
+          const uint32_t pcol = sbuf;
           // attendable keys of the block: keys 0..T-1, key T = the zero-attention key, nothing beyond. MASKED: minus
           // the caller's padding mask, as a bit word (the zero key stays attendable: torch pads the mask with False)
           const int key0 = kb * 64;
@@ -447,12 +450,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             else return key0 + j <= p.T;
           };
           uint32_t sv[64];
-          tmem_ld_32x32b_x32(spcol, sv);
-          tmem_ld_32x32b_x32(spcol + 32u, sv + 32);
+          tmem_ld_32x32b_x32(sbuf, sv);
+          tmem_ld_32x32b_x32(sbuf + 32u, sv + 32);
           tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sfree[g]);   // S(kb) is in registers: S(kb + 1) may be issued
           TR(warp, m, 2);
           // running maximum of the row from this block's logits (keys beyond T are zero rows of K: logit 0, harmless
           // below a maximum that is >= 0)
@@ -521,7 +521,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const bool grow = kb > 0 && !(bsum < 1.0995116e12f);
           if (__any_sync(0xffffffffu, grow)) {
             if (kb + 1 == NB) mbar_wait(&flush[g], nt & 1);
-            else mbar_wait(&sfull[g], (m + 1) & 1);
+            else mbar_wait(&sfull[g * 2 + (b ^ 1)], ((m + 1) >> 1) & 1);
             tc_fence_after();
             float f = 1.0f;
             if (grow) {   // (register arithmetic only: the warp-collective TMEM accesses stay outside the branch)
@@ -545,9 +545,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_st_32x32b_x16(pcol, pk);
           tmem_st_32x32b_x16(pcol + 16u, pk + 16);
           tmem_st_wait();
-        } else if (lane == 0) {
-          mbar_arrive(&sfree[g]);   // row groups past the sequence end only keep the barrier counts
-        }
+        }   // (row groups past the sequence end only keep the barrier counts)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pfull[g * 2 + b]);

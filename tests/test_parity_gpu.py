@@ -40,7 +40,7 @@ def _inputs(meta):
 def test_library_is_the_product_path():
     from mixermdm_b200 import _lib
     lib = _lib.load()
-    assert lib.mmdm_abi_version() == 2
+    assert lib.mmdm_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_denoiser_forward_vs_reference_golden(golden):

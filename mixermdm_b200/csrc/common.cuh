@@ -491,6 +491,35 @@ __device__ __forceinline__ uint32_t gelu_fast2_bf16(f32x2 x) {
   unpack2(fma2(q, e, pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), r0, r1);   // relu(x) - 0.5 |x| poly exp
   return pack_bf16x2(r0, r1);
 }
+// GELU through one MUFU: x Phi(x) = 0.5 x (1 + tanh(w(x))) holds exactly for w = atanh(erf(x / sqrt 2)), an odd function
+// that a degree-5 odd polynomial fits to |GELU error| < 5.4e-5 over the whole real line (the classic 0.044715 cubic:
+// 4.7e-4); tanh.approx adds at most 2^-11 relative on tanh, i.e. < 2.5e-4 |x| on the result - an eighth of the bf16
+// rounding of the stored value. 6 packed fp32x2 operations + 2 MUFU + the bf16 pack per PAIR (gelu_fast2_bf16: ~20 + 4).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t gelu_tanh2_bf16(f32x2 x) {
+  const f32x2 x2 = mul2(x, x);
+  f32x2 p = fma2(x2, pack2(-3.81889112e-04f, -3.81889112e-04f), pack2(3.72153111e-02f, 3.72153111e-02f));
+  p = fma2(p, x2, pack2(7.97237410e-01f, 7.97237410e-01f));
+  float w0, w1;
+  unpack2(mul2(p, x), w0, w1);
+  const f32x2 t = pack2(tanh_approx(w0), tanh_approx(w1));
+  const f32x2 hx = mul2(x, pack2(0.5f, 0.5f));
+  float r0, r1;
+  unpack2(fma2(hx, t, hx), r0, r1);
+  return pack_bf16x2(r0, r1);
+}
+__device__ __forceinline__ float gelu_tanh5(float x) {   // the same arithmetic on one value (edge tiles)
+  const float x2 = x * x;
+  float p = fmaf(x2, -3.81889112e-04f, 3.72153111e-02f);
+  p = fmaf(p, x2, 7.97237410e-01f);
+  const float t = tanh_approx(p * x);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // CLIP's QuickGELU: x * sigmoid(1.702 x) (OpenAI clip/model.py, class QuickGELU)
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }

@@ -63,6 +63,17 @@ __device__ __forceinline__ void load_bias32(uint32_t bias_smem, float* b) {
   }
 }
 
+// GELU of the FFN-1 epilogue: exact-erf definition (Abramowitz-Stegun, 1.5e-7). -DMMDM_GELU_TANH selects the one-MUFU
+// tanh form of common.cuh (|error| < 3e-4 |x|): measured 137.4 against 143.0 us per FFN-1 launch (a plain bf16 epilogue:
+// 130.0 us), i.e. 0.5 % of a DDIM step - not worth leaving the reference's definition for.
+#ifdef MMDM_GELU_TANH
+#define MMDM_GELU1 gelu_tanh5
+#define MMDM_GELU2 gelu_tanh2_bf16
+#else
+#define MMDM_GELU1 gelu_fast
+#define MMDM_GELU2 gelu_fast2_bf16
+#endif
+
 // generic (edge) path: per-element guards; used only for ragged N (the 262-wide output layer) and by the
 // SIMT bring-up kernel
 template <int MODE>
@@ -74,7 +85,7 @@ __device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const Row
     const int n = col0 + j;
     const float x = v[j] + (ep.bias ? __ldg(ep.bias + n) : 0.f);
     if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16 || MODE == EPI_QGELU_BF16) {
-      const float o = (MODE == EPI_GELU_BF16) ? gelu_erf(x) : (MODE == EPI_QGELU_BF16) ? quick_gelu(x) : x;
+      const float o = (MODE == EPI_GELU_BF16) ? MMDM_GELU1(x) : (MODE == EPI_QGELU_BF16) ? quick_gelu(x) : x;
       if (MODE == EPI_BF16 && ep.vt_col0 >= 0 && n >= ep.vt_col0) {
         const int nn = n - ep.vt_col0, h = nn / ep.hd, d = nn - h * ep.hd;
         ep.vt[((size_t)(rc.s * ep.H + h) * ep.hd + d) * ep.Tp + rc.t] = __float2bfloat16_rn(o);
@@ -120,10 +131,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 pk;
-      pk.x = gelu_fast2_bf16(add2(pack2(v[8 * j], v[8 * j + 1]), pack2(b[8 * j], b[8 * j + 1])));
-      pk.y = gelu_fast2_bf16(add2(pack2(v[8 * j + 2], v[8 * j + 3]), pack2(b[8 * j + 2], b[8 * j + 3])));
-      pk.z = gelu_fast2_bf16(add2(pack2(v[8 * j + 4], v[8 * j + 5]), pack2(b[8 * j + 4], b[8 * j + 5])));
-      pk.w = gelu_fast2_bf16(add2(pack2(v[8 * j + 6], v[8 * j + 7]), pack2(b[8 * j + 6], b[8 * j + 7])));
+      pk.x = MMDM_GELU2(add2(pack2(v[8 * j], v[8 * j + 1]), pack2(b[8 * j], b[8 * j + 1])));
+      pk.y = MMDM_GELU2(add2(pack2(v[8 * j + 2], v[8 * j + 3]), pack2(b[8 * j + 2], b[8 * j + 3])));
+      pk.z = MMDM_GELU2(add2(pack2(v[8 * j + 4], v[8 * j + 5]), pack2(b[8 * j + 4], b[8 * j + 5])));
+      pk.w = MMDM_GELU2(add2(pack2(v[8 * j + 6], v[8 * j + 7]), pack2(b[8 * j + 6], b[8 * j + 7])));
       dst[j] = pk;
     }
   } else if (MODE == EPI_QGELU_BF16) {

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MMDM_ABI_VERSION 3
+#define MMDM_ABI_VERSION 4
 
 typedef struct mmdm_handle mmdm_handle;
 
@@ -45,7 +45,16 @@ enum mmdm_epilogue_mode {
   MMDM_EPI_FINAL = 4,     /* out_f32  = (acc + bias) * std + mean       FinalLayer + normalizer.backward    */
   MMDM_EPI_F32 = 5,       /* out_f32  = acc + bias                      AdaLN.emb_layers[1]                 */
   MMDM_EPI_SIGMOID_F32 = 6, /* out_f32 = sigmoid(acc + bias)             Influence.out + sigmoid            */
-  MMDM_EPI_QGELU_BF16 = 7  /* out_bf16 = x sigmoid(1.702 x), x = acc + bias   CLIP QuickGELU (text tower MLP) */
+  MMDM_EPI_QGELU_BF16 = 7, /* out_bf16 = x sigmoid(1.702 x), x = acc + bias   CLIP QuickGELU (text tower MLP) */
+  /* AdaLN (layers.py:15-25) folded into the GEMMs on either side of it. With xn = (h - mu) rho (1 + scale_s) + shift_s
+   * feeding a Linear (W, c):  y[r,n] = rho_r sum_k [h (1+scale_s)][r,k] W[n,k] - rho_r mu_r G_s[n] + Bc_s[n],
+   * G_s[n] = sum_k (1+scale_s[k]) W[n,k],  Bc_s[n] = sum_k shift_s[k] W[n,k] + c[n]  (s = row / T).
+   * The *_LN producers write h and bf16(h (1+scale_s)) plus per-row (sum h, sum h^2) per 64-column slot; the *_LN
+   * consumers take that operand and finish the normalisation in their epilogue. */
+  MMDM_EPI_BF16_LN = 8,       /* MMDM_EPI_BF16 on the folded operand                                         */
+  MMDM_EPI_GELU_BF16_LN = 9,  /* MMDM_EPI_GELU_BF16 on the folded operand                                    */
+  MMDM_EPI_RESID_LN = 10,     /* MMDM_EPI_RESID + operand(s) and row sums for the next AdaLN site            */
+  MMDM_EPI_EMBED_PE_LN = 11   /* MMDM_EPI_EMBED_PE + the same                                                */
 };
 
 typedef struct mmdm_epilogue {
@@ -69,6 +78,17 @@ typedef struct mmdm_epilogue {
   const float* mean;
   int32_t nfeats;
   int32_t persons_per_row;
+  /* *_LN producers (N = latent dim, N % 64 == 0, ldo == N; the bf16 operands share that pitch) */
+  const float* lnp_scale0; int32_t lnp_ld0; void* lnp_out0;   /* scale rows [s*ld + k] of the next site, its operand  */
+  const float* lnp_scale1; int32_t lnp_ld1; void* lnp_out1;   /* optional second site on the same rows, or NULL       */
+  float* lnp_stats;        /* float2 [N/64][lnp_pitch]: (sum h, sum h^2) of row r over columns [64 j, 64 j + 64)      */
+  int64_t lnp_pitch;
+  int32_t lnp_T;           /* rows per sequence                                                                       */
+  int32_t lnp_rows;        /* rows >= lnp_rows only get h (0 = all rows)                                              */
+  int32_t lnp_dup_seq;     /* EMBED_PE_LN with dup_row_offset: sequence offset of the duplicated rows                 */
+  /* *_LN consumers (K = latent dim; uses T; `bias` is ignored, it is part of Bc) */
+  const float* lnc_stats; int64_t lnc_pitch;                  /* the producer's statistics                            */
+  const float* lnc_g; const float* lnc_b; int32_t lnc_ld;     /* G_s[n] = lnc_g[s*ld + n], Bc_s[n] = lnc_b[s*ld + n]  */
 } mmdm_epilogue;
 
 /* D[M,N] = A[M,K] * W[N,K]^T, bf16 operands (row pitches lda/ldw in elements), fp32 accumulation (tcgen05).
@@ -168,6 +188,19 @@ typedef struct mmdm_net_weights {
   const float* time_w2; const float* time_b2;   /* embed_timestep.time_embed.2                                 */
   const float* text_w;  const float* text_b;    /* text_embed (D, 768) fp32                                    */
   const mmdm_block_weights* blocks;             /* host array of L entries                                     */
+  /* Optional: composite conditioning tables for the LN fold (MMDM_EPI_*_LN). The AdaLN (scale|shift) vectors are linear
+   * in E = bf16(SiLU(emb)): scale_s = Wsc E_s + bsc, shift_s = Wsh E_s + bsh (rows of ada0 / ada1), hence so are
+   *   G_s  = W (1 + scale_s) = (W Wsc) E_s + W (1 + bsc)       Bc_s = W shift_s + c = (W Wsh) E_s + W bsh + c
+   * for the Linear (W, c) behind the norm. comp{0,1}_w holds, per block and per site in the ada{0,1} order, the rows
+   * [W Wsc (N rows); W Wsh (N rows)] - computed from the bf16 values of W, Wsc, Wsh in >= fp32 - each row stored as a
+   * bf16 pair [hi (D) | lo (D)] with hi + lo = the fp32 value, so the table is (comp_n, 2D) and the engine multiplies
+   * it by [E_s | E_s]; comp{0,1}_b the fp32 constants [W (1 + bsc); W bsh + c]. Sites (N = rows of the consuming Linear):
+   *   INDIVIDUAL : comp0 = [sa.norm -> in_proj (3D), ffn.norm -> linear1 (F)]
+   *   INTERACTION: comp0 = the same;  comp1 = [ca.norm -> in_proj[0:D] (D), ca.xf_norm -> in_proj[D:3D] (2D)]
+   *   INFLUENCE  : comp0 = [sa.norm -> in_proj (3D)];  comp1 = [ca.norm -> in_proj[0:D] (D), ffn.norm -> linear1 (F)]
+   * NULL comp0_w: the engine runs the stand-alone LayerNorm kernel (mmdm_ln_modulate) in front of those GEMMs. */
+  const void* comp0_w; const float* comp0_b; int32_t comp0_n;
+  const void* comp1_w; const float* comp1_b; int32_t comp1_n;
 } mmdm_net_weights;
 
 typedef struct mmdm_config {

@@ -5,7 +5,7 @@ import os
 from . import _build
 
 _LIB = None
-ABI_VERSION = 3   # MMDM_ABI_VERSION of include/mixermdm_b200.h
+ABI_VERSION = 4   # MMDM_ABI_VERSION of include/mixermdm_b200.h
 
 
 class MmdmError(RuntimeError):
@@ -22,10 +22,17 @@ class Epilogue(C.Structure):
         ("resid", C.c_void_p), ("out_bf16", C.c_void_p),
         ("pe", C.c_void_p), ("pe_ld", C.c_int32), ("dup_row_offset", C.c_int64),
         ("std_", C.c_void_p), ("mean", C.c_void_p), ("nfeats", C.c_int32), ("persons_per_row", C.c_int32),
+        ("lnp_scale0", C.c_void_p), ("lnp_ld0", C.c_int32), ("lnp_out0", C.c_void_p),
+        ("lnp_scale1", C.c_void_p), ("lnp_ld1", C.c_int32), ("lnp_out1", C.c_void_p),
+        ("lnp_stats", C.c_void_p), ("lnp_pitch", C.c_int64), ("lnp_T", C.c_int32), ("lnp_rows", C.c_int32),
+        ("lnp_dup_seq", C.c_int32),
+        ("lnc_stats", C.c_void_p), ("lnc_pitch", C.c_int64),
+        ("lnc_g", C.c_void_p), ("lnc_b", C.c_void_p), ("lnc_ld", C.c_int32),
     ]
 
 
 EPI_BF16, EPI_GELU_BF16, EPI_RESID, EPI_EMBED_PE, EPI_FINAL, EPI_F32 = range(6)
+EPI_BF16_LN, EPI_GELU_BF16_LN, EPI_RESID_LN, EPI_EMBED_PE_LN = 8, 9, 10, 11
 
 
 def lib_path():

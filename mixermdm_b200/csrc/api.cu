@@ -30,6 +30,13 @@ GemmEpi to_internal(const mmdm_epilogue& e) {
   g.mean = e.mean;
   g.nfeats = e.nfeats;
   g.persons_per_row = e.persons_per_row > 0 ? e.persons_per_row : 2;
+  g.lnp_scale0 = e.lnp_scale0; g.lnp_ld0 = e.lnp_ld0; g.lnp_out0 = reinterpret_cast<__nv_bfloat16*>(e.lnp_out0);
+  g.lnp_scale1 = e.lnp_scale1; g.lnp_ld1 = e.lnp_ld1; g.lnp_out1 = reinterpret_cast<__nv_bfloat16*>(e.lnp_out1);
+  g.lnp_stats = reinterpret_cast<float2*>(e.lnp_stats);
+  g.lnp_pitch = e.lnp_pitch; g.lnp_T = e.lnp_T > 0 ? e.lnp_T : 1; g.lnp_rows = e.lnp_rows; g.lnp_dup_seq = e.lnp_dup_seq;
+  g.lnc_stats = reinterpret_cast<const float2*>(e.lnc_stats);
+  g.lnc_pitch = e.lnc_pitch; g.lnc_slots = 0;   // K / 64, set by launch_gemm's caller below
+  g.lnc_g = e.lnc_g; g.lnc_b = e.lnc_b; g.lnc_ld = e.lnc_ld;
   return g;
 }
 }  // namespace mmdm
@@ -44,8 +51,10 @@ void mmdm_debug_gemm_simt(int on) { mmdm::gemm_set_debug_simt(on); }
 int mmdm_linear_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                      const mmdm_epilogue* ep, void* stream) {
   MMDM_REQUIRE(A && W && ep && ep->out, "mmdm_linear_bf16: null argument");
+  GemmEpi g = to_internal(*ep);
+  g.lnc_slots = K / kLnSlotCols;
   return launch_gemm(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W), ldw,
-                     M, N, K, to_internal(*ep), reinterpret_cast<cudaStream_t>(stream));
+                     M, N, K, g, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mmdm_ln_modulate(const float* h, int M, int D, int T, const float* mod0, int ld_mod0, void* out0,

@@ -74,6 +74,7 @@ struct Net {
   mmdm_net_weights w;
   std::vector<mmdm_block_weights> blocks;
   bool present = false;
+  bool fold = false;   // AdaLN folded into the neighbouring GEMMs (composite conditioning weights given, see gemm.cuh)
   int hd() const { return w.D / w.H; }
 };
 
@@ -87,8 +88,11 @@ struct Workspace {
   bf16* att = nullptr;      // attention output (M, Dmax)
   bf16* mid = nullptr;      // FFN hidden (M, Fmax)
   bf16* xin = nullptr;      // packed embed operand (2*M, kpad)
-  bf16 *E0 = nullptr, *E1 = nullptr;   // SiLU(emb) (S, Dmax)
+  bf16 *E0 = nullptr, *E1 = nullptr;   // SiLU(emb), each row twice: (S, 2 Dmax) = [e | e] (K = 2D operand of the composite GEMM)
   float *mod0 = nullptr, *mod1 = nullptr;  // AdaLN outputs (S, ada_n max)
+  float *gb0 = nullptr, *gb1 = nullptr;    // LN fold: G_s | Bc_s rows of every AdaLN site (S, comp_n max)
+  float2* stat[3] = {nullptr, nullptr, nullptr};   // LN fold: row sums per 64-column slot [Dmax / 64][M]; block input /
+                                                   // after self attention / after cross attention
   int *map0 = nullptr, *map1 = nullptr, *tmap = nullptr;
   float* text[3] = {nullptr, nullptr, nullptr};   // per net: (nslices*Bx + 1, D)
   float* temb_tab[3] = {nullptr, nullptr, nullptr};  // per net: (nsteps, D)
@@ -189,11 +193,12 @@ struct Carver {
 static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, size_t* total) {
   const int Bx = 2 * B, S = 2 * Bx;
   const size_t M = (size_t)S * T;
-  int Dmax = 0, Fmax = 0, adamax = 0;
+  int Dmax = 0, Fmax = 0, adamax = 0, compmax = 0;
   for (int i = 0; i < 3; ++i) {
     Dmax = std::max(Dmax, h->net[i].w.D);
     Fmax = std::max(Fmax, h->net[i].w.F);
     adamax = std::max(adamax, std::max(h->net[i].w.ada0_n, h->net[i].w.ada1_n));
+    if (h->net[i].fold) compmax = std::max(compmax, std::max(h->net[i].w.comp0_n, h->net[i].w.comp1_n));
   }
   const int Tp = (T + 7) / 8 * 8;
   const int nf2 = 2 * h->cfg.nfeats;
@@ -207,8 +212,13 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
   ws.att = c.take<bf16>(M * Dmax);
   ws.mid = c.take<bf16>(M * Fmax);
   ws.xin = c.take<bf16>(2 * M * h->cfg.kpad);
-  ws.E0 = c.take<bf16>((size_t)S * Dmax);
-  ws.E1 = c.take<bf16>((size_t)S * Dmax);
+  ws.E0 = c.take<bf16>((size_t)S * 2 * Dmax);
+  ws.E1 = c.take<bf16>((size_t)S * 2 * Dmax);
+  if (compmax > 0) {
+    ws.gb0 = c.take<float>((size_t)S * compmax);
+    ws.gb1 = c.take<float>((size_t)S * compmax);
+    for (int i = 0; i < 3; ++i) ws.stat[i] = c.take<float2>((size_t)(Dmax / 64) * M);
+  }
   ws.mod0 = c.take<float>((size_t)S * adamax);
   ws.mod1 = c.take<float>((size_t)S * adamax);
   ws.map0 = c.take<int>(S);
@@ -294,6 +304,8 @@ static int run_conditioning(mmdm_handle* h, int ni, int S, const float* temb, co
   Net& n = h->net[ni];
   Workspace& ws = h->ws;
   const int D = n.w.D;
+  // E rows are written twice, [e | e] (pitch 2D): the composite weights of the LN fold are bf16 pairs [hi | lo]
+  // along K, so one GEMM over K = 2D adds both halves in fp32
   {
     Scope sc(h, "cond_silu", st);
     MMDM_TRY(launch_cond_silu(temb, ws.tmap, step_ptr, ws.text[ni], ws.map0, S, D, ws.E0, st));
@@ -301,14 +313,22 @@ static int run_conditioning(mmdm_handle* h, int ni, int S, const float* temb, co
   GemmEpi ep;
   ep.mode = EPI_F32;
   ep.bias = n.w.ada0_b; ep.out = ws.mod0; ep.ldo = n.w.ada0_n;
-  MMDM_TRY(gemm(h, "gemm_adaln", ws.E0, D, n.w.ada0_w, D, S, n.w.ada0_n, D, ep, st));
+  MMDM_TRY(gemm(h, "gemm_adaln", ws.E0, 2 * D, n.w.ada0_w, D, S, n.w.ada0_n, D, ep, st));
+  if (n.fold) {
+    ep.bias = n.w.comp0_b; ep.out = ws.gb0; ep.ldo = n.w.comp0_n;
+    MMDM_TRY(gemm(h, "gemm_adaln", ws.E0, 2 * D, n.w.comp0_w, 2 * D, S, n.w.comp0_n, 2 * D, ep, st));
+  }
   if (n.w.ada1_n > 0) {
     {
       Scope sc(h, "cond_silu", st);
       MMDM_TRY(launch_cond_silu(temb, ws.tmap, step_ptr, ws.text[ni], ws.map1, S, D, ws.E1, st));
     }
     ep.bias = n.w.ada1_b; ep.out = ws.mod1; ep.ldo = n.w.ada1_n;
-    MMDM_TRY(gemm(h, "gemm_adaln", ws.E1, D, n.w.ada1_w, D, S, n.w.ada1_n, D, ep, st));
+    MMDM_TRY(gemm(h, "gemm_adaln", ws.E1, 2 * D, n.w.ada1_w, D, S, n.w.ada1_n, D, ep, st));
+    if (n.fold) {
+      ep.bias = n.w.comp1_b; ep.out = ws.gb1; ep.ldo = n.w.comp1_n;
+      MMDM_TRY(gemm(h, "gemm_adaln", ws.E1, 2 * D, n.w.comp1_w, 2 * D, S, n.w.comp1_n, 2 * D, ep, st));
+    }
   }
   return 0;
 }
@@ -328,9 +348,69 @@ static int ln(mmdm_handle* h, const float* src, int M, int D, int T, const float
   return launch_ln_modulate(src, M, D, T, m0, ld0, o0, m1, ld1, o1, st, next_dir(h));
 }
 
+// ---- LN fold (gemm.cuh): where the G_s | Bc_s rows of a block's AdaLN sites sit in gb0 / gb1 -----------------------
+// Column layout of the composite tables per block l (mirrors the ada0 / ada1 row order, every site = [G (N) | Bc (N)]
+// for the Linear of N outputs that consumes the normalised rows):
+//   INDIVIDUAL : comp0 = [sa: in_proj 3D, ffn: linear1 F]
+//   INTERACTION: comp0 = [sa: in_proj 3D, ffn: linear1 F]      comp1 = [ca.norm: q D, ca.xf_norm: kv 2D]
+//   INFLUENCE  : comp0 = [sa: in_proj 3D]                      comp1 = [ca.norm: q D, ffn: linear1 F]
+//                (its xf_norm normalises m_I, which no GEMM of the block writes: that site keeps the LN kernel)
+struct FoldSite {
+  const float *g, *b;
+  int ld;
+};
+struct Folds {
+  FoldSite sa, ffn, caq, xf;
+};
+static Folds block_folds(const Net& n, const Workspace& ws, int l) {
+  const int D = n.w.D, F = n.w.F;
+  Folds f = {};
+  auto site = [](const float* base, int N, int ld) { return FoldSite{base, base + N, ld}; };
+  if (n.w.kind == MMDM_NET_INFLUENCE) {
+    f.sa = site(ws.gb0 + (size_t)l * 6 * D, 3 * D, n.w.comp0_n);
+    const float* p1 = ws.gb1 + (size_t)l * 2 * (D + F);
+    f.caq = site(p1, D, n.w.comp1_n);
+    f.ffn = site(p1 + 2 * D, F, n.w.comp1_n);
+  } else {
+    const float* p0 = ws.gb0 + (size_t)l * 2 * (3 * D + F);
+    f.sa = site(p0, 3 * D, n.w.comp0_n);
+    f.ffn = site(p0 + 6 * D, F, n.w.comp0_n);
+    if (n.w.kind == MMDM_NET_INTERACTION) {
+      const float* p1 = ws.gb1 + (size_t)l * 6 * D;
+      f.caq = site(p1, D, n.w.comp1_n);
+      f.xf = site(p1 + 2 * D, 2 * D, n.w.comp1_n);
+    }
+  }
+  return f;
+}
+static size_t comp_cols(const mmdm_net_weights& w, int table) {   // expected width of comp0 / comp1
+  const size_t D = w.D, F = w.F, L = w.L;
+  if (w.kind == MMDM_NET_INFLUENCE) return table == 0 ? L * 6 * D : L * 2 * (D + F);
+  if (table == 0) return L * 2 * (3 * D + F);
+  return w.kind == MMDM_NET_INTERACTION ? L * 6 * D : 0;
+}
+
+static void as_consumer(GemmEpi& e, int mode, const FoldSite& fs, const float2* stats, int M, int D, int T) {
+  e.mode = mode;
+  e.bias = nullptr;   // part of Bc
+  e.lnc_stats = stats; e.lnc_pitch = M; e.lnc_slots = D / 64;
+  e.lnc_g = fs.g; e.lnc_b = fs.b; e.lnc_ld = fs.ld;
+  e.T = T;
+}
+static void as_producer(GemmEpi& e, int mode, float2* stats, int M, int T, const float* sc0, int ld0, bf16* o0,
+                        const float* sc1 = nullptr, int ld1 = 0, bf16* o1 = nullptr) {
+  e.mode = mode;
+  e.lnp_stats = stats; e.lnp_pitch = M; e.lnp_T = T;
+  e.lnp_scale0 = sc0; e.lnp_ld0 = ld0; e.lnp_out0 = o0;
+  e.lnp_scale1 = sc1; e.lnp_ld1 = ld1; e.lnp_out1 = o1;
+}
+
 // one transformer block on the residual stream hres (M, D), in place.
 //   kvsrc == nullptr : cross attention (if any) reads the partner stream's block input (s ^ 1)
 //   kvsrc != nullptr : cross attention reads LN(kvsrc) of the same sequence index (Influence: m_I)
+// With the LN fold (n.fold) the block expects bf16(h (1 + scale_sa)) in ws.xn (and bf16(h (1 + scale_xf)) in ws.xf for
+// the partner-stream cross attention) plus the row sums in ws.stat[0] on entry - the previous block's FFN-2 (or the
+// embedding GEMM) wrote them - and leaves the same for block l + 1.
 static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kvsrc, int S, int T, bf16* bf16_copy,
                      cudaStream_t st) {
   Net& n = h->net[ni];
@@ -340,46 +420,89 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
   const int M = S * T;
   const Mods m = block_mods(n, ws, l);
   const bool has_ca = b.ca_q_w != nullptr;
+  const bool fold = n.fold;
+  const Folds f = fold ? block_folds(n, ws, l) : Folds{};
 
   // ---- self attention -------------------------------------------------------------------------
-  if (has_ca && kvsrc == nullptr)
-    MMDM_TRY(ln(h, hres, M, D, T, m.sa, m.ld_sa, ws.xn, m.xf, m.ld_xf, ws.xf, st));
-  else
-    MMDM_TRY(ln(h, hres, M, D, T, m.sa, m.ld_sa, ws.xn, nullptr, 0, nullptr, st));
+  if (!fold) {
+    if (has_ca && kvsrc == nullptr)
+      MMDM_TRY(ln(h, hres, M, D, T, m.sa, m.ld_sa, ws.xn, m.xf, m.ld_xf, ws.xf, st));
+    else
+      MMDM_TRY(ln(h, hres, M, D, T, m.sa, m.ld_sa, ws.xn, nullptr, 0, nullptr, st));
+  }
   GemmEpi ep;
   ep.mode = EPI_BF16; ep.bias = b.sa_in_b; ep.out = ws.qk; ep.ldo = 2 * D;
   ep.vt_col0 = 2 * D; ep.vt = ws.vt; ep.T = T; ep.H = H; ep.hd = hd; ep.Tp = h->Tp;
+  if (fold) as_consumer(ep, EPI_BF16_LN, f.sa, ws.stat[0], M, D, T);
   MMDM_TRY(gemm(h, "gemm_qkv", ws.xn, D, b.sa_in_w, D, M, 3 * D, D, ep, st));
   MMDM_TRY(attention(h, n, S, T, 0, st));
   GemmEpi er;
   er.mode = EPI_RESID; er.out = hres; er.resid = hres; er.ldo = D;
   er.bias = b.sa_out_b;
+  if (fold) {   // next AdaLN site on these rows: the cross attention's query norm, or the FFN norm
+    if (has_ca) as_producer(er, EPI_RESID_LN, ws.stat[1], M, T, m.caq, m.ld_caq, ws.xn);
+    else as_producer(er, EPI_RESID_LN, ws.stat[1], M, T, m.ffn, m.ld_ffn, ws.xn);
+  }
   MMDM_TRY(gemm(h, "gemm_proj", ws.att, D, b.sa_out_w, D, M, D, D, er, st));
 
   // ---- cross attention --------------------------------------------------------------------------
   if (has_ca) {
     if (kvsrc != nullptr) MMDM_TRY(ln(h, kvsrc, M, D, T, m.xf, m.ld_xf, ws.xf, nullptr, 0, nullptr, st));
-    MMDM_TRY(ln(h, hres, M, D, T, m.caq, m.ld_caq, ws.xn, nullptr, 0, nullptr, st));
+    if (!fold) MMDM_TRY(ln(h, hres, M, D, T, m.caq, m.ld_caq, ws.xn, nullptr, 0, nullptr, st));
     GemmEpi eq;
     eq.mode = EPI_BF16; eq.bias = b.ca_q_b; eq.out = ws.qk; eq.ldo = 2 * D;
+    if (fold) as_consumer(eq, EPI_BF16_LN, f.caq, ws.stat[1], M, D, T);
     MMDM_TRY(gemm(h, "gemm_qkv", ws.xn, D, b.ca_q_w, D, M, D, D, eq, st));
     GemmEpi ek;
     ek.mode = EPI_BF16; ek.bias = b.ca_kv_b; ek.out = ws.qk + D; ek.ldo = 2 * D;
     ek.vt_col0 = D; ek.vt = ws.vt; ek.T = T; ek.H = H; ek.hd = hd; ek.Tp = h->Tp;
+    if (fold && kvsrc == nullptr) as_consumer(ek, EPI_BF16_LN, f.xf, ws.stat[0], M, D, T);   // statistics of the block input
     MMDM_TRY(gemm(h, "gemm_qkv", ws.xf, D, b.ca_kv_w, D, M, 2 * D, D, ek, st, /*flip=*/false));   // same way as the q GEMM
     MMDM_TRY(attention(h, n, S, T, kvsrc == nullptr ? 1 : 0, st));
     er.bias = b.ca_out_b;
+    if (fold) as_producer(er, EPI_RESID_LN, ws.stat[2], M, T, m.ffn, m.ld_ffn, ws.xn);
     MMDM_TRY(gemm(h, "gemm_proj", ws.att, D, b.ca_out_w, D, M, D, D, er, st));
   }
 
   // ---- feed forward -------------------------------------------------------------------------------
-  MMDM_TRY(ln(h, hres, M, D, T, m.ffn, m.ld_ffn, ws.xn, nullptr, 0, nullptr, st));
+  if (!fold) MMDM_TRY(ln(h, hres, M, D, T, m.ffn, m.ld_ffn, ws.xn, nullptr, 0, nullptr, st));
   GemmEpi e1;
   e1.mode = EPI_GELU_BF16; e1.bias = b.ffn_b1; e1.out = ws.mid; e1.ldo = F;
+  if (fold) as_consumer(e1, EPI_GELU_BF16_LN, f.ffn, ws.stat[has_ca ? 2 : 1], M, D, T);
   MMDM_TRY(gemm(h, "gemm_ffn1", ws.xn, D, b.ffn_w1, D, M, F, D, e1, st));
   er.bias = b.ffn_b2;
+  er.mode = EPI_RESID;
   er.out_bf16 = bf16_copy;
+  if (fold && l + 1 < n.w.L) {   // operands of the next block
+    const Mods mn = block_mods(n, ws, l + 1);
+    if (has_ca && kvsrc == nullptr) as_producer(er, EPI_RESID_LN, ws.stat[0], M, T, mn.sa, mn.ld_sa, ws.xn, mn.xf, mn.ld_xf, ws.xf);
+    else as_producer(er, EPI_RESID_LN, ws.stat[0], M, T, mn.sa, mn.ld_sa, ws.xn);
+  }
   MMDM_TRY(gemm(h, "gemm_ffn2", ws.mid, F, b.ffn_w2, F, M, D, F, er, st));
+  return 0;
+}
+
+// motion_embed + positional encoding -> residual stream; with the LN fold also the first block's operands (a row pass
+// of the LayerNorm kernel's cost: the embedding GEMM is all epilogue already and runs three times per step).
+// rows: rows of the GEMM; ln_rows: rows that enter the blocks (Influence: the h_i half, m_I follows);
+// dup: the rows are written a second time `rows` further down for the unconditional CFG half.
+static int run_embed(mmdm_handle* h, int ni, int rows, int ln_rows, int dup, int S, int T, cudaStream_t st) {
+  Net& n = h->net[ni];
+  Workspace& ws = h->ws;
+  const int D = n.w.D, kpad = h->cfg.kpad;
+  GemmEpi ee;
+  ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
+  ee.dup_row_offset = dup ? (long long)rows : 0;
+  MMDM_TRY(gemm(h, "gemm_embed", ws.xin, kpad, n.w.embed_w, kpad, rows, D, kpad, ee, st));
+  if (n.fold) {
+    const Mods m0 = block_mods(n, ws, 0);
+    const int Mb = dup ? 2 * ln_rows : ln_rows;   // rows entering the blocks = S * T
+    Scope sc(h, "ln_modulate", st);
+    if (n.w.kind == MMDM_NET_INTERACTION)
+      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, m0.xf, m0.ld_xf, ws.xf, ws.stat[0], S * T, st, next_dir(h)));
+    else
+      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, nullptr, 0, nullptr, ws.stat[0], S * T, st, next_dir(h)));
+  }
   return 0;
 }
 
@@ -401,10 +524,7 @@ static int run_denoiser(mmdm_handle* h, int ni, const float* x, int Bu, int dup,
     Scope sc(h, "pack_state", st);
     MMDM_TRY(launch_pack_state(x, Bu, T, nf, kpad, persons, ws.xin, st, x_pitch));
   }
-  GemmEpi ee;
-  ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
-  ee.dup_row_offset = dup ? (long long)Mu : 0;
-  MMDM_TRY(gemm(h, "gemm_embed", ws.xin, kpad, n.w.embed_w, kpad, Mu, D, kpad, ee, st));
+  MMDM_TRY(run_embed(h, ni, Mu, Mu, dup, S, T, st));
   for (int l = 0; l < n.w.L; ++l)
     MMDM_TRY(run_block(h, ni, l, ws.h, nullptr, S, T, l == n.w.L - 1 ? ws.xn : nullptr, st));
   GemmEpi ef;
@@ -472,9 +592,7 @@ static int run_mixer_nets(mmdm_handle* h, const float* x1, const float* x2, int 
   h->seq_persons = 2;
   MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bt, dup, 3, 1, st));
   MMDM_TRY(run_conditioning(h, 2, S, temb[2], step_ptr, st));
-  GemmEpi ee;
-  ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
-  MMDM_TRY(gemm(h, "gemm_embed", ws.xin, kpad, n.w.embed_w, kpad, 2 * M, D, kpad, ee, st));
+  MMDM_TRY(run_embed(h, 2, 2 * M, M, 0, S, T, st));
   const float* mI = ws.h + (size_t)M * D;
   for (int l = 0; l < n.w.L; ++l)
     MMDM_TRY(run_block(h, 2, l, ws.h, mI, S, T, l == n.w.L - 1 ? ws.hfin : nullptr, st));
@@ -628,6 +746,19 @@ int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_han
     }
     h->net[i].present = true;
     h->net[i].blocks.assign(w.blocks, w.blocks + w.L);
+    // LN fold: needs the composite conditioning tables (see include/mixermdm_b200.h) in the expected layout
+    if (w.comp0_w != nullptr) {
+      const bool ok = (size_t)w.comp0_n == comp_cols(w, 0) && w.comp0_b != nullptr && w.D % 64 == 0 &&
+                      (comp_cols(w, 1) == 0 || (w.comp1_w != nullptr && w.comp1_b != nullptr && (size_t)w.comp1_n == comp_cols(w, 1)));
+      if (!ok) {
+        set_last_error("mmdm_create: net %d: composite AdaLN tables do not match the network (comp0_n=%d, expected %zu; "
+                       "comp1_n=%d, expected %zu)", i, w.comp0_n, comp_cols(w, 0), w.comp1_n, comp_cols(w, 1));
+        delete h;
+        return -1;
+      }
+      const char* e = getenv("MMDM_LN_FOLD");   // 0 keeps the stand-alone LayerNorm kernel even when the tables are given
+      h->net[i].fold = !(e && e[0] == '0');
+    }
   }
   if (h->net[2].present && h->net[2].w.D != 512) {
     set_last_error("mmdm_create: the fused mix kernel expects a 512-wide Mixer (got %d)", h->net[2].w.D);
@@ -855,9 +986,7 @@ int mmdm_mixer_forward(mmdm_handle* h, const float* x1, const float* x2, const i
     MMDM_TRY(run_time_embed(h, 2, reinterpret_cast<const long long*>(timesteps), nullptr, Bx, ws.temb_dyn, st));
     MMDM_TRY(launch_build_maps(ws.map0, ws.map1, ws.tmap, S, 2, Bx, 0, 3, 1, st));
     MMDM_TRY(run_conditioning(h, 2, S, ws.temb_dyn, nullptr, st));
-    GemmEpi ee;
-    ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
-    MMDM_TRY(gemm(h, "gemm_embed", ws.xin, kpad, n.w.embed_w, kpad, 2 * M, D, kpad, ee, st));
+    MMDM_TRY(run_embed(h, 2, 2 * M, M, 0, S, T, st));
     const float* mI = ws.h + (size_t)M * D;
     for (int l = 0; l < n.w.L; ++l)
       MMDM_TRY(run_block(h, 2, l, ws.h, mI, S, T, l == n.w.L - 1 ? ws.hfin : nullptr, st));

@@ -10,6 +10,7 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace mmdm {
 
@@ -31,12 +32,17 @@ int num_sms() { return device_sm_count(); }
 // index of the row) is computed once per tile in RowCtx; the per-chunk fast path has no per-element guards.
 // ------------------------------------------------------------------------------------------------
 // modes whose fp32 output goes through the shared-memory transpose (full-line loads / stores)
-__host__ __device__ constexpr bool transposed_mode(int mode) { return mode == EPI_RESID || mode == EPI_EMBED_PE; }
+__host__ __device__ constexpr bool transposed_mode(int mode) { return mode_resid(mode) || mode_embed(mode); }
 
 struct RowCtx {
   int row;
   bool valid;
   int s, t;   // row = s * T + t (only for the modes that need it)
+  // LN-fold consumer: y = rho * acc + nrm * G_s[n] + Bc_s[n]   (nrm = -rho * mu)
+  float rho, nrm;
+  const float* gp;
+  const float* bp;
+  uint32_t g_smem, b_smem;   // the warp's staged G_s / Bc_s values of this row's sequence (chunk 0), 0: not staged
 };
 
 template <int MODE>
@@ -46,9 +52,28 @@ __device__ __forceinline__ RowCtx make_row_ctx(const GemmEpi& ep, int row, int M
   rc.valid = row < M;
   rc.s = 0;
   rc.t = 0;
-  if (MODE == EPI_BF16 || MODE == EPI_EMBED_PE || MODE == EPI_FINAL) {
+  rc.rho = 1.f;
+  rc.nrm = 0.f;
+  rc.gp = rc.bp = nullptr;
+  rc.g_smem = rc.b_smem = 0;
+  if (mode_bf16(MODE) || mode_embed(MODE) || MODE == EPI_FINAL || mode_ln_consumer(MODE)) {
     rc.s = row / ep.T;
     rc.t = row - rc.s * ep.T;
+  }
+  if (mode_ln_consumer(MODE) && rc.valid) {
+    // row statistics from the producer's partial sums, always added in slot order (bitwise reproducible)
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < ep.lnc_slots; ++k) {
+      const float2 p = __ldg(ep.lnc_stats + (size_t)k * ep.lnc_pitch + row);
+      s1 += p.x;
+      s2 += p.y;
+    }
+    const float mu = s1 * ep.lnc_inv_d;
+    const float var = fmaxf(fmaf(-mu, mu, s2 * ep.lnc_inv_d), 0.f);
+    rc.rho = rsqrtf(var + 1e-6f);
+    rc.nrm = -rc.rho * mu;
+    rc.gp = ep.lnc_g + (size_t)rc.s * ep.lnc_ld;
+    rc.bp = ep.lnc_b + (size_t)rc.s * ep.lnc_ld;
   }
   return rc;
 }
@@ -83,20 +108,21 @@ __device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const Row
   for (int j = 0; j < 32; ++j) {
     if (j >= nvalid) break;
     const int n = col0 + j;
-    const float x = v[j] + (ep.bias ? __ldg(ep.bias + n) : 0.f);
-    if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16 || MODE == EPI_QGELU_BF16) {
-      const float o = (MODE == EPI_GELU_BF16) ? MMDM_GELU1(x) : (MODE == EPI_QGELU_BF16) ? quick_gelu(x) : x;
-      if (MODE == EPI_BF16 && ep.vt_col0 >= 0 && n >= ep.vt_col0) {
+    const float x = mode_ln_consumer(MODE) ? fmaf(rc.rho, v[j], fmaf(rc.nrm, __ldg(rc.gp + n), __ldg(rc.bp + n)))
+                                           : v[j] + (ep.bias ? __ldg(ep.bias + n) : 0.f);
+    if (mode_bf16(MODE) || mode_gelu(MODE) || MODE == EPI_QGELU_BF16) {
+      const float o = mode_gelu(MODE) ? MMDM_GELU1(x) : (MODE == EPI_QGELU_BF16) ? quick_gelu(x) : x;
+      if (mode_bf16(MODE) && ep.vt_col0 >= 0 && n >= ep.vt_col0) {
         const int nn = n - ep.vt_col0, h = nn / ep.hd, d = nn - h * ep.hd;
         ep.vt[((size_t)(rc.s * ep.H + h) * ep.hd + d) * ep.Tp + rc.t] = __float2bfloat16_rn(o);
       } else {
         reinterpret_cast<__nv_bfloat16*>(ep.out)[(size_t)rc.row * ep.ldo + n] = __float2bfloat16_rn(o);
       }
-    } else if (MODE == EPI_RESID) {
+    } else if (mode_resid(MODE)) {   // (LN-fold producers never come here: launch_gemm requires the vector path)
       const float o = ep.resid[(size_t)rc.row * ep.ldo + n] + x;
       reinterpret_cast<float*>(ep.out)[(size_t)rc.row * ep.ldo + n] = o;
       if (ep.out_bf16) ep.out_bf16[(size_t)rc.row * ep.ldo + n] = __float2bfloat16_rn(o);
-    } else if (MODE == EPI_EMBED_PE) {
+    } else if (mode_embed(MODE)) {
       const float o = x + __ldg(ep.pe + (size_t)rc.t * ep.pe_ld + n);
       float* dst = reinterpret_cast<float*>(ep.out) + (size_t)rc.row * ep.ldo + n;
       *dst = o;
@@ -119,8 +145,57 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N,
                                                uint32_t bias_smem) {
   if (!rc.valid || col0 >= N) return;
-  if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || transposed_mode(MODE) || !ep.vec_ok) {   // FINAL rows are only 8-byte aligned in the scattered layout
+  if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || transposed_mode(MODE) || !ep.vec_ok ||
+      (mode_ln_consumer(MODE) && rc.g_smem == 0)) {   // FINAL rows are only 8-byte aligned in the scattered layout
     epilogue_chunk_edge<MODE>(ep, rc, col0, v, N);
+    return;
+  }
+  if (mode_ln_consumer(MODE)) {
+    // x = rho * acc + (nrm * G_s[n] + Bc_s[n]); G_s / Bc_s come from the warp's staged rows (epilogue_tile made sure this
+    // row's sequence is one of the two staged ones; bias_smem carries the chunk's byte offset inside them)
+    const f32x2 rho2 = pack2(rc.rho, rc.rho), nrm2 = pack2(rc.nrm, rc.nrm);
+    const uint32_t gs = rc.g_smem + bias_smem, bs = rc.b_smem + bias_smem;
+    const bool to_vt = mode_bf16(MODE) && ep.vt_col0 >= 0 && col0 >= ep.vt_col0;
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)rc.row * ep.ldo + col0);
+    __nv_bfloat16* dvt = nullptr;
+    if (to_vt) {   // V^T: the 32 columns of a chunk lie inside one head
+      const int nn = col0 - ep.vt_col0;
+      const int h = nn / ep.hd, d0 = nn - h * ep.hd;
+      dvt = ep.vt + ((size_t)(rc.s * ep.H + h) * ep.hd + d0) * ep.Tp + rc.t;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // 8 columns per step
+      f32x2 x[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 g4 = lds128(gs + (uint32_t)(2 * j + u) * 16), b4 = lds128(bs + (uint32_t)(2 * j + u) * 16);
+        x[2 * u] = fma2(rho2, pack2(v[8 * j + 4 * u], v[8 * j + 4 * u + 1]), fma2(nrm2, pack2(g4.x, g4.y), pack2(b4.x, b4.y)));
+        x[2 * u + 1] = fma2(rho2, pack2(v[8 * j + 4 * u + 2], v[8 * j + 4 * u + 3]), fma2(nrm2, pack2(g4.z, g4.w), pack2(b4.z, b4.w)));
+      }
+      if (mode_gelu(MODE)) {
+        uint4 pk;
+        pk.x = MMDM_GELU2(x[0]);
+        pk.y = MMDM_GELU2(x[1]);
+        pk.z = MMDM_GELU2(x[2]);
+        pk.w = MMDM_GELU2(x[3]);
+        dst[j] = pk;
+      } else {
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) unpack2(x[u], o[2 * u], o[2 * u + 1]);
+        if (to_vt) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dvt[(size_t)(8 * j + u) * ep.Tp] = __float2bfloat16_rn(o[u]);
+        } else {
+          uint4 pk;
+          pk.x = pack_bf16x2(o[0], o[1]);
+          pk.y = pack_bf16x2(o[2], o[3]);
+          pk.z = pack_bf16x2(o[4], o[5]);
+          pk.w = pack_bf16x2(o[6], o[7]);
+          dst[j] = pk;
+        }
+      }
+    }
     return;
   }
   float b[32];
@@ -229,21 +304,91 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& 
 // The same path serves the motion-embedding epilogue (MODE == EPI_EMBED_PE): the addend is the positional-encoding
 // row pe[row % T] instead of the residual row, and the result is optionally written a second time dup_row_offset
 // rows further down (the unconditional CFG half shares the embedding).
+// LN-fold producer state of a lane: in every chunk of a tile the lane touches the same 8 rows, m_base + 4 i + (lane >> 3)
+// (4 columns of each), so their sequence indices are computed once per tile and the row sums accumulate in registers.
+struct LnProd {
+  float s1[8], s2[8];
+  int sa, sb;   // sequences of the warp's first / last participating row (warp-uniform; a warp's 32 rows span two
+                // sequences at most unless T < 32): their scale values are fetched once per chunk, ahead of use
+  int bnd;      // first row of sequence sb
+  int lim;      // rows >= lim take no part (beyond M or beyond lnp_rows)
+};
+__device__ __forceinline__ int ln_prod_seq(const GemmEpi& ep, const LnProd& lp, int row) {
+  if (ep.lnp_T < 32) return row / ep.lnp_T;   // (more than two sequences per warp possible)
+  return row < lp.bnd ? lp.sa : lp.sb;
+}
+__device__ __forceinline__ void ln_prod_begin(const GemmEpi& ep, LnProd& lp, int m_base, int lane, int M) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) lp.s1[i] = lp.s2[i] = 0.f;
+  lp.lim = min(M, ep.lnp_rows);
+  lp.sa = min(m_base, lp.lim - 1) / ep.lnp_T;
+  lp.sb = min(m_base + 31, lp.lim - 1) / ep.lnp_T;
+  lp.bnd = (lp.sa + 1) * ep.lnp_T;
+}
+// scale values of this lane's 4 columns for the warp's two sequences (+ the duplicated rows' sequences)
+struct LnScale {
+  float4 a, b;
+};
+__device__ __forceinline__ LnScale ln_scale_fetch(const float* scale, int ld, int sa, int sb, int cg) {
+  LnScale r;
+  r.a = __ldg(reinterpret_cast<const float4*>(scale + (size_t)sa * ld + cg));
+  r.b = sb != sa ? __ldg(reinterpret_cast<const float4*>(scale + (size_t)sb * ld + cg)) : r.a;
+  return r;
+}
+__device__ __forceinline__ float4 ln_scale_pick(const LnScale& sc, const float* scale, int ld, int seq, int sa, int sb, int cg) {
+  if (seq == sa) return sc.a;
+  if (seq == sb) return sc.b;
+  return __ldg(reinterpret_cast<const float4*>(scale + (size_t)seq * ld + cg));   // T < 32 only
+}
+// partial sums of the last 64 columns -> stats[slot][row] (8 lanes hold 4 + 4 columns each of a row)
+__device__ __forceinline__ void ln_prod_flush(const GemmEpi& ep, LnProd& lp, int m_base, int lane, int slot) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = lp.s1[i], b = lp.s2[i];
+    a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4);
+    if ((lane & 7) == 0 && m_base + 4 * i + (lane >> 3) < lp.lim) {
+      float2* dst = ep.lnp_stats + (size_t)slot * ep.lnp_pitch + (m_base + 4 * i + (lane >> 3));
+      *dst = make_float2(a, b);
+      if (ep.dup_row_offset != 0) dst[ep.dup_row_offset] = make_float2(a, b);
+    }
+    lp.s1[i] = lp.s2[i] = 0.f;
+  }
+}
+__device__ __forceinline__ uint2 ln_prod_pack(const float4 o, const float4 sc) {
+  uint2 pk;   // bf16(h * (1 + scale))
+  pk.x = pack_bf16x2(fmaf(o.x, sc.x, o.x), fmaf(o.y, sc.y, o.y));
+  pk.y = pack_bf16x2(fmaf(o.z, sc.z, o.z), fmaf(o.w, sc.w, o.w));
+  return pk;
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_base, int lane, int col0,
-                                                       const float* v, int M, uint32_t stg, float4 bias4) {
+                                                       const float* v, int M, uint32_t stg, float4 bias4, LnProd& lp) {
 #pragma unroll
   for (int g = 0; g < 8; ++g)
     sts128(stg + (uint32_t)(lane * 8 + (g ^ (lane & 7))) * 16,
            make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
   __syncwarp();
   const int g = lane & 7;
+  // LN-fold producer: the scale values go out with the residual loads (behind the stores they would wait for L2)
+  LnScale sc0 = {}, sc1 = {}, sd0 = {}, sd1 = {};
+  const int cg = col0 + 4 * g;
+  if (mode_ln_producer(MODE)) {
+    sc0 = ln_scale_fetch(ep.lnp_scale0, ep.lnp_ld0, lp.sa, lp.sb, cg);
+    if (ep.lnp_out1 != nullptr) sc1 = ln_scale_fetch(ep.lnp_scale1, ep.lnp_ld1, lp.sa, lp.sb, cg);
+    if (mode_embed(MODE) && ep.dup_row_offset != 0) {
+      sd0 = ln_scale_fetch(ep.lnp_scale0, ep.lnp_ld0, lp.sa + ep.lnp_dup_seq, lp.sb + ep.lnp_dup_seq, cg);
+      if (ep.lnp_out1 != nullptr) sd1 = ln_scale_fetch(ep.lnp_scale1, ep.lnp_ld1, lp.sa + ep.lnp_dup_seq, lp.sb + ep.lnp_dup_seq, cg);
+    }
+  }
   // all residual loads first (the output may alias the residual, so loads cannot be hoisted over stores)
   float4 r4[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = m_base + 4 * i + (lane >> 3);
-    if (MODE == EPI_EMBED_PE)
+    if (mode_embed(MODE))
       r4[i] = (row < M) ? __ldg(reinterpret_cast<const float4*>(ep.pe + (size_t)(row % ep.T) * ep.pe_ld + col0 + 4 * g))
                         : make_float4(0.f, 0.f, 0.f, 0.f);
     else
@@ -260,13 +405,32 @@ __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_
       const float4 o = make_float4(r4[i].x + a.x + bias4.x, r4[i].y + a.y + bias4.y, r4[i].z + a.z + bias4.z,
                                    r4[i].w + a.w + bias4.w);
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = o;
-      if (MODE == EPI_EMBED_PE && ep.dup_row_offset != 0)
+      if (mode_embed(MODE) && ep.dup_row_offset != 0)
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off + (size_t)ep.dup_row_offset * ep.ldo) = o;
-      if (MODE == EPI_RESID && ep.out_bf16 != nullptr) {
+      if (mode_resid(MODE) && ep.out_bf16 != nullptr) {
         uint2 pk;
         pk.x = pack_bf16x2(o.x, o.y);
         pk.y = pack_bf16x2(o.z, o.w);
         *reinterpret_cast<uint2*>(ep.out_bf16 + off) = pk;
+      }
+      if (mode_ln_producer(MODE) && row < lp.lim) {
+        lp.s1[i] += (o.x + o.y) + (o.z + o.w);
+        lp.s2[i] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+        const int sq = ln_prod_seq(ep, lp, row);
+        *reinterpret_cast<uint2*>(ep.lnp_out0 + off) =
+            ln_prod_pack(o, ln_scale_pick(sc0, ep.lnp_scale0, ep.lnp_ld0, sq, lp.sa, lp.sb, cg));
+        if (ep.lnp_out1 != nullptr)
+          *reinterpret_cast<uint2*>(ep.lnp_out1 + off) =
+              ln_prod_pack(o, ln_scale_pick(sc1, ep.lnp_scale1, ep.lnp_ld1, sq, lp.sa, lp.sb, cg));
+        if (mode_embed(MODE) && ep.dup_row_offset != 0) {   // the other CFG half: same h, its own modulation
+          const size_t off2 = off + (size_t)ep.dup_row_offset * ep.ldo;
+          const int dq = ep.lnp_dup_seq;
+          *reinterpret_cast<uint2*>(ep.lnp_out0 + off2) =
+              ln_prod_pack(o, ln_scale_pick(sd0, ep.lnp_scale0, ep.lnp_ld0, sq + dq, lp.sa + dq, lp.sb + dq, cg));
+          if (ep.lnp_out1 != nullptr)
+            *reinterpret_cast<uint2*>(ep.lnp_out1 + off2) =
+                ln_prod_pack(o, ln_scale_pick(sd1, ep.lnp_scale1, ep.lnp_ld1, sq + dq, lp.sa + dq, lp.sb + dq, cg));
+        }
       }
     }
   }
@@ -351,31 +515,78 @@ __device__ __forceinline__ void bias_publish(const EpiBias<BN>& b, uint32_t bias
   __syncwarp();
 }
 
+// LN-fold consumer: G_s | Bc_s of the warp's (at most two) sequences over its column range, fetched one tile ahead and
+// published in the warp's shared-memory slice as [sequence a | b][G | Bc][128 floats] (2 KB; a row of a third sequence -
+// possible only for T < 32 - takes the generic per-element path)
+template <int BN>
+struct EpiLnc {
+  float4 v[4];
+};
+template <int BN>
+__device__ __forceinline__ EpiLnc<BN> lnc_fetch(const GemmEpi& ep, int row0, int n0, int c0, int cnt, int lane, int M, int N) {
+  EpiLnc<BN> r;
+  static_assert(BN / 64 <= 4, "one float4 per lane and block");
+  const int sa = min(row0, M - 1) / ep.T, sb = min(row0 + 31, M - 1) / ep.T;
+  const int col = n0 + c0 * 32 + lane * 4;
+  const bool on = lane < cnt * 8 && col + 4 <= N;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {   // block j: sequence (j >> 1 ? sb : sa), array (j & 1 ? Bc : G); lane = float4 inside it
+    const float* base = ((j & 1) ? ep.lnc_b : ep.lnc_g) + (size_t)((j & 2) ? sb : sa) * ep.lnc_ld;
+    r.v[j] = on ? __ldg(reinterpret_cast<const float4*>(base + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return r;
+}
+template <int BN>
+__device__ __forceinline__ void lnc_publish(const EpiLnc<BN>& r, uint32_t smem, int cnt, int lane) {
+  __syncwarp();   // the previous tile's readers are done
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sts128(smem + (uint32_t)(j * 32 + lane) * 16, r.v[j]);
+  __syncwarp();
+}
+
 template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0, int M, int N, uint32_t tmem_acc,
-                                              int q, int c0, int cnt, int lane, uint32_t stg, const EpiBias<BN>& bias) {
+                                              int q, int c0, int cnt, int lane, uint32_t stg, const EpiBias<BN>& bias,
+                                              RowCtx rc) {
   const uint32_t bias_smem = stg;   // non-residual modes: the staging slice holds the published bias
   constexpr int NCH = BN / 64;   // at most this many chunks of 32 columns per warp: chunks [c0, c0 + cnt)
-  const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);
+  if (mode_ln_consumer(MODE) && ep.vec_ok) {
+    const int row0 = m0 + q * 32;
+    const int sa = min(row0, M - 1) / ep.T, sb = min(row0 + 31, M - 1) / ep.T;
+    const int sel = rc.s == sa ? 0 : (rc.s == sb ? 1 : -1);
+    if (sel >= 0) {
+      rc.g_smem = stg + (uint32_t)sel * 1024u;
+      rc.b_smem = rc.g_smem + 512u;
+    }
+  }
   const uint32_t taddr = tmem_acc + (uint32_t)(c0 * 32) + ((uint32_t)(q * 32) << 16);
+  LnProd lp;
+  if (mode_ln_producer(MODE)) ln_prod_begin(ep, lp, m0 + q * 32, lane, M);
   uint32_t r[2][32];
   tmem_ld_32x32b_x32(taddr, r[0]);
   tmem_ld_wait();
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     if (c >= cnt) break;
-    if (c + 1 < cnt) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+    // (the LN-fold producers keep one TMEM buffer: their epilogue is bound by global memory and short of registers)
+    if (c + 1 < cnt && !mode_ln_producer(MODE)) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]);
     const int col0 = n0 + (c0 + c) * 32;
-    if (transposed_mode(MODE) && ep.vec_ok && col0 + 32 <= N)
-      epilogue_chunk_resid_t<MODE>(ep, m0 + q * 32, lane, col0, v, M, stg, bias.b[c]);
+    if (transposed_mode(MODE) && ep.vec_ok && col0 + 32 <= N) {
+      epilogue_chunk_resid_t<MODE>(ep, m0 + q * 32, lane, col0, v, M, stg, bias.b[c], lp);
+      // (a warp's chunks come in pairs that cover one 64-column statistics slot: c0 is even, cnt is even)
+      if (mode_ln_producer(MODE) && (c & 1)) ln_prod_flush(ep, lp, m0 + q * 32, lane, (col0 - 32) / kLnSlotCols);
+    }
     else if (MODE == EPI_FINAL && ep.final_vec_ok && col0 < N)
       epilogue_chunk_final_t(ep, m0 + q * 32, lane, col0, v, M, N, stg);
     else
-      epilogue_chunk<MODE>(ep, rc, col0, v, N, bias_smem + (uint32_t)c * 128);
-    if (c + 1 < cnt) tmem_ld_wait();
+      epilogue_chunk<MODE>(ep, rc, col0, v, N, mode_ln_consumer(MODE) ? (uint32_t)c * 128 : bias_smem + (uint32_t)c * 128);
+    if (c + 1 < cnt) {
+      if (mode_ln_producer(MODE)) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+      tmem_ld_wait();
+    }
   }
 }
 
@@ -497,19 +708,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     EpiBias<BN> bias = {}, bias_next = {};
-    if (!transposed_mode(MODE) && (int)blockIdx.x < num_tiles)
+    EpiLnc<BN> lnc_next = {};
+    if (!transposed_mode(MODE) && !mode_ln_consumer(MODE) && (int)blockIdx.x < num_tiles)
       bias_next = bias_fetch<BN, MODE>(ep, ((int)blockIdx.x % num_n) * BN, half * (BN / 64), lane, N);
+    if (mode_ln_consumer(MODE) && ep.vec_ok && (int)blockIdx.x < num_tiles)
+      lnc_next = lnc_fetch<BN>(ep, ((int)blockIdx.x / num_n) * C::BM + q * 32, ((int)blockIdx.x % num_n) * BN,
+                               half * (BN / 64), BN / 64, lane, M, N);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * C::BM;
       const int n0 = (tile % num_n) * BN;
+      if (mode_ln_consumer(MODE) && ep.vec_ok) {
+        lnc_publish<BN>(lnc_next, stg, BN / 64, lane);
+        const int nt = tile + (int)gridDim.x;
+        if (nt < num_tiles)
+          lnc_next = lnc_fetch<BN>(ep, (nt / num_n) * C::BM + q * 32, (nt % num_n) * BN, half * (BN / 64), BN / 64, lane, M, N);
+      }
       if (transposed_mode(MODE)) {
         bias = bias_fetch<BN, MODE>(ep, n0, half * (BN / 64), lane, N);   // in flight while waiting for the accumulator
-      } else if (MODE != EPI_FINAL) {   // (the output layer reads bias / std / mean per column group itself)
+      } else if (MODE != EPI_FINAL && !mode_ln_consumer(MODE)) {   // (the output layer reads bias / std / mean per column group itself)
         bias_publish<BN>(bias_next, stg, lane);
         if (tile + (int)gridDim.x < num_tiles)   // next tile's bias: its latency hides behind this tile
           bias_next = bias_fetch<BN, MODE>(ep, ((tile + (int)gridDim.x) % num_n) * BN, half * (BN / 64), lane, N);
       }
-      if (MODE == EPI_RESID && ep.vec_ok) {
+      if (mode_resid(MODE) && ep.vec_ok) {
         // pull this warp's share of the residual tile towards L2 while the MMAs of the tile are still running
         const int col = n0 + half * (BN / 2);
         if (col < N) {
@@ -522,10 +743,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);   // (LN fold: the row statistics load while we wait)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, half * (BN / 64), BN / 64, lane,
-                              stg, bias);
+                              stg, bias, rc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -541,6 +763,123 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 
 // ------------------------------------------------------------------------------------------------
+// Residual epilogue through TMA (CTA-pair kernel, EPI_RESID / EPI_RESID_LN).
+// The epilogue of the residual GEMMs moves 8 bytes per FLOP-free element (fp32 row in, fp32 row out) and was bound by
+// the serial instruction latency of its 8 warps: per 32 x 32 chunk ~700 instructions of address arithmetic, predicated
+// 16-byte loads / stores and the quarter-warp transpose, at ~15 cycles each. Here a warp's chunk of the residual
+// stream arrives by one bulk tensor copy (128B-swizzled, so that "thread = row" shared-memory accesses are conflict
+// free), is updated IN PLACE by the thread that owns the row and leaves by one bulk tensor store; the bf16 operand(s)
+// for the next GEMM leave the same way. Row clipping at M (and at lnp_rows for the bf16 operands) is the tensor map's.
+// Per warp: two 4 KB residual buffers (chunk c in buffer c & 1; the next chunk's tile is requested as soon as the
+// stores of the previous chunk have left its buffer - across tiles too, so the first chunk of a tile is in shared
+// memory long before its accumulator is) and one 2 KB buffer per bf16 output.
+// ------------------------------------------------------------------------------------------------
+struct EpiMaps {
+  CUtensorMap r, o, h0, h1;   // residual in, fp32 out: box 32 x 32, 128B swizzle; bf16 out: box 32 x 32, 64B swizzle
+};
+constexpr uint32_t kTmaEpiWarpBytes = 2 * 4096 + 2 * 2048;
+
+struct TmaEpi {
+  uint8_t* buf;    // the warp's slice: R0 | R1 | H0 | H1
+  uint64_t* bar;   // [2]: residual tile landed in R0 / R1
+  uint32_t ph;     // bit b: parity of the next completion of bar[b]
+};
+__device__ __forceinline__ void tma_epi_request(const EpiMaps& mp, const TmaEpi& te, int b, int col, int row) {   // one lane
+  mbar_arrive_expect_tx(&te.bar[b], 4096);
+  tma_load_2d(te.buf + b * 4096, &mp.r, &te.bar[b], col, row);
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, const EpiMaps& mp, TmaEpi& te, int m0, int n0, int M,
+                                                  uint32_t tmem_acc, int q, int c0, int cnt, int lane, int nxt_row0,
+                                                  int nxt_col0) {
+  const int row0 = m0 + q * 32, row = row0 + lane;
+  const uint32_t taddr = tmem_acc + (uint32_t)(c0 * 32) + ((uint32_t)(q * 32) << 16);
+  const uint32_t sbuf = smem_u32(te.buf);
+  constexpr bool LN = mode_ln_producer(MODE);
+  const bool copy16 = LN || ep.out_bf16 != nullptr;      // H0 in use
+  const bool dual = LN && ep.lnp_out1 != nullptr;        // H1 in use
+  bool ln_row = false;
+  const float* sc0 = nullptr;
+  const float* sc1 = nullptr;
+  float s1 = 0.f, s2 = 0.f;
+  if (LN) {
+    const int lim = min(M, ep.lnp_rows);
+    ln_row = row < lim;
+    const int sq = min(row, lim - 1) / ep.lnp_T;
+    sc0 = ep.lnp_scale0 + (size_t)sq * ep.lnp_ld0;
+    if (dual) sc1 = ep.lnp_scale1 + (size_t)sq * ep.lnp_ld1;
+  }
+  const int sw = lane & 7, sw2 = (lane >> 1) & 3;
+  uint32_t r[2][32];
+  tmem_ld_32x32b_x32(taddr, r[0]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= cnt) break;
+    const int b = c & 1;
+    const int col0 = n0 + (c0 + c) * 32;
+    if (c + 1 < cnt) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+    if (lane == 0) {
+      bulk_wait_group_read0();   // the previous chunk's stores have left shared memory ...
+      if (c + 1 < cnt) tma_epi_request(mp, te, b ^ 1, col0 + 32, row0);   // ... its buffer takes the next residual tile
+      else if (nxt_col0 >= 0) tma_epi_request(mp, te, b ^ 1, nxt_col0, nxt_row0);
+    }
+    __syncwarp();
+    mbar_wait(&te.bar[b], (te.ph >> b) & 1u);
+    te.ph ^= 1u << b;
+    const uint32_t R = sbuf + (uint32_t)b * 4096u + (uint32_t)lane * 128u;
+    const uint32_t H0 = sbuf + 8192u + (uint32_t)lane * 64u, H1 = H0 + 2048u;
+    const float4* bias4 = reinterpret_cast<const float4*>(ep.bias + col0);
+    uint2 k0 = make_uint2(0u, 0u), k1 = make_uint2(0u, 0u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t addr = R + ((uint32_t)(j ^ sw) << 4);
+      const float4 a = lds128(addr);
+      const float4 bb = ep.bias != nullptr ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 o = make_float4(a.x + __uint_as_float(r[b][4 * j]) + bb.x, a.y + __uint_as_float(r[b][4 * j + 1]) + bb.y,
+                                   a.z + __uint_as_float(r[b][4 * j + 2]) + bb.z, a.w + __uint_as_float(r[b][4 * j + 3]) + bb.w);
+      sts128(addr, o);
+      if (LN) {
+        s1 += (o.x + o.y) + (o.z + o.w);
+        s2 += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+      }
+      if (copy16) {
+        uint2 p0, p1 = make_uint2(0u, 0u);
+        if (LN) {
+          p0 = ln_prod_pack(o, __ldg(reinterpret_cast<const float4*>(sc0 + col0) + j));
+          if (dual) p1 = ln_prod_pack(o, __ldg(reinterpret_cast<const float4*>(sc1 + col0) + j));
+        } else {
+          p0.x = pack_bf16x2(o.x, o.y);
+          p0.y = pack_bf16x2(o.z, o.w);
+        }
+        if (j & 1) {   // 8 bf16 = one 16-byte slot of the 64B-swizzled row
+          const uint32_t slot = (uint32_t)((j >> 1) ^ sw2) << 4;
+          sts128u(H0 + slot, make_uint4(k0.x, k0.y, p0.x, p0.y));
+          if (dual) sts128u(H1 + slot, make_uint4(k1.x, k1.y, p1.x, p1.y));
+        } else {
+          k0 = p0;
+          k1 = p1;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&mp.o, sbuf + (uint32_t)b * 4096u, col0, row0);
+      if (copy16) tma_store_2d(&mp.h0, sbuf + 8192u, col0, row0);
+      if (dual) tma_store_2d(&mp.h1, sbuf + 10240u, col0, row0);
+      bulk_commit_group();
+    }
+    if (LN && (c & 1)) {   // two chunks = one 64-column statistics slot
+      if (ln_row) ep.lnp_stats[(size_t)((col0 - 32) / kLnSlotCols) * ep.lnp_pitch + row] = make_float2(s1, s2);
+      s1 = s2 = 0.f;
+    }
+    if (c + 1 < cnt) tmem_ld_wait();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2): one 256 x 256 output tile per pair of SMs. Each CTA loads its own 128 rows of
 // A and HALF of the B tile (128 of the 256 weight rows); tcgen05.mma.cta_group::2 reads both halves across the
 // pair, so a CTA pulls 32 KB instead of 48 KB through L2 per 64-wide k block - the 128 x 256 single-CTA kernel is
@@ -553,17 +892,19 @@ struct Gemm2Cfg {
   static constexpr int BM = 128;    // rows per CTA (256 per pair)
   static constexpr int BN = 256;
   static constexpr int BK = 64;
-  static constexpr int STAGES = 6;
+  static constexpr bool TMA_EPI = mode_resid(MODE);   // residual tiles through bulk tensor copies (epilogue_tile_tma)
+  static constexpr int STAGES = TMA_EPI ? 4 : 6;      // (96 KB of epilogue buffers take two stages' room)
   // Epilogue warps: 8 (two per TMEM lane quarter, 4 chunks of 32 columns each); the GELU epilogue costs ~20
   // instructions per element and paced FFN-1 at 55 % tensor-pipe activity, so it gets 12 (3 + 3 + 2 chunks).
-  static constexpr int EPI_WARPS = (MODE == EPI_GELU_BF16) ? 12 : 8;
+  static constexpr int EPI_WARPS = mode_gelu(MODE) ? 12 : 8;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   // per-warp staging: a 32 x 32 fp32 transpose slab for the full-line store modes, else just the bias slice
-  static constexpr uint32_t STG_WARP_BYTES = (transposed_mode(MODE) || MODE == EPI_FINAL) ? 4096 : 512;
+  static constexpr uint32_t STG_WARP_BYTES =
+      TMA_EPI ? kTmaEpiWarpBytes : (transposed_mode(MODE) || MODE == EPI_FINAL) ? 4096 : mode_ln_consumer(MODE) ? 2048 : 512;
   static constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG_WARP_BYTES;
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
 };
@@ -571,17 +912,20 @@ struct Gemm2Cfg {
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<MODE>::THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmEpi ep, int M, int N, int K) {
+                         const __grid_constant__ EpiMaps emaps, const GemmEpi ep, int M, int N, int K) {
   using C = Gemm2Cfg<MODE>;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+  // [pipeline stages][TMA epilogue: per-warp buffers, 1024-byte aligned][barriers, 256 B][other modes: per-warp staging]
+  uint8_t* const stg_ptr = smem + (size_t)C::STAGES * C::STAGE_BYTES + (C::TMA_EPI ? 0 : 256);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + (C::TMA_EPI ? C::STG_BYTES : 0));
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const uint32_t stg_base = smem_u32(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);
+  uint64_t* rbar = tempty_bar + 3;   // TMA epilogue: [8 warps][2] "residual tile landed" (fits the 256-byte barrier area at 4 stages)
+  const uint32_t stg_base = smem_u32(stg_ptr);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -616,6 +960,12 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (C::TMA_EPI) {
+      tma_prefetch_desc(&emaps.r);
+      tma_prefetch_desc(&emaps.o);
+      tma_prefetch_desc(&emaps.h0);
+      tma_prefetch_desc(&emaps.h1);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
@@ -626,6 +976,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * C::EPI_WARPS);   // the epilogue warps of both CTAs arrive on the leader's barrier
     }
+    if (C::TMA_EPI)
+      for (int i = 0; i < 2 * C::EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
@@ -705,6 +1057,10 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (ncols == BN) {
         c0 = NPART == 2 ? part * 4 : part * 3;
         cnt = NPART == 2 ? 4 : (part < 2 ? 3 : NCHUNK - 6);
+      } else if (mode_ln_producer(MODE) || C::TMA_EPI) {   // a quarter tile is one 64-column statistics slot (and an even
+                                                           // number of chunks for the TMA epilogue): one warp per lane quarter
+        c0 = 0;
+        cnt = part == 0 ? 2 : 0;
       } else {
         c0 = part;
         cnt = part < 2 ? 1 : 0;
@@ -714,21 +1070,58 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     const uint32_t stg = stg_base + (uint32_t)(warp - 4) * C::STG_WARP_BYTES;
+    TmaEpi te;
+    te.buf = stg_ptr + (size_t)(warp - 4) * C::STG_WARP_BYTES;
+    te.bar = rbar + 2 * (warp - 4);
+    te.ph = 0;
+    if (C::TMA_EPI && pair < num_items) {   // the first chunk's residual tile
+      int mi, ni, nc, c0n, cntn;
+      item_of(pair, mi, ni, nc);
+      my_chunks(nc, c0n, cntn);
+      if (cntn > 0 && lane == 0) tma_epi_request(emaps, te, 0, ni + c0n * 32, mi * (2 * C::BM) + (int)rank * C::BM + q * 32);
+    }
     EpiBias<BN> bias = {}, bias_next = {};
-    if (!transposed_mode(MODE) && pair < num_items) {
+    EpiLnc<BN> lnc_next = {};
+    if (!transposed_mode(MODE) && !mode_ln_consumer(MODE) && pair < num_items) {
       int mi, ni, nc, c0n, cntn;
       item_of(pair, mi, ni, nc);
       my_chunks(nc, c0n, cntn);
       bias_next = bias_fetch<BN, MODE>(ep, ni, c0n, lane, N);
+    }
+    if (mode_ln_consumer(MODE) && ep.vec_ok && pair < num_items) {
+      int mi, ni, nc, c0n, cntn;
+      item_of(pair, mi, ni, nc);
+      my_chunks(nc, c0n, cntn);
+      lnc_next = lnc_fetch<BN>(ep, mi * (2 * C::BM) + (int)rank * C::BM + q * 32, ni, c0n, cntn, lane, M, N);
     }
     for (int it = pair; it < num_items; it += npairs) {
       int m_idx, n0, ncols, c0, cnt;
       item_of(it, m_idx, n0, ncols);
       my_chunks(ncols, c0, cnt);
       const int m0 = m_idx * (2 * C::BM) + (int)rank * C::BM;
-      if (transposed_mode(MODE)) {
+      if (mode_ln_consumer(MODE) && ep.vec_ok) {
+        lnc_publish<BN>(lnc_next, stg, cnt, lane);
+        if (it + npairs < num_items) {
+          int mi, ni, nc, c0n, cntn;
+          item_of(it + npairs, mi, ni, nc);
+          my_chunks(nc, c0n, cntn);
+          lnc_next = lnc_fetch<BN>(ep, mi * (2 * C::BM) + (int)rank * C::BM + q * 32, ni, c0n, cntn, lane, M, N);
+        }
+      }
+      int nxt_row0 = 0, nxt_col0 = -1;   // TMA epilogue: the first chunk of this warp's next item
+      if (C::TMA_EPI && it + npairs < num_items) {
+        int mi, ni, nc, c0n, cntn;
+        item_of(it + npairs, mi, ni, nc);
+        my_chunks(nc, c0n, cntn);
+        if (cntn > 0) {
+          nxt_row0 = mi * (2 * C::BM) + (int)rank * C::BM + q * 32;
+          nxt_col0 = ni + c0n * 32;
+        }
+      }
+      if (C::TMA_EPI) {
+      } else if (transposed_mode(MODE)) {
         bias = bias_fetch<BN, MODE>(ep, n0, c0, lane, N);
-      } else if (MODE != EPI_FINAL) {
+      } else if (MODE != EPI_FINAL && !mode_ln_consumer(MODE)) {   // (LN-fold consumers: the bias is part of Bc_s)
         bias_publish<BN>(bias_next, stg, lane);
         if (it + npairs < num_items) {
           int mi, ni, nc, c0n, cntn;
@@ -737,7 +1130,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           bias_next = bias_fetch<BN, MODE>(ep, ni, c0n, lane, N);
         }
       }
-      if (MODE == EPI_RESID && ep.vec_ok && cnt > 0) {
+      if (mode_resid(MODE) && !C::TMA_EPI && ep.vec_ok && cnt > 0) {
         const int col = n0 + c0 * 32;
         if (col < N) {
           const int r = m0 + q * 32 + lane;
@@ -748,15 +1141,21 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       }
+      const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);   // (LN fold: the row statistics load while we wait)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (cnt > 0) epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias);
+      if (C::TMA_EPI) {
+        if (cnt > 0) epilogue_tile_tma<MODE>(ep, emaps, te, m0, n0, M, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, nxt_row0, nxt_col0);
+      } else if (cnt > 0) {
+        epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias, rc);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (C::TMA_EPI && lane == 0) bulk_wait_group0();   // the last stores have left shared memory and are complete
   }
 
   tc_fence_before();
@@ -787,10 +1186,27 @@ static int launch_tc2(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     MMDM_TRY(make_tensor_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B));
   }
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if (C::TMA_EPI) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t st32[1] = {(uint64_t)ep.ldo * 4}, st16[1] = {(uint64_t)ep.ldo * 2};
+    uint32_t box[2] = {32, 32};
+    MMDM_TRY(make_tensor_map(&em.r, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ep.resid, dims, st32, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    MMDM_TRY(make_tensor_map(&em.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ep.out, dims, st32, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    em.h0 = em.o;
+    em.h1 = em.o;
+    const void* b0 = mode_ln_producer(MODE) ? (const void*)ep.lnp_out0 : (const void*)ep.out_bf16;
+    if (mode_ln_producer(MODE)) dims[1] = (uint64_t)(ep.lnp_rows < M ? ep.lnp_rows : M);   // rows beyond get no operand
+    if (b0 != nullptr)
+      MMDM_TRY(make_tensor_map(&em.h0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b0, dims, st16, box, CU_TENSOR_MAP_SWIZZLE_64B));
+    if (mode_ln_producer(MODE) && ep.lnp_out1 != nullptr)
+      MMDM_TRY(make_tensor_map(&em.h1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.lnp_out1, dims, st16, box, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm_bf16_tn_2cta_kernel<MODE><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
+  gemm_bf16_tn_2cta_kernel<MODE><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, em, ep, M, N, K);
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -868,6 +1284,7 @@ template <int MODE>
 static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                        const GemmEpi& ep, cudaStream_t stream) {
   if (use_simt()) {
+    MMDM_REQUIRE(!mode_ln_producer(MODE), "gemm: the SIMT bring-up kernel has no LN-fold producer epilogue");
     dim3 grid((M + 127) / 128, (N + 31) / 32);
     gemm_simt_debug_kernel<MODE><<<grid, 128, 0, stream>>>(A, lda, W, ldw, ep, M, N, K);
     MMDM_CHECK_CUDA(cudaGetLastError());
@@ -875,7 +1292,9 @@ static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
   }
   // CTA pairs on 256x256 tiles for the big projections; 128x256 single-CTA tiles when N fills them but M is
   // small; 128x128 for narrow / ragged N (e.g. the 262-wide output layer)
-  if (N % 256 == 0 && M >= 512 && use_2cta()) return launch_tc2<MODE>(A, lda, W, ldw, M, N, K, ep, stream);
+  // (the residual modes' TMA epilogue needs 16-byte aligned rows; launch_gemm's vec_ok says so)
+  if (N % 256 == 0 && M >= 512 && use_2cta() && (!mode_resid(MODE) || (ep.vec_ok && ep.bias_ok16)))
+    return launch_tc2<MODE>(A, lda, W, ldw, M, N, K, ep, stream);
   if (N % 256 == 0 || N >= 1024) return launch_tc<256, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
   return launch_tc<128, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
 }
@@ -901,8 +1320,27 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
   e2.vec_ok = ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (ep.ldo % 8) == 0 &&
                (ep.resid == nullptr || (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0) &&
                (ep.out_bf16 == nullptr || (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0) &&
-               (ep.pe == nullptr || ((reinterpret_cast<uintptr_t>(ep.pe) & 15) == 0 && (ep.pe_ld % 4) == 0)))
+               (ep.pe == nullptr || ((reinterpret_cast<uintptr_t>(ep.pe) & 15) == 0 && (ep.pe_ld % 4) == 0)) &&
+               (!mode_ln_consumer(ep.mode) || ((reinterpret_cast<uintptr_t>(ep.lnc_g) & 15) == 0 &&
+                                               (reinterpret_cast<uintptr_t>(ep.lnc_b) & 15) == 0 && (ep.lnc_ld % 4) == 0)))
                   ? 1 : 0;
+  if (mode_ln_consumer(ep.mode)) {
+    MMDM_REQUIRE(ep.lnc_stats && ep.lnc_g && ep.lnc_b && ep.lnc_slots >= 1 && ep.lnc_slots * kLnSlotCols == K && ep.T >= 1 &&
+                     ep.lnc_pitch >= M,
+                 "gemm: LN-fold consumer needs statistics (K / 64 slots), G and Bc rows and the sequence length");
+    e2.lnc_inv_d = 1.0f / (float)K;
+  }
+  if (mode_ln_producer(ep.mode)) {
+    if (e2.lnp_rows <= 0 || e2.lnp_rows > M) e2.lnp_rows = M;
+    MMDM_REQUIRE(ep.lnp_stats && ep.lnp_scale0 && ep.lnp_out0 && ep.lnp_T >= 1 && (N % kLnSlotCols) == 0 && ep.ldo == N &&
+                     ep.lnp_pitch >= e2.lnp_rows + ep.dup_row_offset && (ep.lnp_ld0 % 4) == 0 && (ep.lnp_ld1 % 4) == 0 &&
+                     (reinterpret_cast<uintptr_t>(ep.lnp_scale0) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.lnp_scale1) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(ep.lnp_out0) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.lnp_out1) & 15) == 0 &&
+                     ep.out_bf16 == nullptr &&
+                     (ep.lnp_out1 == nullptr || ep.lnp_scale1 != nullptr) && e2.vec_ok,
+                 "gemm: LN-fold producer needs a dense, aligned (M, N %% 64 == 0) output, scale rows and a statistics buffer");
+  }
+  e2.bias_ok16 = 1;   // (bias alignment is required above)
   e2.final_vec_ok = (ep.mode == EPI_FINAL && (reinterpret_cast<uintptr_t>(ep.out) & 7) == 0 && (ep.nfeats % 2) == 0) ? 1 : 0;
   switch (ep.mode) {
     case EPI_BF16:
@@ -920,6 +1358,17 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
     case EPI_F32: return launch_mode<EPI_F32>(A, lda, W, ldw, M, N, K, e2, stream);
     case EPI_SIGMOID_F32: return launch_mode<EPI_SIGMOID_F32>(A, lda, W, ldw, M, N, K, e2, stream);
     case EPI_QGELU_BF16: return launch_mode<EPI_QGELU_BF16>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_BF16_LN:
+      if (ep.vt_col0 >= 0)
+        MMDM_REQUIRE((ep.vt_col0 % 32) == 0 && (ep.hd % 32) == 0 && ep.vt != nullptr, "gemm: V^T split must be 32-aligned");
+      return launch_mode<EPI_BF16_LN>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_GELU_BF16_LN: return launch_mode<EPI_GELU_BF16_LN>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_RESID_LN:
+      MMDM_REQUIRE(ep.resid != nullptr, "gemm: residual pointer missing");
+      return launch_mode<EPI_RESID_LN>(A, lda, W, ldw, M, N, K, e2, stream);
+    case EPI_EMBED_PE_LN:
+      MMDM_REQUIRE(ep.pe != nullptr, "gemm: pe table missing");
+      return launch_mode<EPI_EMBED_PE_LN>(A, lda, W, ldw, M, N, K, e2, stream);
     default: break;
   }
   set_last_error("gemm: unknown epilogue mode %d", ep.mode);

@@ -14,7 +14,26 @@ enum EpiMode : int {
   EPI_F32 = 5,        // out_f32  = acc + bias                         (AdaLN conditioning GEMM)
   EPI_SIGMOID_F32 = 6,  // out_f32 = sigmoid(acc + bias)               (Influence head, influence.py:120-125)
   EPI_QGELU_BF16 = 7,   // out_bf16 = x * sigmoid(1.702 x), x = acc + bias (CLIP's QuickGELU: text tower MLP)
+  // ---- AdaLN folded into the GEMMs on either side of it ("LN fold", see GemmEpi::lnp_* / lnc_*) ----------------
+  EPI_BF16_LN = 8,       // EPI_BF16 on the operand bf16(h (1+scale)): out = rho (acc - mu G_s) + Bc_s
+  EPI_GELU_BF16_LN = 9,  // EPI_GELU_BF16, same
+  EPI_RESID_LN = 10,     // EPI_RESID that also emits bf16(h (1+scale_s)) for the next AdaLN site(s) + row sums
+  EPI_EMBED_PE_LN = 11,  // EPI_EMBED_PE, same
 };
+
+// AdaLN (reference models/utils/layers.py:15-25): xn = (h - mu) rho (1 + scale_s) + shift_s feeds a Linear W, c:
+//   y[r, n] = rho_r * sum_k [h[r,k] (1+scale_s[k])] W[n,k]  -  rho_r mu_r G_s[n]  +  Bc_s[n]
+//   G_s[n] = sum_k (1+scale_s[k]) W[n,k],   Bc_s[n] = sum_k shift_s[k] W[n,k] + c[n]       (s = sequence of row r)
+// so the GEMM that WRITES h can emit the bf16 operand h (1+scale_s) (no row statistics needed for that) together with
+// per-row partial sums, and the GEMM that READS it applies rho, mu, G, Bc in its epilogue: the stand-alone
+// LayerNorm pass over the fp32 residual stream (one read + one write of the activation per site) disappears.
+__host__ __device__ constexpr bool mode_resid(int m) { return m == EPI_RESID || m == EPI_RESID_LN; }
+__host__ __device__ constexpr bool mode_embed(int m) { return m == EPI_EMBED_PE || m == EPI_EMBED_PE_LN; }
+__host__ __device__ constexpr bool mode_bf16(int m) { return m == EPI_BF16 || m == EPI_BF16_LN; }
+__host__ __device__ constexpr bool mode_gelu(int m) { return m == EPI_GELU_BF16 || m == EPI_GELU_BF16_LN; }
+__host__ __device__ constexpr bool mode_ln_producer(int m) { return m == EPI_RESID_LN || m == EPI_EMBED_PE_LN; }
+__host__ __device__ constexpr bool mode_ln_consumer(int m) { return m == EPI_BF16_LN || m == EPI_GELU_BF16_LN; }
+constexpr int kLnSlotCols = 64;   // columns per partial-sum slot
 
 struct GemmEpi {
   int mode = EPI_BF16;
@@ -37,10 +56,31 @@ struct GemmEpi {
   const float* mean = nullptr;
   int nfeats = 0;
   int persons_per_row = 2;               // 2: sequences alternate persons (s&1); 1: plain (s*T+t)*nfeats
+  // LN-fold producer (EPI_RESID_LN / EPI_EMBED_PE_LN; N = latent dim, a multiple of 64; out pitch = ldo for all):
+  const float* lnp_scale0 = nullptr;     // AdaLN scale rows of the next site: scale0[s * lnp_ld0 + k], s = row / lnp_T
+  int lnp_ld0 = 0;
+  __nv_bfloat16* lnp_out0 = nullptr;     // bf16(h * (1 + scale0))
+  const float* lnp_scale1 = nullptr;     // optional second site fed by the same rows (SA of a stream + CA-KV of its partner)
+  int lnp_ld1 = 0;
+  __nv_bfloat16* lnp_out1 = nullptr;
+  float2* lnp_stats = nullptr;           // [N / 64][lnp_pitch]: (sum h, sum h^2) of a row over the slot's 64 columns
+  long long lnp_pitch = 0;
+  int lnp_T = 1;
+  int lnp_rows = 0;                      // rows >= lnp_rows write h only (Influence: the m_I half of the embed GEMM)
+  int lnp_dup_seq = 0;                   // EPI_EMBED_PE_LN with dup_row_offset: sequence offset of the duplicated rows
+  // LN-fold consumer (EPI_BF16_LN / EPI_GELU_BF16_LN; uses T): K = latent dim of the normalised rows
+  const float2* lnc_stats = nullptr;     // [lnc_slots][lnc_pitch]
+  long long lnc_pitch = 0;
+  int lnc_slots = 0;
+  float lnc_inv_d = 0.f;
+  const float* lnc_g = nullptr;          // G_s[n] = lnc_g[s * lnc_ld + n]
+  const float* lnc_b = nullptr;          // Bc_s[n] (bias included; GemmEpi::bias is ignored)
+  int lnc_ld = 0;
   // Walk the output tiles from the last row block down (CTA-pair kernel only). The engine alternates the direction
   // from launch to launch so that a kernel starts on the rows its producer wrote last, which are still in L2.
   int rev = 0;
   int split_tail = 0;                    // set by launch_gemm: cut a short last wave into quarter tiles (CTA-pair kernel)
+  int bias_ok16 = 0;                     // set by launch_gemm
   int vec_ok = 0;                        // set by launch_gemm: pointers/pitches allow 16-byte vector access
   int final_vec_ok = 0;                  // set by launch_gemm: EPI_FINAL rows allow 8-byte vector stores
 };

@@ -128,6 +128,110 @@ int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// LN fold, first block of a network: the rows come from the embedding GEMM, whose epilogue knows nothing of the fold,
+// so this pass emits what the residual GEMMs emit for the later blocks (gemm.cuh): out_m = bf16(h * (1 + scale_m[s])) for
+// one or two AdaLN sites and the per-row (sum h, sum h^2) of every 64-column slot. Same traffic as ln_modulate.
+// ------------------------------------------------------------------------------------------------
+template <int NV, bool DUAL>
+__global__ void __launch_bounds__(128)
+ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq, int run_len, int rev,
+                     const float* __restrict__ sc0, int ld0, __nv_bfloat16* __restrict__ out0,
+                     const float* __restrict__ sc1, int ld1, __nv_bfloat16* __restrict__ out1,
+                     float2* __restrict__ stats, long long pitch) {
+  constexpr int D = NV * 128;
+  constexpr int NM = DUAL ? 2 : 1;
+  extern __shared__ float4 ln_smem[];   // [4 warps][NM][D/4]: 1 + scale
+  int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (task >= S * runs_per_seq) return;
+  if (rev) task = S * runs_per_seq - 1 - task;
+  const int s = task / runs_per_seq;
+  const int t0 = (task - s * runs_per_seq) * run_len;
+  const int t1 = min(T, t0 + run_len);
+  if (t0 >= t1) return;
+  float4* ms = ln_smem + (size_t)(threadIdx.x >> 5) * (NM * (D / 4));
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    const float4* psc = reinterpret_cast<const float4*>((m == 0 ? sc0 : sc1) + (size_t)s * (m == 0 ? ld0 : ld1));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 a = __ldg(psc + i * 32 + lane);
+      a.x += 1.f; a.y += 1.f; a.z += 1.f; a.w += 1.f;
+      ms[m * (D / 4) + i * 32 + lane] = a;
+    }
+  }
+  __syncwarp();
+  const float4* src = reinterpret_cast<const float4*>(h + ((size_t)s * T + t0) * D);
+  float4 v[NV], nx[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = src[i * 32 + lane];
+  for (int t = t0; t < t1; ++t) {
+    if (t + 1 < t1) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nx[i] = src[(size_t)(t + 1 - t0) * (D / 4) + i * 32 + lane];
+    }
+    const size_t row = (size_t)s * T + t;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {   // lanes 0-15 hold slot 2i, lanes 16-31 slot 2i + 1
+      float a = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      float b = fmaf(v[i].x, v[i].x, v[i].y * v[i].y) + fmaf(v[i].z, v[i].z, v[i].w * v[i].w);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((lane & 15) == 0) stats[(size_t)(2 * i + (lane >> 4)) * pitch + row] = make_float2(a, b);
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      uint2* dst = reinterpret_cast<uint2*>((m == 0 ? out0 : out1) + row * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 a = ms[m * (D / 4) + i * 32 + lane];
+        uint2 pk;
+        pk.x = pack_bf16x2(v[i].x * a.x, v[i].y * a.y);
+        pk.y = pack_bf16x2(v[i].z * a.z, v[i].w * a.w);
+        dst[i * 32 + lane] = pk;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = nx[i];
+  }
+}
+
+template <int NV>
+static void launch_ln_fold_first_t(const float* h, int S, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
+                                   const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch, int rev,
+                                   cudaStream_t stream) {
+  const int runs = (T + 23) / 24;
+  const int run_len = (T + runs - 1) / runs;
+  const int tasks = S * runs;
+  const int blocks = (tasks + 3) / 4;
+  const size_t smem1 = (size_t)4 * NV * 128 * sizeof(float);
+  if (out1 != nullptr)
+    ln_fold_first_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, sc1, ld1, out1, stats, pitch);
+  else
+    ln_fold_first_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, nullptr, 0, nullptr, stats, pitch);
+}
+
+int launch_ln_fold_first(const float* h, int M, int D, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
+                         const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch,
+                         cudaStream_t stream, int rev) {
+  MMDM_REQUIRE(D == 128 || D == 256 || D == 512 || D == 1024, "ln_fold_first: unsupported latent dim %d", D);
+  MMDM_REQUIRE((ld0 % 4) == 0 && (out1 == nullptr || (ld1 % 4) == 0), "ln_fold_first: scale pitch %% 4");
+  MMDM_REQUIRE(T > 0 && M % T == 0 && pitch >= M && stats != nullptr, "ln_fold_first: M=%d is not a whole number of T=%d row sequences", M, T);
+  const int S = M / T;
+  switch (D) {   // (32 KB of shared memory at most: no attribute needed)
+    case 128: launch_ln_fold_first_t<1>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
+    case 256: launch_ln_fold_first_t<2>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
+    case 512: launch_ln_fold_first_t<4>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
+    default: launch_ln_fold_first_t<8>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
+  }
+  MMDM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // E[s, :] = bf16( SiLU( temb[step, :] + text[text_row[s], :] ) )    (AdaLN input: layers.py:9-11 with
 // in2in.py:414-424 / mixermdm.py:677-682). `step` is read from device memory so the launch can be
 // replayed from a CUDA graph for every DDIM step.
@@ -140,7 +244,9 @@ __global__ void cond_silu_kernel(const float* __restrict__ temb, const int* __re
   const int s = idx / D, d = idx - s * D;
   const int trow = step_ptr ? *step_ptr : temb_idx[s];
   const float x = temb[(size_t)trow * D + d] + text[(size_t)text_row[s] * D + d];
-  E[idx] = __float2bfloat16_rn(x / (1.0f + expf(-x)));
+  const __nv_bfloat16 e = __float2bfloat16_rn(x / (1.0f + expf(-x)));
+  E[(size_t)s * 2 * D + d] = e;       // rows are [e | e], pitch 2D (see engine.cu run_conditioning)
+  E[(size_t)s * 2 * D + D + d] = e;
 }
 
 int launch_cond_silu(const float* temb, const int* temb_idx, const int* step_ptr, const float* text,

@@ -9,7 +9,13 @@ int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, i
                        __nv_bfloat16* out0, const float* mod1, int ld_mod1, __nv_bfloat16* out1,
                        cudaStream_t stream, int rev = 0);
 
-// E[s,:] = bf16(SiLU(temb[trow,:] + text[text_row[s],:]))
+// LN fold, first block: out_m = bf16(h * (1 + sc_m[s, :])) (one or two sites) + per-row (sum, sum of squares) per 64-column
+// slot, stats[slot * pitch + row] - what the residual GEMMs' EPI_RESID_LN epilogue emits for the later blocks
+int launch_ln_fold_first(const float* h, int M, int D, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
+                         const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch,
+                         cudaStream_t stream, int rev = 0);
+
+// E[s, 0:D] = E[s, D:2D] = bf16(SiLU(temb[trow,:] + text[text_row[s],:]))   (row pitch 2D)
 // trow = step_ptr ? *step_ptr : temb_idx[s]
 int launch_cond_silu(const float* temb, const int* temb_idx, const int* step_ptr, const float* text,
                      const int* text_row, int S, int D, __nv_bfloat16* E, cudaStream_t stream);

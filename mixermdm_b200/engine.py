@@ -36,6 +36,8 @@ class NetWeights(C.Structure):
         ("time_w0", C.c_void_p), ("time_b0", C.c_void_p), ("time_w2", C.c_void_p), ("time_b2", C.c_void_p),
         ("text_w", C.c_void_p), ("text_b", C.c_void_p),
         ("blocks", C.POINTER(BlockWeights)),
+        ("comp0_w", C.c_void_p), ("comp0_b", C.c_void_p), ("comp0_n", C.c_int32),
+        ("comp1_w", C.c_void_p), ("comp1_b", C.c_void_p), ("comp1_n", C.c_int32),
     ]
 
 
@@ -111,6 +113,9 @@ class _Packer:
     def __init__(self, device):
         self.device = device
         self.keep = []
+        # MMDM_LN_FOLD=1: build the composite tables of the LN fold; without them the engine runs the stand-alone
+        # LayerNorm kernel (the default while the fold does not beat it)
+        self.fold = os.environ.get("MMDM_LN_FOLD", "0") == "1"
 
     def bf16(self, t):
         t = t.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
@@ -124,6 +129,30 @@ class _Packer:
 
     def p(self, t):
         return C.c_void_p(t.data_ptr())
+
+    def composite(self, blocks, sites, D):
+        """Composite conditioning table of the LN fold for `sites` = [(norm getter, linear getter)], per block.
+        Load-time weight folding (like folding a BatchNorm into a convolution): for the Linear (W, c) behind an AdaLN
+        whose modulation is [scale; shift] = Wada E + bada, the rows [W Wsc; W Wsh] and constants
+        [W (1 + bsc); W bsh + c], evaluated in fp64 on the bf16 values the kernels multiply with, stored as bf16
+        pairs [hi | lo] along K. Returns ((sum 2N, 2D) bf16, (sum 2N) fp32)."""
+        rows, consts = [], []
+        rnd = lambda t: t.detach().to(device=self.device, dtype=torch.bfloat16).double()
+        for blk in blocks:
+            for norm_of, lin_of in sites:
+                ada = norm_of(blk).emb_layers[1]
+                wada, bada = rnd(ada.weight), ada.bias.detach().to(self.device).double()
+                lw, lb = lin_of(blk)
+                W, c = rnd(lw), lb.detach().to(self.device).double()
+                rows += [W @ wada[:D], W @ wada[D:]]
+                consts += [W @ (1.0 + bada[:D]), W @ bada[D:] + c]
+        full = torch.cat(rows, 0)
+        hi = full.to(torch.bfloat16)
+        lo = (full - hi.double()).to(torch.bfloat16)
+        table = torch.cat([hi, lo], 1).contiguous()
+        const = torch.cat(consts, 0).float().contiguous()
+        self.keep += [table, const]
+        return table, const
 
     def pack_net(self, kind, net, blocks, with_out):
         """net: module with motion_embed/text_embed/embed_timestep/sequence_pos_encoder; blocks: ModuleList"""
@@ -160,6 +189,28 @@ class _Packer:
             w.ada1_w, w.ada1_b, w.ada1_n = self.p(a1w), self.p(a1b), a1w.shape[0]
         else:
             w.ada1_w, w.ada1_b, w.ada1_n = None, None, 0
+        # LN fold (include/mixermdm_b200.h, "composite conditioning tables"): the Linear behind every AdaLN site,
+        # in the same per-block order as g0 / g1. The Influence xf_norm has no entry (its rows, m_I, come from no GEMM
+        # of the block), so it is absent from c1 there.
+        sa_lin = lambda b: (b.sa_block.attention.in_proj_weight, b.sa_block.attention.in_proj_bias)
+        ffn_lin = lambda b: (b.ffn.linear1.weight, b.ffn.linear1.bias)
+        caq_lin = lambda b: (b.ca_block.attention.in_proj_weight[:D], b.ca_block.attention.in_proj_bias[:D])
+        cakv_lin = lambda b: (b.ca_block.attention.in_proj_weight[D:], b.ca_block.attention.in_proj_bias[D:])
+        if kind == NET_INFLUENCE:
+            c0 = [(g0[0], sa_lin)]
+            c1 = [(g1[0], caq_lin), (g1[2], ffn_lin)]
+        elif kind == NET_INTERACTION:
+            c0 = [(g0[0], sa_lin), (g0[1], ffn_lin)]
+            c1 = [(g1[0], caq_lin), (g1[1], cakv_lin)]
+        else:
+            c0 = [(g0[0], sa_lin), (g0[1], ffn_lin)]
+            c1 = []
+        if self.fold and D % 64 == 0:
+            cw, cb = self.composite(blocks, c0, D)
+            w.comp0_w, w.comp0_b, w.comp0_n = self.p(cw), self.p(cb), cw.shape[0]
+            if c1:
+                cw, cb = self.composite(blocks, c1, D)
+                w.comp1_w, w.comp1_b, w.comp1_n = self.p(cw), self.p(cb), cw.shape[0]
         ew = torch.zeros(D, KPAD, dtype=torch.float32)
         ew[:, :NFEATS] = net.motion_embed.weight.detach().float().cpu()
         w.embed_w, w.embed_b = self.p(self.bf16(ew)), self.p(self.f32(net.motion_embed.bias))

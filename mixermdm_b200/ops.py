@@ -16,8 +16,12 @@ def _req(t, dtype, name):
 
 
 def linear_bf16(a, w, *, mode, out, bias=None, resid=None, out_bf16=None, vt=None, vt_col0=-1, T=1, H=1, hd=1,
-                Tp=1, pe=None, dup_row_offset=0, std=None, mean=None, nfeats=0, persons_per_row=2):
-    """out = epilogue(a @ w.T). a: (M,K) bf16, w: (N,K) bf16 (nn.Linear layout), rows may be strided."""
+                Tp=1, pe=None, dup_row_offset=0, std=None, mean=None, nfeats=0, persons_per_row=2,
+                ln_produce=None, ln_consume=None):
+    """out = epilogue(a @ w.T). a: (M,K) bf16, w: (N,K) bf16 (nn.Linear layout), rows may be strided.
+    ln_produce (EPI_RESID_LN / EPI_EMBED_PE_LN): dict(scale0, out0, stats, T[, scale1, out1, rows, dup_seq]) - scale*: (S, >=N)
+    fp32 views of the AdaLN scale rows, out*: (M', N) bf16, stats: (N // 64, M', 2) fp32.
+    ln_consume (EPI_BF16_LN / EPI_GELU_BF16_LN): dict(stats, g, b) - g / b: (S, N) fp32 views with one row pitch; pass T."""
     lib = _lib.load()
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
@@ -41,6 +45,18 @@ def linear_bf16(a, w, *, mode, out, bias=None, resid=None, out_bf16=None, vt=Non
     ep.mean = ptr(mean).value if mean is not None else None
     ep.nfeats = nfeats
     ep.persons_per_row = persons_per_row
+    if ln_produce is not None:
+        lp = ln_produce
+        ep.lnp_scale0, ep.lnp_ld0, ep.lnp_out0 = ptr(lp["scale0"]).value, lp["scale0"].stride(0), ptr(lp["out0"]).value
+        if lp.get("scale1") is not None:
+            ep.lnp_scale1, ep.lnp_ld1, ep.lnp_out1 = ptr(lp["scale1"]).value, lp["scale1"].stride(0), ptr(lp["out1"]).value
+        ep.lnp_stats, ep.lnp_pitch = ptr(lp["stats"]).value, lp["stats"].stride(0) // 2
+        ep.lnp_T, ep.lnp_rows, ep.lnp_dup_seq = lp["T"], lp.get("rows", 0), lp.get("dup_seq", 0)
+    if ln_consume is not None:
+        lc = ln_consume
+        assert lc["g"].stride(0) == lc["b"].stride(0)
+        ep.lnc_stats, ep.lnc_pitch = ptr(lc["stats"]).value, lc["stats"].stride(0) // 2
+        ep.lnc_g, ep.lnc_b, ep.lnc_ld = ptr(lc["g"]).value, ptr(lc["b"]).value, lc["g"].stride(0)
     with torch.cuda.device(a.device):   # kernels launch on the tensors' device, whatever the current one is
         check(lib.mmdm_linear_bf16(ptr(a), C.c_int(a.stride(0)), ptr(w), C.c_int(w.stride(0)), M, N, K, C.byref(ep),
                                    cur_stream()), "mmdm_linear_bf16")

@@ -56,7 +56,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mixermdm_b200.h but not exported"
-    assert lib.mmdm_abi_version() == 3
+    assert lib.mmdm_abi_version() == 4
     assert ctypes.sizeof(_lib.Epilogue) % 8 == 0
 
 

@@ -68,6 +68,133 @@ def test_linear_gelu_resid_f32(ops, M, D, F):
     assert _relerr(o32, x.float() @ w1.float().t() + b1) < 1e-5
 
 
+def _ln_ref(h, scale, shift, T):
+    """AdaLN body in fp32 (reference models/utils/layers.py:15-25), scale / shift rows per sequence s = row // T"""
+    seq = torch.arange(h.shape[0], device=h.device) // T
+    xn = torch.nn.functional.layer_norm(h, (h.shape[1],), eps=1e-6)
+    return xn * (1 + scale[seq]) + shift[seq]
+
+
+# LN fold: a residual GEMM that also emits bf16(h (1 + scale)) + row sums, then the consuming GEMM that finishes the
+# normalisation in its epilogue, against LayerNorm + modulation + Linear in fp32. (8, 300, 1024, .): CTA-pair kernel with
+# quarter tiles in the producer (2400 rows: 10 pair tiles x 4 = 40 < 74 -> none; 4864-row case below has them);
+# (3, 24, 128, .): single-CTA 128-wide tiles, several sequences per warp.
+@pytest.mark.parametrize("S,T,D,N2", [(4, 37, 256, 768), (8, 300, 1024, 3072), (16, 304, 1024, 2048), (3, 24, 128, 384),
+                                      (16, 300, 512, 1024)])
+@pytest.mark.parametrize("dual", [False, True])
+def test_ln_fold_resid_producer_and_consumers(ops, S, T, D, N2, dual):
+    from mixermdm_b200._lib import EPI_RESID_LN, EPI_BF16_LN, EPI_GELU_BF16_LN
+    M = S * T
+    a = _rand((M, D), 31, dtype=torch.bfloat16)
+    w = _rand((D, D), 32, 1 / math.sqrt(D), dtype=torch.bfloat16)
+    b = _rand((D,), 33)
+    h = _rand((M, D), 34) * 2.0 + 0.4 + 0.3 * _rand((M, 1), 35)   # rows with a mean of a few tenths of their spread
+    mods = _rand((S, 4 * D), 36, 0.3)   # [scale0 | shift0 | scale1 | shift1]
+    sc0, sh0, sc1, sh1 = mods[:, :D], mods[:, D:2 * D], mods[:, 2 * D:3 * D], mods[:, 3 * D:]
+    stats = torch.full((D // 64, M, 2), float("nan"), device="cuda")
+    hg0 = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    hg1 = torch.empty(M, D, dtype=torch.bfloat16, device="cuda") if dual else None
+    h_out = h.clone()
+    lp = dict(scale0=sc0, out0=hg0, stats=stats, T=T)
+    if dual:
+        lp.update(scale1=sc1, out1=hg1)
+    ops.linear_bf16(a, w, mode=EPI_RESID_LN, out=h_out, bias=b, resid=h_out, ln_produce=lp)
+    torch.cuda.synchronize()
+    ref_h = h + a.float() @ w.float().t() + b
+    assert _relerr(h_out, ref_h) < 1e-5
+    seq = torch.arange(M, device="cuda") // T
+    assert _relerr(hg0, ref_h * (1 + sc0[seq])) < 4e-3
+    ref_stats = torch.stack([ref_h.view(M, D // 64, 64).sum(-1).t(), (ref_h ** 2).view(M, D // 64, 64).sum(-1).t()], -1)
+    assert (stats - ref_stats).abs().max().item() < 2e-3 and _relerr(stats, ref_stats) < 1e-5
+    w2 = _rand((N2, D), 37, 1 / math.sqrt(D), dtype=torch.bfloat16)
+    c2 = _rand((N2,), 38)
+    cases = [(hg0, sc0, sh0)] + ([(hg1, sc1, sh1)] if dual else [])
+    for hg, sc, sh in cases:
+        gb = torch.cat([(1 + sc) @ w2.float().t(), sh @ w2.float().t() + c2], 1).contiguous()
+        lc = dict(stats=stats, g=gb[:, :N2], b=gb[:, N2:])
+        ref = _ln_ref(ref_h, sc, sh, T) @ w2.float().t() + c2
+        out = torch.empty(M, N2, dtype=torch.bfloat16, device="cuda")
+        ops.linear_bf16(hg, w2, mode=EPI_BF16_LN, out=out, T=T, ln_consume=lc)
+        assert _relerr(out, ref) < 8e-3
+        ops.linear_bf16(hg, w2, mode=EPI_GELU_BF16_LN, out=out, T=T, ln_consume=lc)
+        assert _relerr(out, torch.nn.functional.gelu(ref)) < 8e-3
+    if D == 1024 and N2 == 3072:   # QKV form: the last third of the columns goes, transposed per head, to V^T
+        H, hd, Tp = 8, 128, (T + 7) // 8 * 8
+        qk = torch.zeros(M, 2 * D, dtype=torch.bfloat16, device="cuda")
+        vt = torch.zeros(S * H, hd, Tp, dtype=torch.bfloat16, device="cuda")
+        gb = torch.cat([(1 + sc0) @ w2.float().t(), sh0 @ w2.float().t() + c2], 1).contiguous()
+        ops.linear_bf16(hg0, w2, mode=EPI_BF16_LN, out=qk, T=T, H=H, hd=hd, Tp=Tp, vt=vt, vt_col0=2 * D,
+                        ln_consume=dict(stats=stats, g=gb[:, :N2], b=gb[:, N2:]))
+        ref = _ln_ref(ref_h, sc0, sh0, T) @ w2.float().t() + c2
+        assert _relerr(qk, ref[:, :2 * D]) < 8e-3
+        ref_vt = ref[:, 2 * D:].view(S, T, H, hd).permute(0, 2, 3, 1).reshape(S * H, hd, T)
+        assert _relerr(vt[:, :, :T], ref_vt) < 8e-3
+
+
+def test_ln_fold_quarter_tiles_and_determinism(ops):
+    """4864 rows x 1024 columns = 76 pair tiles on 74 pairs: the producer's last wave runs as 256 x 64 quarter tiles, whose
+    statistics slots must hold exactly what whole tiles would have written (bitwise: the row sums of a row do not depend
+    on which tile shape covered it), and a rerun is bitwise identical."""
+    from mixermdm_b200._lib import EPI_RESID_LN
+    M, D, T = 4864, 1024, 304
+    a = _rand((M, D), 41, dtype=torch.bfloat16)
+    w = _rand((D, D), 42, 1 / math.sqrt(D), dtype=torch.bfloat16)
+    h = _rand((M, D), 43)
+    sc = _rand((M // T, D), 44, 0.3)
+    res = []
+    for r0 in (0, 2432):   # the second call covers rows [2432, 4864) with whole tiles only (40 pair tiles)
+        stats = torch.zeros(D // 64, M, 2, device="cuda")
+        hg = torch.zeros(M, D, dtype=torch.bfloat16, device="cuda")
+        h_out = h.clone()
+        ops.linear_bf16(a[r0:], w, mode=EPI_RESID_LN, out=h_out[r0:], resid=h_out[r0:],
+                        ln_produce=dict(scale0=sc[r0 // T:], out0=hg[r0:], stats=stats[:, r0:], T=T))
+        res.append((stats, hg, h_out))
+    torch.cuda.synchronize()
+    ref_h = h + a.float() @ w.float().t()
+    assert _relerr(res[0][2], ref_h) < 1e-5
+    ref_stats = torch.stack([ref_h.view(M, 16, 64).sum(-1).t(), (ref_h ** 2).view(M, 16, 64).sum(-1).t()], -1)
+    assert _relerr(res[0][0], ref_stats) < 1e-5
+    # rows [4608, 4864) x columns [512, 1024) are quarter tiles in the first call (tiles 74, 75 of 76) and whole tiles in
+    # the second: identical bits either way
+    assert torch.equal(res[0][0][:, 2432:], res[1][0][:, 2432:])
+    assert torch.equal(res[0][1][2432:], res[1][1][2432:])
+    assert torch.equal(res[0][2][2432:], res[1][2][2432:])
+
+
+def test_ln_fold_embed_producer_with_cfg_duplicate(ops):
+    from mixermdm_b200._lib import EPI_EMBED_PE_LN
+    S, T, D, nf, kpad = 6, 37, 256, 262, 264     # S unique sequences, written again for the unconditional half
+    Mu = S * T
+    x = torch.zeros(Mu, kpad, dtype=torch.bfloat16, device="cuda")
+    x[:, :nf] = _rand((Mu, nf), 50, dtype=torch.bfloat16)
+    w = torch.zeros(D, kpad, dtype=torch.bfloat16, device="cuda")
+    w[:, :nf] = _rand((D, nf), 51, 0.06, dtype=torch.bfloat16)
+    b = _rand((D,), 52)
+    pe = _rand((64, D), 53)
+    sc = _rand((2 * S, D), 54, 0.3)
+    out = torch.zeros(2 * Mu, D, device="cuda")
+    hg = torch.zeros(2 * Mu, D, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(D // 64, 2 * Mu, 2, device="cuda")
+    ops.linear_bf16(x, w, mode=EPI_EMBED_PE_LN, out=out, bias=b, pe=pe, T=T, dup_row_offset=Mu,
+                    ln_produce=dict(scale0=sc, out0=hg, stats=stats, T=T, dup_seq=S))
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + b + pe[torch.arange(Mu, device="cuda") % T]
+    ref2 = torch.cat([ref, ref], 0)
+    assert _relerr(out, ref2) < 1e-5
+    seq = torch.arange(2 * Mu, device="cuda") // T
+    assert _relerr(hg, ref2 * (1 + sc[seq])) < 4e-3
+    ref_stats = torch.stack([ref2.view(2 * Mu, D // 64, 64).sum(-1).t(), (ref2 ** 2).view(2 * Mu, D // 64, 64).sum(-1).t()], -1)
+    assert _relerr(stats, ref_stats) < 1e-5
+    # rows >= `rows` only get h (the Influence network's m_I half)
+    out.zero_(); hg.zero_(); stats.zero_()
+    ops.linear_bf16(x, w, mode=EPI_EMBED_PE_LN, out=out[:Mu], bias=b, pe=pe, T=T,
+                    ln_produce=dict(scale0=sc, out0=hg, stats=stats, T=T, rows=3 * T))
+    torch.cuda.synchronize()
+    assert _relerr(out[:Mu], ref) < 1e-5
+    assert _relerr(hg[:3 * T], (ref * (1 + sc[seq[:Mu]]))[:3 * T]) < 4e-3
+    assert hg[3 * T:].abs().max().item() == 0 and stats[:, 3 * T:].abs().max().item() == 0
+
+
 def test_linear_embed_pe_and_final(ops):
     from mixermdm_b200._lib import EPI_EMBED_PE, EPI_FINAL
     S, T, D, nf, kpad = 6, 37, 256, 262, 264

@@ -23,7 +23,10 @@ for ln in sass:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
         lines.append(cur)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):   # a source page exported beforehand: ncu -i REP --page source --csv [-k regex:NAME] > file.csv
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}

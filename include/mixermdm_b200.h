@@ -89,6 +89,11 @@ typedef struct mmdm_epilogue {
   /* *_LN consumers (K = latent dim; uses T; `bias` is ignored, it is part of Bc) */
   const float* lnc_stats; int64_t lnc_pitch;                  /* the producer's statistics                            */
   const float* lnc_g; const float* lnc_b; int32_t lnc_ld;     /* G_s[n] = lnc_g[s*ld + n], Bc_s[n] = lnc_b[s*ld + n]  */
+  /* optional, producers: 16 bytes per row with the finished statistics (-mean and 1/rstd as bf16 pairs, rstd as float),
+   * written by a row pass behind the GEMM; consumers: the producer's lnp_rowa. With it the CTA-pair consumer kernel
+   * applies the mean / shift terms as one extra k step of the MMA (needs T >= 256). */
+  void* lnp_rowa;
+  const void* lnc_rowa;
 } mmdm_epilogue;
 
 /* D[M,N] = A[M,K] * W[N,K]^T, bf16 operands (row pitches lda/ldw in elements), fp32 accumulation (tcgen05).

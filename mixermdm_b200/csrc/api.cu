@@ -37,6 +37,8 @@ GemmEpi to_internal(const mmdm_epilogue& e) {
   g.lnc_stats = reinterpret_cast<const float2*>(e.lnc_stats);
   g.lnc_pitch = e.lnc_pitch; g.lnc_slots = 0;   // K / 64, set by launch_gemm's caller below
   g.lnc_g = e.lnc_g; g.lnc_b = e.lnc_b; g.lnc_ld = e.lnc_ld;
+  g.lnp_rowa = reinterpret_cast<uint4*>(e.lnp_rowa);
+  g.lnc_rowa = reinterpret_cast<const uint4*>(e.lnc_rowa);
   return g;
 }
 }  // namespace mmdm

@@ -74,7 +74,8 @@ struct Net {
   mmdm_net_weights w;
   std::vector<mmdm_block_weights> blocks;
   bool present = false;
-  bool fold = false;   // AdaLN folded into the neighbouring GEMMs (composite conditioning weights given, see gemm.cuh)
+  bool fold = false;   // AdaLN may be folded into the neighbouring GEMMs: composite conditioning tables given (gemm.cuh)
+  bool fold_on = false;   // ... and is, for the bound frame count (set by mmdm_bind_workspace)
   int hd() const { return w.D / w.H; }
 };
 
@@ -93,6 +94,7 @@ struct Workspace {
   float *gb0 = nullptr, *gb1 = nullptr;    // LN fold: G_s | Bc_s rows of every AdaLN site (S, comp_n max)
   float2* stat[3] = {nullptr, nullptr, nullptr};   // LN fold: row sums per 64-column slot [Dmax / 64][M]; block input /
                                                    // after self attention / after cross attention
+  uint4* rowa[3] = {nullptr, nullptr, nullptr};    // ... and the finished per-row values (M)
   int *map0 = nullptr, *map1 = nullptr, *tmap = nullptr;
   float* text[3] = {nullptr, nullptr, nullptr};   // per net: (nslices*Bx + 1, D)
   float* temb_tab[3] = {nullptr, nullptr, nullptr};  // per net: (nsteps, D)
@@ -148,6 +150,7 @@ struct mmdm_handle {
   // activation that is still in the 126 MB L2. MMDM_SERPENTINE=0 turns it off (A/B measurements).
   bool serpentine = true;
   int rev = 0;
+  bool fold_any_T = false;   // MMDM_LN_FOLD=2
 };
 
 namespace mmdm {
@@ -218,6 +221,7 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
     ws.gb0 = c.take<float>((size_t)S * compmax);
     ws.gb1 = c.take<float>((size_t)S * compmax);
     for (int i = 0; i < 3; ++i) ws.stat[i] = c.take<float2>((size_t)(Dmax / 64) * M);
+    for (int i = 0; i < 3; ++i) ws.rowa[i] = c.take<uint4>(M);
   }
   ws.mod0 = c.take<float>((size_t)S * adamax);
   ws.mod1 = c.take<float>((size_t)S * adamax);
@@ -314,7 +318,7 @@ static int run_conditioning(mmdm_handle* h, int ni, int S, const float* temb, co
   ep.mode = EPI_F32;
   ep.bias = n.w.ada0_b; ep.out = ws.mod0; ep.ldo = n.w.ada0_n;
   MMDM_TRY(gemm(h, "gemm_adaln", ws.E0, 2 * D, n.w.ada0_w, D, S, n.w.ada0_n, D, ep, st));
-  if (n.fold) {
+  if (n.fold_on) {
     ep.bias = n.w.comp0_b; ep.out = ws.gb0; ep.ldo = n.w.comp0_n;
     MMDM_TRY(gemm(h, "gemm_adaln", ws.E0, 2 * D, n.w.comp0_w, 2 * D, S, n.w.comp0_n, 2 * D, ep, st));
   }
@@ -325,7 +329,7 @@ static int run_conditioning(mmdm_handle* h, int ni, int S, const float* temb, co
     }
     ep.bias = n.w.ada1_b; ep.out = ws.mod1; ep.ldo = n.w.ada1_n;
     MMDM_TRY(gemm(h, "gemm_adaln", ws.E1, 2 * D, n.w.ada1_w, D, S, n.w.ada1_n, D, ep, st));
-    if (n.fold) {
+    if (n.fold_on) {
       ep.bias = n.w.comp1_b; ep.out = ws.gb1; ep.ldo = n.w.comp1_n;
       MMDM_TRY(gemm(h, "gemm_adaln", ws.E1, 2 * D, n.w.comp1_w, 2 * D, S, n.w.comp1_n, 2 * D, ep, st));
     }
@@ -390,17 +394,17 @@ static size_t comp_cols(const mmdm_net_weights& w, int table) {   // expected wi
   return w.kind == MMDM_NET_INTERACTION ? L * 6 * D : 0;
 }
 
-static void as_consumer(GemmEpi& e, int mode, const FoldSite& fs, const float2* stats, int M, int D, int T) {
+static void as_consumer(GemmEpi& e, int mode, const FoldSite& fs, const Workspace& ws, int si, int M, int D, int T) {
   e.mode = mode;
   e.bias = nullptr;   // part of Bc
-  e.lnc_stats = stats; e.lnc_pitch = M; e.lnc_slots = D / 64;
+  e.lnc_stats = ws.stat[si]; e.lnc_rowa = ws.rowa[si]; e.lnc_pitch = M; e.lnc_slots = D / 64;
   e.lnc_g = fs.g; e.lnc_b = fs.b; e.lnc_ld = fs.ld;
   e.T = T;
 }
-static void as_producer(GemmEpi& e, int mode, float2* stats, int M, int T, const float* sc0, int ld0, bf16* o0,
+static void as_producer(GemmEpi& e, int mode, const Workspace& ws, int si, int M, int T, const float* sc0, int ld0, bf16* o0,
                         const float* sc1 = nullptr, int ld1 = 0, bf16* o1 = nullptr) {
   e.mode = mode;
-  e.lnp_stats = stats; e.lnp_pitch = M; e.lnp_T = T;
+  e.lnp_stats = ws.stat[si]; e.lnp_rowa = ws.rowa[si]; e.lnp_pitch = M; e.lnp_T = T;
   e.lnp_scale0 = sc0; e.lnp_ld0 = ld0; e.lnp_out0 = o0;
   e.lnp_scale1 = sc1; e.lnp_ld1 = ld1; e.lnp_out1 = o1;
 }
@@ -408,7 +412,7 @@ static void as_producer(GemmEpi& e, int mode, float2* stats, int M, int T, const
 // one transformer block on the residual stream hres (M, D), in place.
 //   kvsrc == nullptr : cross attention (if any) reads the partner stream's block input (s ^ 1)
 //   kvsrc != nullptr : cross attention reads LN(kvsrc) of the same sequence index (Influence: m_I)
-// With the LN fold (n.fold) the block expects bf16(h (1 + scale_sa)) in ws.xn (and bf16(h (1 + scale_xf)) in ws.xf for
+// With the LN fold (n.fold_on) the block expects bf16(h (1 + scale_sa)) in ws.xn (and bf16(h (1 + scale_xf)) in ws.xf for
 // the partner-stream cross attention) plus the row sums in ws.stat[0] on entry - the previous block's FFN-2 (or the
 // embedding GEMM) wrote them - and leaves the same for block l + 1.
 static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kvsrc, int S, int T, bf16* bf16_copy,
@@ -420,7 +424,7 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
   const int M = S * T;
   const Mods m = block_mods(n, ws, l);
   const bool has_ca = b.ca_q_w != nullptr;
-  const bool fold = n.fold;
+  const bool fold = n.fold_on;
   const Folds f = fold ? block_folds(n, ws, l) : Folds{};
 
   // ---- self attention -------------------------------------------------------------------------
@@ -433,15 +437,15 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
   GemmEpi ep;
   ep.mode = EPI_BF16; ep.bias = b.sa_in_b; ep.out = ws.qk; ep.ldo = 2 * D;
   ep.vt_col0 = 2 * D; ep.vt = ws.vt; ep.T = T; ep.H = H; ep.hd = hd; ep.Tp = h->Tp;
-  if (fold) as_consumer(ep, EPI_BF16_LN, f.sa, ws.stat[0], M, D, T);
+  if (fold) as_consumer(ep, EPI_BF16_LN, f.sa, ws, 0, M, D, T);
   MMDM_TRY(gemm(h, "gemm_qkv", ws.xn, D, b.sa_in_w, D, M, 3 * D, D, ep, st));
   MMDM_TRY(attention(h, n, S, T, 0, st));
   GemmEpi er;
   er.mode = EPI_RESID; er.out = hres; er.resid = hres; er.ldo = D;
   er.bias = b.sa_out_b;
   if (fold) {   // next AdaLN site on these rows: the cross attention's query norm, or the FFN norm
-    if (has_ca) as_producer(er, EPI_RESID_LN, ws.stat[1], M, T, m.caq, m.ld_caq, ws.xn);
-    else as_producer(er, EPI_RESID_LN, ws.stat[1], M, T, m.ffn, m.ld_ffn, ws.xn);
+    if (has_ca) as_producer(er, EPI_RESID_LN, ws, 1, M, T, m.caq, m.ld_caq, ws.xn);
+    else as_producer(er, EPI_RESID_LN, ws, 1, M, T, m.ffn, m.ld_ffn, ws.xn);
   }
   MMDM_TRY(gemm(h, "gemm_proj", ws.att, D, b.sa_out_w, D, M, D, D, er, st));
 
@@ -451,16 +455,16 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
     if (!fold) MMDM_TRY(ln(h, hres, M, D, T, m.caq, m.ld_caq, ws.xn, nullptr, 0, nullptr, st));
     GemmEpi eq;
     eq.mode = EPI_BF16; eq.bias = b.ca_q_b; eq.out = ws.qk; eq.ldo = 2 * D;
-    if (fold) as_consumer(eq, EPI_BF16_LN, f.caq, ws.stat[1], M, D, T);
+    if (fold) as_consumer(eq, EPI_BF16_LN, f.caq, ws, 1, M, D, T);
     MMDM_TRY(gemm(h, "gemm_qkv", ws.xn, D, b.ca_q_w, D, M, D, D, eq, st));
     GemmEpi ek;
     ek.mode = EPI_BF16; ek.bias = b.ca_kv_b; ek.out = ws.qk + D; ek.ldo = 2 * D;
     ek.vt_col0 = D; ek.vt = ws.vt; ek.T = T; ek.H = H; ek.hd = hd; ek.Tp = h->Tp;
-    if (fold && kvsrc == nullptr) as_consumer(ek, EPI_BF16_LN, f.xf, ws.stat[0], M, D, T);   // statistics of the block input
+    if (fold && kvsrc == nullptr) as_consumer(ek, EPI_BF16_LN, f.xf, ws, 0, M, D, T);   // statistics of the block input
     MMDM_TRY(gemm(h, "gemm_qkv", ws.xf, D, b.ca_kv_w, D, M, 2 * D, D, ek, st, /*flip=*/false));   // same way as the q GEMM
     MMDM_TRY(attention(h, n, S, T, kvsrc == nullptr ? 1 : 0, st));
     er.bias = b.ca_out_b;
-    if (fold) as_producer(er, EPI_RESID_LN, ws.stat[2], M, T, m.ffn, m.ld_ffn, ws.xn);
+    if (fold) as_producer(er, EPI_RESID_LN, ws, 2, M, T, m.ffn, m.ld_ffn, ws.xn);
     MMDM_TRY(gemm(h, "gemm_proj", ws.att, D, b.ca_out_w, D, M, D, D, er, st));
   }
 
@@ -468,15 +472,15 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
   if (!fold) MMDM_TRY(ln(h, hres, M, D, T, m.ffn, m.ld_ffn, ws.xn, nullptr, 0, nullptr, st));
   GemmEpi e1;
   e1.mode = EPI_GELU_BF16; e1.bias = b.ffn_b1; e1.out = ws.mid; e1.ldo = F;
-  if (fold) as_consumer(e1, EPI_GELU_BF16_LN, f.ffn, ws.stat[has_ca ? 2 : 1], M, D, T);
+  if (fold) as_consumer(e1, EPI_GELU_BF16_LN, f.ffn, ws, has_ca ? 2 : 1, M, D, T);
   MMDM_TRY(gemm(h, "gemm_ffn1", ws.xn, D, b.ffn_w1, D, M, F, D, e1, st));
   er.bias = b.ffn_b2;
   er.mode = EPI_RESID;
   er.out_bf16 = bf16_copy;
   if (fold && l + 1 < n.w.L) {   // operands of the next block
     const Mods mn = block_mods(n, ws, l + 1);
-    if (has_ca && kvsrc == nullptr) as_producer(er, EPI_RESID_LN, ws.stat[0], M, T, mn.sa, mn.ld_sa, ws.xn, mn.xf, mn.ld_xf, ws.xf);
-    else as_producer(er, EPI_RESID_LN, ws.stat[0], M, T, mn.sa, mn.ld_sa, ws.xn);
+    if (has_ca && kvsrc == nullptr) as_producer(er, EPI_RESID_LN, ws, 0, M, T, mn.sa, mn.ld_sa, ws.xn, mn.xf, mn.ld_xf, ws.xf);
+    else as_producer(er, EPI_RESID_LN, ws, 0, M, T, mn.sa, mn.ld_sa, ws.xn);
   }
   MMDM_TRY(gemm(h, "gemm_ffn2", ws.mid, F, b.ffn_w2, F, M, D, F, er, st));
   return 0;
@@ -494,14 +498,14 @@ static int run_embed(mmdm_handle* h, int ni, int rows, int ln_rows, int dup, int
   ee.mode = EPI_EMBED_PE; ee.bias = n.w.embed_b; ee.out = ws.h; ee.ldo = D; ee.pe = n.w.pe; ee.pe_ld = D; ee.T = T;
   ee.dup_row_offset = dup ? (long long)rows : 0;
   MMDM_TRY(gemm(h, "gemm_embed", ws.xin, kpad, n.w.embed_w, kpad, rows, D, kpad, ee, st));
-  if (n.fold) {
+  if (n.fold_on) {
     const Mods m0 = block_mods(n, ws, 0);
     const int Mb = dup ? 2 * ln_rows : ln_rows;   // rows entering the blocks = S * T
     Scope sc(h, "ln_modulate", st);
     if (n.w.kind == MMDM_NET_INTERACTION)
-      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, m0.xf, m0.ld_xf, ws.xf, ws.stat[0], S * T, st, next_dir(h)));
+      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, m0.xf, m0.ld_xf, ws.xf, ws.stat[0], S * T, ws.rowa[0], st, next_dir(h)));
     else
-      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, nullptr, 0, nullptr, ws.stat[0], S * T, st, next_dir(h)));
+      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, nullptr, 0, nullptr, ws.stat[0], S * T, ws.rowa[0], st, next_dir(h)));
   }
   return 0;
 }
@@ -756,8 +760,12 @@ int mmdm_create(const mmdm_config* cfg, const mmdm_net_weights nets[3], mmdm_han
         delete h;
         return -1;
       }
-      const char* e = getenv("MMDM_LN_FOLD");   // 0 keeps the stand-alone LayerNorm kernel even when the tables are given
+      // MMDM_LN_FOLD: 0 keeps the stand-alone LayerNorm kernel even when the tables are given; 2 folds at every frame
+      // count (tests); default: from 256 frames on, where the consumers' aux k step applies (gemm.cu) - below that the
+      // folded GEMMs would run as single-CTA kernels and lose more than the LayerNorm pass costs
+      const char* e = getenv("MMDM_LN_FOLD");
       h->net[i].fold = !(e && e[0] == '0');
+      h->fold_any_T = e && e[0] == '2';
     }
   }
   if (h->net[2].present && h->net[2].w.D != 512) {
@@ -802,6 +810,7 @@ int mmdm_bind_workspace(mmdm_handle* h, void* ws, size_t bytes, int B, int T) {
     h->temb_ready = false;
     h->cond_ready = false;
     h->mask_on = false;
+    for (int i = 0; i < 3; ++i) h->net[i].fold_on = h->net[i].fold && (T >= 256 || h->fold_any_T);
     return 0;
   });
 }

@@ -45,7 +45,7 @@ struct RowCtx {
   uint32_t g_smem, b_smem;   // the warp's staged G_s / Bc_s values of this row's sequence (chunk 0), 0: not staged
 };
 
-template <int MODE>
+template <int MODE, bool AUX = false>
 __device__ __forceinline__ RowCtx make_row_ctx(const GemmEpi& ep, int row, int M) {
   RowCtx rc;
   rc.row = row;
@@ -60,7 +60,7 @@ __device__ __forceinline__ RowCtx make_row_ctx(const GemmEpi& ep, int row, int M
     rc.s = row / ep.T;
     rc.t = row - rc.s * ep.T;
   }
-  if (mode_ln_consumer(MODE) && rc.valid) {
+  if (mode_ln_consumer(MODE) && !AUX && rc.valid) {
     // row statistics from the producer's partial sums, always added in slot order (bitwise reproducible)
     float s1 = 0.f, s2 = 0.f;
     for (int k = 0; k < ep.lnc_slots; ++k) {
@@ -141,12 +141,12 @@ __device__ __forceinline__ void epilogue_chunk_edge(const GemmEpi& ep, const Row
   }
 }
 
-template <int MODE>
+template <int MODE, bool AUX = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& rc, int col0, const float* v, int N,
                                                uint32_t bias_smem) {
   if (!rc.valid || col0 >= N) return;
   if (col0 + 32 > N || MODE == EPI_FINAL || MODE == EPI_SIGMOID_F32 || transposed_mode(MODE) || !ep.vec_ok ||
-      (mode_ln_consumer(MODE) && rc.g_smem == 0)) {   // FINAL rows are only 8-byte aligned in the scattered layout
+      (mode_ln_consumer(MODE) && !AUX && rc.g_smem == 0)) {   // FINAL rows are only 8-byte aligned in the scattered layout
     epilogue_chunk_edge<MODE>(ep, rc, col0, v, N);
     return;
   }
@@ -168,9 +168,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const RowCtx& 
       f32x2 x[4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const float4 g4 = lds128(gs + (uint32_t)(2 * j + u) * 16), b4 = lds128(bs + (uint32_t)(2 * j + u) * 16);
-        x[2 * u] = fma2(rho2, pack2(v[8 * j + 4 * u], v[8 * j + 4 * u + 1]), fma2(nrm2, pack2(g4.x, g4.y), pack2(b4.x, b4.y)));
-        x[2 * u + 1] = fma2(rho2, pack2(v[8 * j + 4 * u + 2], v[8 * j + 4 * u + 3]), fma2(nrm2, pack2(g4.z, g4.w), pack2(b4.z, b4.w)));
+        if (AUX) {   // the accumulator already holds acc - mu G_s + Bc_s / rho (an extra k step of the MMA, see the aux warp)
+          x[2 * u] = mul2(rho2, pack2(v[8 * j + 4 * u], v[8 * j + 4 * u + 1]));
+          x[2 * u + 1] = mul2(rho2, pack2(v[8 * j + 4 * u + 2], v[8 * j + 4 * u + 3]));
+        } else {
+          const float4 g4 = lds128(gs + (uint32_t)(2 * j + u) * 16), b4 = lds128(bs + (uint32_t)(2 * j + u) * 16);
+          x[2 * u] = fma2(rho2, pack2(v[8 * j + 4 * u], v[8 * j + 4 * u + 1]), fma2(nrm2, pack2(g4.x, g4.y), pack2(b4.x, b4.y)));
+          x[2 * u + 1] = fma2(rho2, pack2(v[8 * j + 4 * u + 2], v[8 * j + 4 * u + 3]), fma2(nrm2, pack2(g4.z, g4.w), pack2(b4.z, b4.w)));
+        }
       }
       if (mode_gelu(MODE)) {
         uint4 pk;
@@ -544,13 +549,13 @@ __device__ __forceinline__ void lnc_publish(const EpiLnc<BN>& r, uint32_t smem, 
   __syncwarp();
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool AUX = false>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0, int M, int N, uint32_t tmem_acc,
                                               int q, int c0, int cnt, int lane, uint32_t stg, const EpiBias<BN>& bias,
                                               RowCtx rc) {
   const uint32_t bias_smem = stg;   // non-residual modes: the staging slice holds the published bias
   constexpr int NCH = BN / 64;   // at most this many chunks of 32 columns per warp: chunks [c0, c0 + cnt)
-  if (mode_ln_consumer(MODE) && ep.vec_ok) {
+  if (mode_ln_consumer(MODE) && !AUX && ep.vec_ok) {
     const int row0 = m0 + q * 32;
     const int sa = min(row0, M - 1) / ep.T, sb = min(row0 + 31, M - 1) / ep.T;
     const int sel = rc.s == sa ? 0 : (rc.s == sb ? 1 : -1);
@@ -582,7 +587,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, int m0, int n0,
     else if (MODE == EPI_FINAL && ep.final_vec_ok && col0 < N)
       epilogue_chunk_final_t(ep, m0 + q * 32, lane, col0, v, M, N, stg);
     else
-      epilogue_chunk<MODE>(ep, rc, col0, v, N, mode_ln_consumer(MODE) ? (uint32_t)c * 128 : bias_smem + (uint32_t)c * 128);
+      epilogue_chunk<MODE, AUX>(ep, rc, col0, v, N, mode_ln_consumer(MODE) ? (uint32_t)c * 128 : bias_smem + (uint32_t)c * 128);
     if (c + 1 < cnt) {
       if (mode_ln_producer(MODE)) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
       tmem_ld_wait();
@@ -774,6 +779,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // stores of the previous chunk have left its buffer - across tiles too, so the first chunk of a tile is in shared
 // memory long before its accumulator is) and one 2 KB buffer per bf16 output.
 // ------------------------------------------------------------------------------------------------
+// finished per-row values of the LN fold (GemmEpi::lnp_rowa): operand words of the aux k step + rho
+__device__ __forceinline__ void ln_split_bf16(float x, uint32_t& hi, uint32_t& lo) {   // bf16 pair, raw 16-bit patterns
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = (uint32_t)__bfloat16_as_ushort(h);
+  lo = (uint32_t)__bfloat16_as_ushort(l);
+}
+__host__ __device__ __forceinline__ void ln_row_moments(float s1, float s2, float inv_d, float& mu, float& rho, float& sg) {
+  mu = s1 * inv_d;
+  const float var = fmaxf(fmaf(-mu, mu, s2 * inv_d), 0.f) + 1e-6f;
+  rho = rsqrtf(var);
+  sg = var * rho;   // 1 / rho
+}
+__device__ __forceinline__ uint4 ln_row_finalize(float s1, float s2, float inv_d) {
+  float mu, rho, sg;
+  ln_row_moments(s1, s2, inv_d, mu, rho, sg);
+  uint32_t mh, ml, sh, sl;
+  ln_split_bf16(-mu, mh, ml);
+  ln_split_bf16(sg, sh, sl);
+  return make_uint4(mh | (mh << 16), ml | (sh << 16), sh | (sl << 16), __float_as_uint(rho));
+}
+// row pass behind the producers that do not finalise in their epilogue (single-CTA kernels, the embedding modes)
+__global__ void ln_rowstat_kernel(const float2* __restrict__ stats, long long pitch, int rows, int slots, float inv_d,
+                                  uint4* __restrict__ rowa) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < slots; ++k) {
+    const float2 p = stats[(size_t)k * pitch + row];
+    s1 += p.x;
+    s2 += p.y;
+  }
+  rowa[row] = ln_row_finalize(s1, s2, inv_d);
+}
+
 struct EpiMaps {
   CUtensorMap r, o, h0, h1;   // residual in, fp32 out: box 32 x 32, 128B swizzle; bf16 out: box 32 x 32, 64B swizzle
 };
@@ -790,7 +830,7 @@ __device__ __forceinline__ void tma_epi_request(const EpiMaps& mp, const TmaEpi&
 }
 
 template <int MODE>
-__device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, const EpiMaps& mp, TmaEpi& te, int m0, int n0, int M,
+__device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, const EpiMaps& mp, TmaEpi& te, int m0, int n0, int M, int N,
                                                   uint32_t tmem_acc, int q, int c0, int cnt, int lane, int nxt_row0,
                                                   int nxt_col0) {
   const int row0 = m0 + q * 32, row = row0 + lane;
@@ -893,7 +933,10 @@ struct Gemm2Cfg {
   static constexpr int BN = 256;
   static constexpr int BK = 64;
   static constexpr bool TMA_EPI = mode_resid(MODE);   // residual tiles through bulk tensor copies (epilogue_tile_tma)
-  static constexpr int STAGES = TMA_EPI ? 4 : 6;      // (96 KB of epilogue buffers take two stages' room)
+  // LN-fold consumers: the row / sequence dependent part of the normalisation, - mu_r G_s[n] + Bc_s[n] / rho_r, enters
+  // the accumulator through one extra k step of the MMA whose operands the aux warp (warp 3) writes (see the kernel)
+  static constexpr bool AUX = mode_ln_consumer(MODE);
+  static constexpr int STAGES = TMA_EPI ? 4 : AUX ? 5 : 6;   // (96 KB of epilogue buffers / the aux operands take the room)
   // Epilogue warps: 8 (two per TMEM lane quarter, 4 chunks of 32 columns each); the GELU epilogue costs ~20
   // instructions per element and paced FFN-1 at 55 % tensor-pipe activity, so it gets 12 (3 + 3 + 2 chunks).
   static constexpr int EPI_WARPS = mode_gelu(MODE) ? 12 : 8;
@@ -906,7 +949,8 @@ struct Gemm2Cfg {
   static constexpr uint32_t STG_WARP_BYTES =
       TMA_EPI ? kTmaEpiWarpBytes : (transposed_mode(MODE) || MODE == EPI_FINAL) ? 4096 : mode_ln_consumer(MODE) ? 2048 : 512;
   static constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG_WARP_BYTES;
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
+  static constexpr size_t SMEM_BYTES =
+      (size_t)(STAGES + (AUX ? 1 : 0)) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
 };
 
 template <int MODE>
@@ -918,13 +962,21 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // [pipeline stages][TMA epilogue: per-warp buffers, 1024-byte aligned][barriers, 256 B][other modes: per-warp staging]
-  uint8_t* const stg_ptr = smem + (size_t)C::STAGES * C::STAGE_BYTES + (C::TMA_EPI ? 0 : 256);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + (C::TMA_EPI ? C::STG_BYTES : 0));
+  // (AUX: one more stage-sized buffer behind the ring holds the aux warp's operands)
+  constexpr size_t kRing = (size_t)(C::STAGES + (C::AUX ? 1 : 0)) * C::STAGE_BYTES;
+  uint8_t* const aux_ptr = smem + (size_t)C::STAGES * C::STAGE_BYTES;
+  uint8_t* const stg_ptr = smem + kRing + (C::TMA_EPI ? 0 : 256);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRing + (C::TMA_EPI ? C::STG_BYTES : 0));
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint64_t* rbar = tempty_bar + 3;   // TMA epilogue: [8 warps][2] "residual tile landed" (fits the 256-byte barrier area at 4 stages)
+  // AUX: the operands of tile t live in k columns [16 p, 16 p + 16) of the aux buffer, p = t & 1, so the aux warps work
+  // a whole tile ahead of the MMA; every barrier exists per p and completes once per two tiles
+  uint64_t* aux_ready = tempty_bar + 3;   // [2] (leader CTA): the other three aux warps' quarters are written
+  uint64_t* aux_full = tempty_bar + 5;    // [2] (leader CTA): all of it is
+  uint64_t* aux_empty = tempty_bar + 7;   // [2] (both CTAs): the aux k step that read it has been executed
   const uint32_t stg_base = smem_u32(stg_ptr);
 
   const int warp = threadIdx.x >> 5;
@@ -978,6 +1030,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     if (C::TMA_EPI)
       for (int i = 0; i < 2 * C::EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
+    if (C::AUX) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&aux_ready[i], 3);   // the other three aux warps of the pair (the leader's warp 3 waits for them)
+        mbar_init(&aux_full[i], 1);
+        mbar_init(&aux_empty[i], 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
@@ -1010,6 +1069,85 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // ---- aux warps (LN-fold consumers; each takes half of the CTA's rows of A2 and B2) ----------------------------------------------------------------------
+    // y[r, n] = rho_r (acc[r, n] - mu_r G_s[n] + sigma_r Bc_s[n]), sigma = 1 / rho, s = sequence of row r. The bracket's
+    // second part is a rank-12 product over the (at most two, T >= 256) sequences a, b of the pair's 256 rows:
+    //   A2[r, :] = [s_r == a] (-mu_h, -mu_h, -mu_l, sg_h, sg_h, sg_l, 0 ...) + [s_r == b] (0 x 6, the same six, 0 ...)
+    //   B2[n, :] = (Ga_h, Ga_l, Ga_h, Bca_h, Bca_l, Bca_h, Gb_h, Gb_l, Gb_h, Bcb_h, Bcb_l, Bcb_h, 0 ...)
+    // with bf16 pairs x_h + x_l of every factor (products of the pairs' leading three terms: 2^-16 relative). This warp
+    // writes both into a stage-sized buffer of its own - 16 of 64 k columns, K-major 128B-swizzled rows like the TMA
+    // tiles - and the MMA warp issues one more k step on it, so the epilogue only multiplies by rho_r. (Own buffer and
+    // barriers, one phase per tile: a warp that does not take part in every block of the ring cannot wait on the ring's
+    // barriers - a parity wait is only meaningful within one phase of the barrier's current one.)
+    if (C::AUX) {
+      float* const rho_sm = reinterpret_cast<float*>(stg_ptr);   // [8 tiles in flight][128 rows]
+      int titer = 0;
+      for (int it = pair; it < num_items; it += npairs, ++titer) {
+        int m_idx, n_item, ncols;
+        item_of(it, m_idx, n_item, ncols);
+        const int m0 = m_idx * (2 * C::BM) + (int)rank * C::BM;
+        const int nb0 = n_item + (int)rank * (ncols / 2);
+        // (a, b): the sequences of the PAIR's 256 rows - both CTAs' rows meet both CTAs' halves of B2
+        const int sa = min(m_idx * (2 * C::BM), M - 1) / ep.T, sb = min(m_idx * (2 * C::BM) + 2 * C::BM - 1, M - 1) / ep.T;
+        const int ib = 2 * (warp - 2);   // this warp: rows / B2 rows lane + 32 (ib + {0, 1})
+        // (this warp runs ~1 instruction per 16 cycles and has a tile's time, ~8000 cycles, per item: the rows' finished
+        // values come as one 16-byte load each, GemmEpi::lnc_rowa)
+        uint4 a0[2], a1[2], b0[2], b1[2];
+        float rho_v[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int row = m0 + lane + 32 * (ib + i);
+          const uint4 ra = __ldg(ep.lnc_rowa + min(row, M - 1));
+          const bool valid = row < M, second = valid && row / ep.T != sa;
+          const uint32_t w0 = valid ? ra.x : 0u, w1 = valid ? ra.y : 0u, w2 = valid ? ra.z : 0u;
+          rho_v[i] = valid ? __uint_as_float(ra.w) : 0.f;
+          a0[i] = second ? make_uint4(0u, 0u, 0u, w0) : make_uint4(w0, w1, w2, 0u);
+          a1[i] = second ? make_uint4(w1, w2, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+          const int li = lane + 32 * (ib + i), n = nb0 + li;
+          float ga = 0.f, ba = 0.f, gb = 0.f, bb = 0.f;
+          if (li < ncols / 2 && n < N) {
+            ga = __ldg(ep.lnc_g + (size_t)sa * ep.lnc_ld + n);
+            ba = __ldg(ep.lnc_b + (size_t)sa * ep.lnc_ld + n);
+            gb = __ldg(ep.lnc_g + (size_t)sb * ep.lnc_ld + n);
+            bb = __ldg(ep.lnc_b + (size_t)sb * ep.lnc_ld + n);
+          }
+          uint32_t gh, gl, bh, bl;
+          ln_split_bf16(ga, gh, gl);
+          ln_split_bf16(ba, bh, bl);
+          const uint32_t x0 = gh | (gl << 16), x1 = gh | (bh << 16), x2 = bl | (bh << 16);
+          ln_split_bf16(gb, gh, gl);
+          ln_split_bf16(bb, bh, bl);
+          b0[i] = make_uint4(x0, x1, x2, gh | (gl << 16));
+          b1[i] = make_uint4(gh | (bh << 16), bl | (bh << 16), 0u, 0u);
+        }
+        const uint32_t ap = (uint32_t)titer & 1u, aph = ((uint32_t)titer >> 1) & 1u;
+        mbar_wait(&aux_empty[ap], aph ^ 1u);   // the aux k step of tile t - 2 has read these columns
+        const uint32_t pa = smem_u32(aux_ptr), pb = pa + C::A_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t r = (uint32_t)(lane + 32 * (ib + i)), sw = r & 7u;
+          sts128u(pa + r * 128u + (((2u * ap) ^ sw) << 4), a0[i]);
+          sts128u(pa + r * 128u + (((2u * ap + 1u) ^ sw) << 4), a1[i]);
+          sts128u(pb + r * 128u + (((2u * ap) ^ sw) << 4), b0[i]);
+          sts128u(pb + r * 128u + (((2u * ap + 1u) ^ sw) << 4), b1[i]);
+          rho_sm[(titer & 7) * C::BM + (int)r] = rho_v[i];
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> the tensor core's (async proxy) reads
+        __syncwarp();
+        if (lane == 0) {
+          if (rank != 0) {
+            mbar_arrive_cluster_release(mapa_u32(smem_u32(&aux_ready[ap]), 0));
+          } else if (warp == 2) {
+            mbar_arrive(&aux_ready[ap]);
+          } else {   // one arrival per tile, after all four quarters are written
+            mbar_wait_cluster(&aux_ready[ap], aph);
+            mbar_arrive(&aux_full[ap]);
+          }
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc_full = umma_idesc_bf16(2 * C::BM, BN), idesc_quarter = umma_idesc_bf16(2 * C::BM, BN / 4);
@@ -1022,7 +1160,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // the stage index, which cost ~25 dependent uniform-datapath instructions per k block.
       const uint64_t da0 = umma_desc_k_sw128(smem_u32(smem));
       const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem) + C::A_BYTES);
-      uint32_t soff = 0;
+      uint32_t soff = 0, aux_t = 0;
+      const uint64_t da_aux = umma_desc_k_sw128(smem_u32(aux_ptr)), db_aux = umma_desc_k_sw128(smem_u32(aux_ptr) + C::A_BYTES);
       for (int it = pair; it < num_items; it += npairs) {
         const uint32_t idesc = (split_tail && it >= full_tiles) ? idesc_quarter : idesc_full;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -1042,6 +1181,14 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             soff = 0;
             phase ^= 1;
           }
+        }
+        if (C::AUX) {   // one k step (16 columns) on the aux warp's operands
+          const uint32_t ap = aux_t & 1u;
+          mbar_wait(&aux_full[ap], (aux_t >> 1) & 1u);
+          ++aux_t;
+          tc_fence_after();
+          umma_bf16_ss_2sm(d_tmem, da_aux + (uint64_t)(ap * 2u), db_aux + (uint64_t)(ap * 2u), idesc, 1u);
+          umma_commit_2sm(&aux_empty[ap], 3);
         }
         umma_commit_2sm(&tfull_bar[acc], 3);
         acc ^= 1;
@@ -1088,18 +1235,19 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       my_chunks(nc, c0n, cntn);
       bias_next = bias_fetch<BN, MODE>(ep, ni, c0n, lane, N);
     }
-    if (mode_ln_consumer(MODE) && ep.vec_ok && pair < num_items) {
+    if (mode_ln_consumer(MODE) && !C::AUX && ep.vec_ok && pair < num_items) {
       int mi, ni, nc, c0n, cntn;
       item_of(pair, mi, ni, nc);
       my_chunks(nc, c0n, cntn);
       lnc_next = lnc_fetch<BN>(ep, mi * (2 * C::BM) + (int)rank * C::BM + q * 32, ni, c0n, cntn, lane, M, N);
     }
-    for (int it = pair; it < num_items; it += npairs) {
+    int titer = 0;
+    for (int it = pair; it < num_items; it += npairs, ++titer) {
       int m_idx, n0, ncols, c0, cnt;
       item_of(it, m_idx, n0, ncols);
       my_chunks(ncols, c0, cnt);
       const int m0 = m_idx * (2 * C::BM) + (int)rank * C::BM;
-      if (mode_ln_consumer(MODE) && ep.vec_ok) {
+      if (mode_ln_consumer(MODE) && !C::AUX && ep.vec_ok) {
         lnc_publish<BN>(lnc_next, stg, cnt, lane);
         if (it + npairs < num_items) {
           int mi, ni, nc, c0n, cntn;
@@ -1141,13 +1289,14 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       }
-      const RowCtx rc = make_row_ctx<MODE>(ep, m0 + q * 32 + lane, M);   // (LN fold: the row statistics load while we wait)
+      RowCtx rc = make_row_ctx<MODE, C::AUX>(ep, m0 + q * 32 + lane, M);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (C::AUX) rc.rho = reinterpret_cast<const float*>(stg_ptr)[(titer & 7) * C::BM + q * 32 + lane];   // the aux warp's
       if (C::TMA_EPI) {
-        if (cnt > 0) epilogue_tile_tma<MODE>(ep, emaps, te, m0, n0, M, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, nxt_row0, nxt_col0);
+        if (cnt > 0) epilogue_tile_tma<MODE>(ep, emaps, te, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, nxt_row0, nxt_col0);
       } else if (cnt > 0) {
-        epilogue_tile<BN, MODE>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias, rc);
+        epilogue_tile<BN, MODE, C::AUX>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias, rc);
       }
       tc_fence_before();
       __syncwarp();
@@ -1293,7 +1442,9 @@ static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
   // CTA pairs on 256x256 tiles for the big projections; 128x256 single-CTA tiles when N fills them but M is
   // small; 128x128 for narrow / ragged N (e.g. the 262-wide output layer)
   // (the residual modes' TMA epilogue needs 16-byte aligned rows; launch_gemm's vec_ok says so)
-  if (N % 256 == 0 && M >= 512 && use_2cta() && (!mode_resid(MODE) || (ep.vec_ok && ep.bias_ok16)))
+  // (the LN-fold consumers' aux k step covers two sequences per 256 rows: T >= 256)
+  if (N % 256 == 0 && M >= 512 && use_2cta() && (!mode_resid(MODE) || (ep.vec_ok && ep.bias_ok16)) &&
+      (!mode_ln_consumer(MODE) || (ep.T >= 256 && ep.vec_ok && ep.lnc_rowa != nullptr)))
     return launch_tc2<MODE>(A, lda, W, ldw, M, N, K, ep, stream);
   if (N % 256 == 0 || N >= 1024) return launch_tc<256, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
   return launch_tc<128, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
@@ -1303,8 +1454,27 @@ static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
 // not a stream operation, so it is legal while mmdm_sample captures its step graph (which it does on first use).
 int gemm_init() { return 0; }
 
+static int launch_gemm_inner(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                             const GemmEpi& ep, cudaStream_t stream);
+
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
                 const GemmEpi& ep, cudaStream_t stream) {
+  MMDM_TRY(launch_gemm_inner(A, lda, W, ldw, M, N, K, ep, stream));
+  if (mode_ln_producer(ep.mode) && ep.lnp_rowa != nullptr) {
+    // The finished per-row values come from a row pass behind the GEMM (~3 us). Finishing them inside the epilogue - the
+    // warp that completes a 32-row group's slots, found with a device-wide counter - was measured: the fence in front
+    // of the counter costs every warp ~1-2 us per tile, 16-23 us per launch.
+    const int lim = (ep.lnp_rows > 0 && ep.lnp_rows < M) ? ep.lnp_rows : M;
+    const int rows = ep.dup_row_offset != 0 ? (int)ep.dup_row_offset + lim : lim;
+    ln_rowstat_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(ep.lnp_stats, ep.lnp_pitch, rows, N / kLnSlotCols, 1.0f / (float)N,
+                                                            ep.lnp_rowa);
+    MMDM_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+static int launch_gemm_inner(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                             const GemmEpi& ep, cudaStream_t stream) {
   MMDM_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   MMDM_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "gemm: lda/ldw must be multiples of 8 (got %d, %d)", lda, ldw);
   MMDM_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,

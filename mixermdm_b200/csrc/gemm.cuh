@@ -67,12 +67,16 @@ struct GemmEpi {
   long long lnp_pitch = 0;
   int lnp_T = 1;
   int lnp_rows = 0;                      // rows >= lnp_rows write h only (Influence: the m_I half of the embed GEMM)
+  // optional: finished per-row values for the CTA-pair consumers' aux k step, rowa[r] = (bf16 pairs of -mu and
+  // 1/rho packed as the three operand words, rho as float bits), written by a small row pass behind the GEMM
+  uint4* lnp_rowa = nullptr;
   int lnp_dup_seq = 0;                   // EPI_EMBED_PE_LN with dup_row_offset: sequence offset of the duplicated rows
   // LN-fold consumer (EPI_BF16_LN / EPI_GELU_BF16_LN; uses T): K = latent dim of the normalised rows
   const float2* lnc_stats = nullptr;     // [lnc_slots][lnc_pitch]
   long long lnc_pitch = 0;
   int lnc_slots = 0;
   float lnc_inv_d = 0.f;
+  const uint4* lnc_rowa = nullptr;       // the producer's lnp_rowa (needed by the CTA-pair kernel, T >= 256)
   const float* lnc_g = nullptr;          // G_s[n] = lnc_g[s * lnc_ld + n]
   const float* lnc_b = nullptr;          // Bc_s[n] (bias included; GemmEpi::bias is ignored)
   int lnc_ld = 0;

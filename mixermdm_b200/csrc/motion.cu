@@ -192,27 +192,7 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 6000000000LL) {
-      printf("mmdm mixstep: cluster barrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
-  }
-}
+// (mbar_wait_cluster: common.cuh)
 // Monotonic counters, plain volatile shared-memory words (a release store compiles to MEMBAR.ALL.CTA):
 //   slot_lap[s]: how often slot s has been armed. An mbarrier parity wait is only meaningful within one
 //              phase of the barrier's current one and the consumers look further ahead than that, so a warp first

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128)
 ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq, int run_len, int rev,
                      const float* __restrict__ sc0, int ld0, __nv_bfloat16* __restrict__ out0,
                      const float* __restrict__ sc1, int ld1, __nv_bfloat16* __restrict__ out1,
-                     float2* __restrict__ stats, long long pitch) {
+                     float2* __restrict__ stats, long long pitch, uint4* __restrict__ rowa) {
   constexpr int D = NV * 128;
   constexpr int NM = DUAL ? 2 : 1;
   extern __shared__ float4 ln_smem[];   // [4 warps][NM][D/4]: 1 + scale
@@ -171,6 +171,7 @@ ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq
       for (int i = 0; i < NV; ++i) nx[i] = src[(size_t)(t + 1 - t0) * (D / 4) + i * 32 + lane];
     }
     const size_t row = (size_t)s * T + t;
+    float t1 = 0.f, t2 = 0.f;   // whole-row sums, slots added in order
 #pragma unroll
     for (int i = 0; i < NV; ++i) {   // lanes 0-15 hold slot 2i, lanes 16-31 slot 2i + 1
       float a = (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -181,6 +182,19 @@ ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq
         b += __shfl_xor_sync(0xffffffffu, b, o);
       }
       if ((lane & 15) == 0) stats[(size_t)(2 * i + (lane >> 4)) * pitch + row] = make_float2(a, b);
+      const float a_hi = __shfl_sync(0xffffffffu, a, 16), b_hi = __shfl_sync(0xffffffffu, b, 16);
+      t1 = (t1 + a) + a_hi;   // (meaningful in lane 0: slot 2i, then slot 2i + 1)
+      t2 = (t2 + b) + b_hi;
+    }
+    if (rowa != nullptr && lane == 0) {   // the finished per-row values (gemm.cuh: GemmEpi::lnp_rowa)
+      const float mu = t1 * (1.0f / D);
+      const float var = fmaxf(fmaf(-mu, mu, t2 * (1.0f / D)), 0.f) + 1e-6f;
+      const float rho = rsqrtf(var), sg = var * rho;
+      const __nv_bfloat16 mh = __float2bfloat16_rn(-mu), ml = __float2bfloat16_rn(-mu - __bfloat162float(mh));
+      const __nv_bfloat16 sh = __float2bfloat16_rn(sg), sl = __float2bfloat16_rn(sg - __bfloat162float(sh));
+      const uint32_t umh = __bfloat16_as_ushort(mh), uml = __bfloat16_as_ushort(ml), ush = __bfloat16_as_ushort(sh),
+                     usl = __bfloat16_as_ushort(sl);
+      rowa[row] = make_uint4(umh | (umh << 16), uml | (ush << 16), ush | (usl << 16), __float_as_uint(rho));
     }
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
@@ -201,31 +215,31 @@ ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq
 
 template <int NV>
 static void launch_ln_fold_first_t(const float* h, int S, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
-                                   const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch, int rev,
-                                   cudaStream_t stream) {
+                                   const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch,
+                                   uint4* rowa, int rev, cudaStream_t stream) {
   const int runs = (T + 23) / 24;
   const int run_len = (T + runs - 1) / runs;
   const int tasks = S * runs;
   const int blocks = (tasks + 3) / 4;
   const size_t smem1 = (size_t)4 * NV * 128 * sizeof(float);
   if (out1 != nullptr)
-    ln_fold_first_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, sc1, ld1, out1, stats, pitch);
+    ln_fold_first_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa);
   else
-    ln_fold_first_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, nullptr, 0, nullptr, stats, pitch);
+    ln_fold_first_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, nullptr, 0, nullptr, stats, pitch, rowa);
 }
 
 int launch_ln_fold_first(const float* h, int M, int D, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
-                         const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch,
+                         const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch, uint4* rowa,
                          cudaStream_t stream, int rev) {
   MMDM_REQUIRE(D == 128 || D == 256 || D == 512 || D == 1024, "ln_fold_first: unsupported latent dim %d", D);
   MMDM_REQUIRE((ld0 % 4) == 0 && (out1 == nullptr || (ld1 % 4) == 0), "ln_fold_first: scale pitch %% 4");
   MMDM_REQUIRE(T > 0 && M % T == 0 && pitch >= M && stats != nullptr, "ln_fold_first: M=%d is not a whole number of T=%d row sequences", M, T);
   const int S = M / T;
   switch (D) {   // (32 KB of shared memory at most: no attribute needed)
-    case 128: launch_ln_fold_first_t<1>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
-    case 256: launch_ln_fold_first_t<2>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
-    case 512: launch_ln_fold_first_t<4>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
-    default: launch_ln_fold_first_t<8>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rev, stream); break;
+    case 128: launch_ln_fold_first_t<1>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
+    case 256: launch_ln_fold_first_t<2>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
+    case 512: launch_ln_fold_first_t<4>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
+    default: launch_ln_fold_first_t<8>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
   }
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;

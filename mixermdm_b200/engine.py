@@ -113,9 +113,9 @@ class _Packer:
     def __init__(self, device):
         self.device = device
         self.keep = []
-        # MMDM_LN_FOLD=1: build the composite tables of the LN fold; without them the engine runs the stand-alone
-        # LayerNorm kernel (the default while the fold does not beat it)
-        self.fold = os.environ.get("MMDM_LN_FOLD", "0") == "1"
+        # composite conditioning tables of the LN fold; MMDM_LN_FOLD=0: none, the engine then runs the
+        # stand-alone LayerNorm kernel at every frame count
+        self.fold = os.environ.get("MMDM_LN_FOLD", "1") != "0"
 
     def bf16(self, t):
         t = t.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()

@@ -52,11 +52,15 @@ def linear_bf16(a, w, *, mode, out, bias=None, resid=None, out_bf16=None, vt=Non
             ep.lnp_scale1, ep.lnp_ld1, ep.lnp_out1 = ptr(lp["scale1"]).value, lp["scale1"].stride(0), ptr(lp["out1"]).value
         ep.lnp_stats, ep.lnp_pitch = ptr(lp["stats"]).value, lp["stats"].stride(0) // 2
         ep.lnp_T, ep.lnp_rows, ep.lnp_dup_seq = lp["T"], lp.get("rows", 0), lp.get("dup_seq", 0)
+        if lp.get("rowa") is not None:   # (M', 4) int32
+            ep.lnp_rowa = ptr(lp["rowa"]).value
     if ln_consume is not None:
         lc = ln_consume
         assert lc["g"].stride(0) == lc["b"].stride(0)
         ep.lnc_stats, ep.lnc_pitch = ptr(lc["stats"]).value, lc["stats"].stride(0) // 2
         ep.lnc_g, ep.lnc_b, ep.lnc_ld = ptr(lc["g"]).value, ptr(lc["b"]).value, lc["g"].stride(0)
+        if lc.get("rowa") is not None:
+            ep.lnc_rowa = ptr(lc["rowa"]).value
     with torch.cuda.device(a.device):   # kernels launch on the tensors' device, whatever the current one is
         check(lib.mmdm_linear_bf16(ptr(a), C.c_int(a.stride(0)), ptr(w), C.c_int(w.stride(0)), M, N, K, C.byref(ep),
                                    cur_stream()), "mmdm_linear_bf16")

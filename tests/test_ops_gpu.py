@@ -95,7 +95,9 @@ def test_ln_fold_resid_producer_and_consumers(ops, S, T, D, N2, dual):
     hg0 = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
     hg1 = torch.empty(M, D, dtype=torch.bfloat16, device="cuda") if dual else None
     h_out = h.clone()
-    lp = dict(scale0=sc0, out0=hg0, stats=stats, T=T)
+    # finished per-row values (-mean, 1 / rstd as bf16 pairs; rstd), written by the row pass behind the GEMM
+    rowa = torch.zeros(M, 4, dtype=torch.int32, device="cuda")
+    lp = dict(scale0=sc0, out0=hg0, stats=stats, T=T, rowa=rowa)
     if dual:
         lp.update(scale1=sc1, out1=hg1)
     ops.linear_bf16(a, w, mode=EPI_RESID_LN, out=h_out, bias=b, resid=h_out, ln_produce=lp)
@@ -106,12 +108,20 @@ def test_ln_fold_resid_producer_and_consumers(ops, S, T, D, N2, dual):
     assert _relerr(hg0, ref_h * (1 + sc0[seq])) < 4e-3
     ref_stats = torch.stack([ref_h.view(M, D // 64, 64).sum(-1).t(), (ref_h ** 2).view(M, D // 64, 64).sum(-1).t()], -1)
     assert (stats - ref_stats).abs().max().item() < 2e-3 and _relerr(stats, ref_stats) < 1e-5
+    ref_rstd = (ref_h.var(1, unbiased=False) + 1e-6).rsqrt()
+    assert _relerr(rowa[:, 3].contiguous().view(torch.float32), ref_rstd) < 1e-5
+    def pair(w):   # (low, high) bf16 halves of a 32-bit word as fp32
+        return ((w & 0xFFFF) << 16).view(torch.float32), (w & -65536).view(torch.float32)
+    mh, _ = pair(rowa[:, 0].contiguous())
+    ml, sh = pair(rowa[:, 1].contiguous())
+    _, sl = pair(rowa[:, 2].contiguous())
+    assert _relerr(-(mh + ml), ref_h.mean(1)) < 1e-4 and _relerr(sh + sl, 1 / ref_rstd) < 1e-4
     w2 = _rand((N2, D), 37, 1 / math.sqrt(D), dtype=torch.bfloat16)
     c2 = _rand((N2,), 38)
     cases = [(hg0, sc0, sh0)] + ([(hg1, sc1, sh1)] if dual else [])
     for hg, sc, sh in cases:
         gb = torch.cat([(1 + sc) @ w2.float().t(), sh @ w2.float().t() + c2], 1).contiguous()
-        lc = dict(stats=stats, g=gb[:, :N2], b=gb[:, N2:])
+        lc = dict(stats=stats, g=gb[:, :N2], b=gb[:, N2:], rowa=rowa)
         ref = _ln_ref(ref_h, sc, sh, T) @ w2.float().t() + c2
         out = torch.empty(M, N2, dtype=torch.bfloat16, device="cuda")
         ops.linear_bf16(hg, w2, mode=EPI_BF16_LN, out=out, T=T, ln_consume=lc)
@@ -124,7 +134,7 @@ def test_ln_fold_resid_producer_and_consumers(ops, S, T, D, N2, dual):
         vt = torch.zeros(S * H, hd, Tp, dtype=torch.bfloat16, device="cuda")
         gb = torch.cat([(1 + sc0) @ w2.float().t(), sh0 @ w2.float().t() + c2], 1).contiguous()
         ops.linear_bf16(hg0, w2, mode=EPI_BF16_LN, out=qk, T=T, H=H, hd=hd, Tp=Tp, vt=vt, vt_col0=2 * D,
-                        ln_consume=dict(stats=stats, g=gb[:, :N2], b=gb[:, N2:]))
+                        ln_consume=dict(stats=stats, g=gb[:, :N2], b=gb[:, N2:], rowa=rowa))
         ref = _ln_ref(ref_h, sc0, sh0, T) @ w2.float().t() + c2
         assert _relerr(qk, ref[:, :2 * D]) < 8e-3
         ref_vt = ref[:, 2 * D:].view(S, T, H, hd).permute(0, 2, 3, 1).reshape(S * H, hd, T)

@@ -322,16 +322,21 @@ def test_sampler_rejects_what_the_reference_path_never_uses(golden):
 #   ~|c| (worst case 6x the error of Mixer.forward); the DDIM update is a_t * prediction + b_t * x with a_t growing
 #   from ~0 at the noisy end (state error 4e-4 at index 30 of the small goldens) to ~0.8 at the end, so the state
 #   inherits the guided error there: below 1e-2 for every index >= 2, 1.9e-2 at index 1.
-#   Which steps come out worst is a property of the rounding pattern, not of its size: two builds whose denoisers are
-#   equally close to the oracle at every step (2.8e-3 / 3.05e-3 mean, LN kernel vs LN folded into the GEMMs, tools/
-#   fold_ab.py) give 1.7e-2 vs 2.3e-2 at index 18 and 0.6e-2 vs 1.9e-2 at index 26, means 7.0e-3 vs 7.4e-3. Hence two
-#   gates: the MEAN over the 50 steps at the north star's 1e-2 and the single worst step at 3e-2.
+#   Which steps come out worst is a property of the rounding pattern, not of its size: the two code paths of the engine
+#   - stand-alone LayerNorm kernel (what this geometry runs by default) and LayerNorm folded into the GEMMs (the default
+#   from 256 frames on, forced here with MMDM_LN_FOLD=2) - have denoisers equally close to the oracle at every step (2.8e-3
+#   / 3.05e-3 mean, tools/fold_ab.py) and give 1.7e-2 vs 2.3e-2 for Mixer.forward at index 18, 0.6e-2 vs 1.9e-2 at index
+#   26, means 7.0e-3 vs 7.4e-3; the state after the last step (3x Mixer.forward's error there) 1.9e-2 vs 3.2e-2. Hence:
+#   the MEAN of Mixer.forward over the 50 steps at the north star's 1e-2, its single worst step at 3e-2, the state at
+#   2.5e-2 (LayerNorm kernel) / 4e-2 (folded).
 TOL_MIXER_STEP = 3e-2
 TOL_MIXER_MEAN = 1e-2
 TOL_GUIDED_STATE = 2.5e-2
+TOL_GUIDED_STATE_FOLD = 4e-2
 
 
-def test_every_ddim_step_teacher_forced_vs_reference_chain():
+@pytest.mark.parametrize("ln_fold", ["kernel", "folded"])
+def test_every_ddim_step_teacher_forced_vs_reference_chain(ln_fold, monkeypatch):
     """All 50 DDIM indices, each fed the REFERENCE's own x_t (tests/golden/reference_chain.npz: the reference's
     trajectory, rounded to fp16 between steps so that the stored inputs are exactly what it saw).
     Gates per step: (a) both denoisers' outputs against the fp32 oracle (itself pinned to this chain on the CPU) at the
@@ -340,6 +345,8 @@ def test_every_ddim_step_teacher_forced_vs_reference_chain():
     import json
     import os
     from helpers import GOLDEN
+    monkeypatch.setenv("MMDM_LN_FOLD", "2" if ln_fold == "folded" else "0")   # read when the engine is built
+    tol_state = TOL_GUIDED_STATE_FOLD if ln_fold == "folded" else TOL_GUIDED_STATE
     ch = np.load(os.path.join(GOLDEN, "reference_chain.npz"))
     with open(os.path.join(GOLDEN, "reference_chain.json")) as f:
         meta = json.load(f)
@@ -385,7 +392,7 @@ def test_every_ddim_step_teacher_forced_vs_reference_chain():
         mixer_sum += e_net
         assert e_den < TOL_BF16, f"DDIM index {idx}: denoiser outputs off by {e_den:.3e}"
         assert e_net < TOL_MIXER_STEP, f"DDIM index {idx}: Mixer.forward off by {e_net:.3e}"
-        assert e < TOL_GUIDED_STATE, f"DDIM index {idx}: state off by {e:.3e}"
+        assert e < tol_state, f"DDIM index {idx}: state off by {e:.3e}"
     report("worst per-step denoiser output over the 50 teacher-forced steps", worst["den"])
     report("worst per-step Mixer.forward over the 50 teacher-forced steps", worst["mixer"])
     assert report("mean per-step Mixer.forward over the 50 teacher-forced steps", mixer_sum / 50) < TOL_MIXER_MEAN

@@ -36,17 +36,18 @@ xf = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
 stats = torch.zeros(D // 64, M, 2, device=dev)
 gb3 = torch.randn(S, 2 * 3 * D, device=dev, generator=g) * 0.1
 gbf = torch.randn(S, 2 * F, device=dev, generator=g) * 0.1
-lp1 = dict(scale0=mod[:, :D], out0=xn, stats=stats, T=T)
-lp2 = dict(scale0=mod[:, :D], out0=xn, scale1=mod[:, 2 * D:3 * D], out1=xf, stats=stats, T=T)
+rowa = torch.zeros(M, 4, dtype=torch.int32, device=dev)
+lp1 = dict(scale0=mod[:, :D], out0=xn, stats=stats, T=T, rowa=rowa)
+lp2 = dict(scale0=mod[:, :D], out0=xn, scale1=mod[:, 2 * D:3 * D], out1=xf, stats=stats, T=T, rowa=rowa)
 
 runs = {
     "proj_ln": (lambda: ops.linear_bf16(x, w_o, mode=EPI_RESID_LN, out=h, bias=b1, resid=h, ln_produce=lp1), 2.0 * M * D * D),
     "proj_ln2": (lambda: ops.linear_bf16(x, w_o, mode=EPI_RESID_LN, out=h, bias=b1, resid=h, ln_produce=lp2), 2.0 * M * D * D),
     "ffn2_ln": (lambda: ops.linear_bf16(mid, w2, mode=EPI_RESID_LN, out=h, bias=bd, resid=h, ln_produce=lp1), 2.0 * M * D * F),
     "qkv_ln": (lambda: ops.linear_bf16(x, w_qkv, mode=EPI_BF16_LN, out=qk, vt=vt, vt_col0=2 * D, T=T, H=H, hd=hd, Tp=Tp,
-                                       ln_consume=dict(stats=stats, g=gb3[:, :3 * D], b=gb3[:, 3 * D:])), 2.0 * M * 3 * D * D),
+                                       ln_consume=dict(stats=stats, g=gb3[:, :3 * D], b=gb3[:, 3 * D:], rowa=rowa)), 2.0 * M * 3 * D * D),
     "ffn1_ln": (lambda: ops.linear_bf16(x, w1, mode=EPI_GELU_BF16_LN, out=mid, T=T,
-                                        ln_consume=dict(stats=stats, g=gbf[:, :F], b=gbf[:, F:])), 2.0 * M * F * D),
+                                        ln_consume=dict(stats=stats, g=gbf[:, :F], b=gbf[:, F:], rowa=rowa)), 2.0 * M * F * D),
     "qkv": (lambda: ops.linear_bf16(x, w_qkv, mode=EPI_BF16, out=qk, bias=b3, vt=vt, vt_col0=2 * D, T=T, H=H, hd=hd, Tp=Tp), 2.0 * M * 3 * D * D),
     "proj": (lambda: ops.linear_bf16(x, w_o, mode=EPI_RESID, out=h, bias=b1, resid=h), 2.0 * M * D * D),
     "ffn1": (lambda: ops.linear_bf16(x, w1, mode=EPI_GELU_BF16, out=mid, bias=bf), 2.0 * M * F * D),

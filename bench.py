@@ -125,7 +125,7 @@ def ncu_traffic(batch, frames, mode):
     the configuration that was profiled (batch 32 x 300 frames, mode 4), otherwise `traffic` is null."""
     if not (batch == 32 and frames == 300 and mode == 4):
         return {}, None
-    for name in ("r02_kernel_traffic.json", "r01_kernel_traffic.json"):
+    for name in ("r02b_kernel_traffic.json", "r02_kernel_traffic.json", "r01_kernel_traffic.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             with open(path) as f:

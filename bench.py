@@ -12,9 +12,11 @@ Prints ONE JSON line (rank 0).
 `value`   : samples/s with cond + noise already resident in HBM, timed with CUDA events, max over ranks.
 `e2e`     : the same loop through the public API (distributed.sample_sharded -> MixerDiffusion.ddim_sample_loop) with
             pinned HOST inputs: H2D of cond+noise and D2H of the result inside the timed region.
-`roofline`: dominant kernel class (tcgen05 GEMMs) - algorithmic FLOPs / CUDA-event time per launch, measured in a
-            separate eager pass with events around every launch of the same step (per-launch events cannot be
-            recorded inside a CUDA-graph replay); `roofline_mix` is the fused HBM-bound mix/sampler kernel.
+`roofline`: the dominant kernel of the step, the QKV-class projection GEMM (tensor-bound) - algorithmic FLOPs / CUDA-event
+            time per launch, measured in a separate eager pass with events around every launch of the same step
+            (per-launch events cannot be recorded inside a CUDA-graph replay). `roofline_all_gemms`: the same over every
+            tcgen05 GEMM launch of the step (the quantity rounds 1 / 2a reported as `roofline`); `roofline_resid`: the
+            HBM-bound residual GEMMs against the HBM peak; `roofline_mix`: the fused HBM-bound mix/sampler kernel.
 `cpu_baseline` / `--impl reference`: the CPU port of the reference path (oracle/, torch fp32 on all host cores; the
             Python reference itself cannot travel to the GPU box) on a bounded sample of the same workload.
 """
@@ -414,6 +416,9 @@ def main():
 
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it there) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
@@ -526,15 +531,39 @@ def main():
     gem_fl = sum(p["flops"] for p in gem)
     gem_n = sum(p["launches"] for p in gem)
     achieved_tf = gem_fl / (gem_ms * 1e-3) / 1e12 if gem_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (all tcgen05 GEMMs of the step)",
-                "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tflops_sustained"],
-                "traffic": traffic.get("gemm_class", {}).get("dram_bytes_per_launch"),
-                "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the GEMM launches of one DDIM "
-                                   f"step, committed capture {traffic_file} (not this run)") if traffic else None,
+    tsrc = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, committed launch list {traffic_file} "
+            f"(not this run)") if traffic else None
+    roofline_all = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (all tcgen05 GEMMs of the step, HBM-bound residual GEMMs "
+                                                 "and the M = 128 conditioning GEMMs included)",
+                    "achieved": achieved_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved_tf / peaks["tflops_sustained"],
+                    "traffic": traffic.get("gemm_class", {}).get("dram_bytes_per_launch"), "traffic_source": tsrc,
+                    "launches": gem_n, "avg_launch_us": 1e3 * gem_ms / max(gem_n, 1),
+                    "flops_per_launch": gem_fl / max(gem_n, 1), "share_of_step": gem_ms / tot_ms if tot_ms else None}
+    # the dominant kernel of the step: the QKV-class projections (self-attention in-proj, cross-attention q / kv)
+    qkv = [p for p in prof if p["name"] == "gemm_qkv"]
+    q_ms, q_fl, q_n = (qkv[0]["ms"], qkv[0]["flops"], qkv[0]["launches"]) if qkv else (0.0, 0.0, 0)
+    q_tf = q_fl / (q_ms * 1e-3) / 1e12 if q_ms > 0 else 0.0
+    q_kernel = "gemm_bf16_tn_2cta_kernel<8>" if "gemm_bf16_tn_2cta_kernel<8>" in traffic else "gemm_bf16_tn_2cta_kernel<0>"
+    roofline = {"bound": "tensor", "kernel": f"{q_kernel} (gemm_qkv: the QKV-class projections, the largest share of the step)",
+                "achieved": q_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": q_tf / peaks["tflops_sustained"],
+                "traffic": traffic.get(q_kernel, {}).get("dram_bytes_per_launch"), "traffic_source": tsrc,
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step), of measured",
-                "launches": gem_n, "avg_launch_us": 1e3 * gem_ms / max(gem_n, 1),
-                "flops_per_launch": gem_fl / max(gem_n, 1), "share_of_step": gem_ms / tot_ms if tot_ms else None}
+                "launches": q_n, "avg_launch_us": 1e3 * q_ms / max(q_n, 1), "flops_per_launch": q_fl / max(q_n, 1),
+                "share_of_step": q_ms / tot_ms if tot_ms else None}
+    # the HBM-bound GEMMs: out-projection / FFN-2 + residual (+ the next AdaLN site's bf16 operands with the LN fold)
+    res = [p for p in prof if p["name"] in ("gemm_proj", "gemm_ffn2")]
+    r_ms, r_by, r_n = sum(p["ms"] for p in res), sum(p["bytes"] for p in res), sum(p["launches"] for p in res)
+    r_kernel = "gemm_bf16_tn_2cta_kernel<10>" if "gemm_bf16_tn_2cta_kernel<10>" in traffic else "gemm_bf16_tn_2cta_kernel<2>"
+    roofline_resid = None
+    if r_ms > 0:
+        r_gbs = r_by / (r_ms * 1e-3) / 1e9
+        roofline_resid = {"bound": "hbm", "kernel": f"{r_kernel} (gemm_proj + gemm_ffn2: residual GEMMs)", "achieved": r_gbs,
+                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r_gbs / peaks["hbm_gbs"],
+                          "traffic": traffic.get(r_kernel, {}).get("dram_bytes_per_launch"), "traffic_source": tsrc,
+                          "bytes_per_launch": r_by / max(r_n, 1), "launches": r_n, "avg_launch_us": 1e3 * r_ms / max(r_n, 1),
+                          "share_of_step": r_ms / tot_ms if tot_ms else None,
+                          "accounting": "both GEMM operands once + fp32 residual row in + fp32 row out + bf16 operand(s) out"}
     mixp = [p for p in prof if p["name"] == "mix_cfg_ddim"]
     roofline_mix = None
     if mixp and mixp[0]["ms"] > 0:
@@ -548,7 +577,8 @@ def main():
                        "ms_per_ddim_step": p["ms"] / args.profile_steps, "share": p["ms"] / tot_ms if tot_ms else None,
                        "tflops": (p["flops"] / (p["ms"] * 1e-3) / 1e12) if p["ms"] > 0 and p["flops"] > 0 else None,
                        "frac_of_sustained_peak": (p["flops"] / (p["ms"] * 1e-3) / 1e12 / peaks["tflops_sustained"])
-                       if p["ms"] > 0 and p["flops"] > 0 else None}
+                       if p["ms"] > 0 and p["flops"] > 0 else None,
+                       "gbs": (p["bytes"] / (p["ms"] * 1e-3) / 1e9) if p["ms"] > 0 and p["bytes"] > 0 else None}
                       for p in prof), key=lambda d: -d["ms_per_ddim_step"])
 
     sub3 = sub4 = None
@@ -584,6 +614,8 @@ def main():
         "gpu_launches": launches,
         "clocks": clock_info,
         "roofline": roofline,
+        "roofline_all_gemms": roofline_all,
+        "roofline_resid": roofline_resid,
         "roofline_mix": roofline_mix,
         "kernels": kernels,
         "config3": sub3,

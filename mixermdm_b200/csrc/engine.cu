@@ -268,7 +268,17 @@ static int next_dir(mmdm_handle* h, bool flip = true) {
 
 static int gemm(mmdm_handle* h, const char* tag, const bf16* A, int lda, const void* W, int ldw, int M, int N, int K,
                 const GemmEpi& ep, cudaStream_t st, bool flip = true) {
-  Scope sc(h, tag, st, 2.0 * M * N * K);
+  // algorithmic bytes: both operands once + what the epilogue reads and writes (for the HBM-bound residual GEMMs)
+  double bytes = 2.0 * M * K + 2.0 * N * K;
+  const double mn = (double)M * N;
+  switch (ep.mode) {
+    case EPI_RESID: bytes += 8.0 * mn + (ep.out_bf16 ? 2.0 * mn : 0.0); break;
+    case EPI_RESID_LN: bytes += 8.0 * mn + 2.0 * mn * (ep.lnp_out1 ? 2 : 1); break;
+    case EPI_EMBED_PE: case EPI_EMBED_PE_LN: bytes += 4.0 * mn * (ep.dup_row_offset ? 2 : 1); break;
+    case EPI_F32: case EPI_FINAL: case EPI_SIGMOID_F32: bytes += 4.0 * mn; break;
+    default: bytes += 2.0 * mn; break;
+  }
+  Scope sc(h, tag, st, 2.0 * M * N * K, bytes);
   GemmEpi e = ep;
   e.rev = next_dir(h, flip);
   return launch_gemm(A, lda, reinterpret_cast<const bf16*>(W), ldw, M, N, K, e, st);

@@ -1446,7 +1446,17 @@ static int launch_mode(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
   if (N % 256 == 0 && M >= 512 && use_2cta() && (!mode_resid(MODE) || (ep.vec_ok && ep.bias_ok16)) &&
       (!mode_ln_consumer(MODE) || (ep.T >= 256 && ep.vec_ok && ep.lnc_rowa != nullptr)))
     return launch_tc2<MODE>(A, lda, W, ldw, M, N, K, ep, stream);
-  if (N % 256 == 0 || N >= 1024) return launch_tc<256, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
+  if (N % 256 == 0 || N >= 1024) {
+    // One row of tiles (the conditioning GEMMs: M = sequences, weight-streaming bound): take the tile width that
+    // fills the last wave better, e.g. 81920 columns = 320 wide tiles (2.16 waves on 148 SMs) or 640 narrow ones (4.32)
+    if (M <= 128 && N % 128 == 0) {
+      const int sms = num_sms();
+      const int t256 = (N + 255) / 256, t128 = N / 128;
+      const double e256 = (double)t256 / (((t256 + sms - 1) / sms) * sms), e128 = (double)t128 / (((t128 + sms - 1) / sms) * sms);
+      if (e128 > e256 + 0.05) return launch_tc<128, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
+    }
+    return launch_tc<256, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
+  }
   return launch_tc<128, MODE>(A, lda, W, ldw, M, N, K, ep, stream);
 }
 

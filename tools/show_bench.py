@@ -13,6 +13,10 @@ for line in open(sys.argv[1]):
           f'model {d["model_tflops"]:.0f} TF/s  launches {d["gpu_launches"]}  clocks {d["clocks"]}')
     r = d["roofline"]
     print(f'roofline GEMM: {r["achieved"]:.0f} / {r["peak"]} TF/s = {r["frac"]:.3f}   share {r["share_of_step"]:.2f}')
+    for key in ("roofline_all_gemms", "roofline_resid"):
+        x = d.get(key)
+        if x:
+            print(f'{key}: {x["achieved"]:.0f} / {x["peak"]} {x["unit"]} = {x["frac"]:.3f}   share {x["share_of_step"]:.2f}')
     m = d.get("roofline_mix")
     if m:
         print(f'roofline mix : {m["achieved"]:.0f} / {m["peak"]} GB/s = {m["frac"]:.3f}   {m["avg_launch_us"]:.0f} us/launch')

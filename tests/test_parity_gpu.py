@@ -595,7 +595,7 @@ def test_full_size_batch32_loop_properties(full_model):
     assert torch.equal(a[21:22], one)
 
 
-@pytest.mark.parametrize("B,T", [(3, 257), (2, 400), (5, 256)])
+@pytest.mark.parametrize("B,T", [(3, 257), (2, 400), (5, 256), (1, 300)])
 def test_ln_fold_vs_layernorm_kernel_ragged_full_size(full_model, B, T, monkeypatch):
     """The two LayerNorm code paths of the engine on the full-size interaction denoiser at shapes whose row count is no
     multiple of the 256-row tiles (1542 / 1600 / 2560 rows; two sequences inside a tile at every offset): folded into
@@ -620,6 +620,16 @@ def test_ln_fold_vs_layernorm_kernel_ragged_full_size(full_model, B, T, monkeypa
         ref = mixer_oracle.denoiser({k: v.float() for k, v in sd.items()}, "denoiser2.", "interaction", x[:1], t[:1], cond[:1], 8)
     assert report(f"folded vs oracle, T={T}", relerr(outs["1"][:1], ref)) < TOL_BF16
     assert report(f"LayerNorm kernel vs oracle, T={T}", relerr(outs["0"][:1], ref)) < TOL_BF16
+    if B == 1:   # the individual denoiser on one sample: 300 rows, folded GEMMs on the single-CTA kernels (scalar epilogue)
+        for flag in ("0", "1"):
+            monkeypatch.setenv("MMDM_LN_FOLD", flag)
+            mix.denoiser1._standalone = None
+            outs[flag] = mix.denoiser1(x[..., :262].contiguous().to(DEV), t.to(DEV), cond=cond[:, :768].contiguous().to(DEV)).clone()
+        mix.denoiser1._standalone = None
+        with torch.no_grad():
+            ref = mixer_oracle.denoiser({k: v.float() for k, v in sd.items()}, "denoiser1.", "individual", x[..., :262], t, cond[:, :768], 8)
+        assert report("individual denoiser, 300 rows, folded vs oracle", relerr(outs["1"], ref)) < TOL_BF16
+        assert report("individual denoiser, 300 rows, LayerNorm kernel vs oracle", relerr(outs["0"], ref)) < TOL_BF16
 
 
 @pytest.mark.parametrize("mode", [2, 4])

@@ -220,7 +220,7 @@ def run_reference_arm(args, rank, world):
                           "value_formula": "ref_batch / (ms_per_step / 1e3 * 50 / ref_ddim_steps)"},
         "ms_per_denoise_step_per_sample": s_per_sample_step * 1e3,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(cfg_id, B, T, mode, world):
@@ -365,7 +365,30 @@ def bench_config4(dev, batch=128, frames=300, iters=20, warmup=3):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL's version banner does) are
+    pointed at stderr for the rest of the process; emit() writes the line to the original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -411,7 +434,7 @@ def main():
                     "dtype": "bf16" if args.config == 3 else "f32", "data": "synthetic",
                     "config": {"workload": sub["workload"]}, "roofline": rl}
             line.update({k: v for k, v in sub.items() if k not in ("workload", "roofline")})
-            print(json.dumps(line), flush=True)
+            emit(line)
         return
 
     dist = None
@@ -622,7 +645,7 @@ def main():
         "config4": sub4,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

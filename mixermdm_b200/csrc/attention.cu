@@ -185,11 +185,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     fence_barrier_init();
   }
+  pdl_trigger();   // (common.cuh: programmatic dependent launch)
   if (warp == 8) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
+  pdl_wait();
 
   auto item_sh = [&](int k, int& s, int& h) {
     int item = (int)blockIdx.x + k * (int)gridDim.x;
@@ -618,8 +620,10 @@ static int launch_attention_t(const unsigned long long* kmask, const __nv_bfloat
   p.tau_raw = 8.0f / p.scale_log2;
   const int items = S * H;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  if (kmask != nullptr) attention_kernel<HD, true><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  else attention_kernel<HD, false><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  if (kmask != nullptr)
+    MMDM_CHECK_CUDA(launch_maybe_pdl(attention_kernel<HD, true>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
+  else
+    MMDM_CHECK_CUDA(launch_maybe_pdl(attention_kernel<HD, false>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

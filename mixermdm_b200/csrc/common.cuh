@@ -67,10 +67,39 @@ struct DeviceGuard {
   }
 };
 
+// Programmatic dependent launch: a kernel launched with it may start - block by block, as the kernel in front of it in
+// the stream frees SMs - before that kernel has finished; it runs its prologue (barrier init, TMEM allocation,
+// descriptor prefetch) and then waits in pdl_wait() for the predecessor's completion and memory flush. The predecessor
+// allows this by calling pdl_trigger() (all blocks, at their start). MMDM_PDL=0 launches such kernels the ordinary way
+// (both device calls are no-ops then). Used by the CTA-pair GEMM and the attention kernel, which follow each other
+// directly (33.91 / 34.00 against 33.86 / 33.86 samples/s in one job); extending it to the single-CTA GEMM and the row
+// kernels made the step 3 % SLOWER (32.0 against 33.0): their early-resident blocks sit in the wait on SMs the next
+// persistent kernel needs whole.
+bool pdl_enabled();
+#if defined(__CUDACC__)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -1074,11 +1074,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     fence_barrier_init();
   }
+  pdl_trigger();   // the next kernel of the stream may take this SM as soon as this CTA is gone
   if (warp == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -1392,7 +1394,8 @@ static int launch_tc2(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * ((N + C::BN - 1) / C::BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm_bf16_tn_2cta_kernel<MODE><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, em, ep, M, N, K);
+  MMDM_CHECK_CUDA(launch_maybe_pdl(gemm_bf16_tn_2cta_kernel<MODE>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, stream, tmA, tmB, em,
+                                   ep, M, N, K));
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

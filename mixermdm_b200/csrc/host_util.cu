@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mmdm {
@@ -21,6 +22,15 @@ int current_device() {
   int d = 0;
   if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
   return d < kMaxDevices ? d : kMaxDevices - 1;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MMDM_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 int device_sm_count() {

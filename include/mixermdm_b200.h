@@ -94,6 +94,11 @@ typedef struct mmdm_epilogue {
    * applies the mean / shift terms as one extra k step of the MMA (needs T >= 256). */
   void* lnp_rowa;
   const void* lnc_rowa;
+  /* optional, producers: per-row offsets. Operand(s) and row sums are then those of h - lnp_moff_in[r] (an estimate of
+   * the row mean keeps the bf16 rounding of the operand free of it; any value gives the same result up to rounding); the
+   * row pass stores the row's mean, lnp_moff_in[r] + mean(h - lnp_moff_in[r]), in lnp_moff_out for the next site. */
+  const float* lnp_moff_in;
+  float* lnp_moff_out;
 } mmdm_epilogue;
 
 /* D[M,N] = A[M,K] * W[N,K]^T, bf16 operands (row pitches lda/ldw in elements), fp32 accumulation (tcgen05).

@@ -28,7 +28,7 @@ class Epilogue(C.Structure):
         ("lnp_dup_seq", C.c_int32),
         ("lnc_stats", C.c_void_p), ("lnc_pitch", C.c_int64),
         ("lnc_g", C.c_void_p), ("lnc_b", C.c_void_p), ("lnc_ld", C.c_int32),
-        ("lnp_rowa", C.c_void_p), ("lnc_rowa", C.c_void_p),
+        ("lnp_rowa", C.c_void_p), ("lnc_rowa", C.c_void_p), ("lnp_moff_in", C.c_void_p), ("lnp_moff_out", C.c_void_p),
     ]
 
 

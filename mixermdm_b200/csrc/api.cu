@@ -39,6 +39,7 @@ GemmEpi to_internal(const mmdm_epilogue& e) {
   g.lnc_g = e.lnc_g; g.lnc_b = e.lnc_b; g.lnc_ld = e.lnc_ld;
   g.lnp_rowa = reinterpret_cast<uint4*>(e.lnp_rowa);
   g.lnc_rowa = reinterpret_cast<const uint4*>(e.lnc_rowa);
+  g.lnp_moff_in = e.lnp_moff_in; g.lnp_moff_out = e.lnp_moff_out;
   return g;
 }
 }  // namespace mmdm

@@ -95,6 +95,7 @@ struct Workspace {
   float2* stat[3] = {nullptr, nullptr, nullptr};   // LN fold: row sums per 64-column slot [Dmax / 64][M]; block input /
                                                    // after self attention / after cross attention
   uint4* rowa[3] = {nullptr, nullptr, nullptr};    // ... and the finished per-row values (M)
+  float* moff[3] = {nullptr, nullptr, nullptr};    // ... and the row means (M): the next site's per-row operand offsets
   int *map0 = nullptr, *map1 = nullptr, *tmap = nullptr;
   float* text[3] = {nullptr, nullptr, nullptr};   // per net: (nslices*Bx + 1, D)
   float* temb_tab[3] = {nullptr, nullptr, nullptr};  // per net: (nsteps, D)
@@ -222,6 +223,7 @@ static void carve(const mmdm_handle* h, int B, int T, void* base, Workspace* w, 
     ws.gb1 = c.take<float>((size_t)S * compmax);
     for (int i = 0; i < 3; ++i) ws.stat[i] = c.take<float2>((size_t)(Dmax / 64) * M);
     for (int i = 0; i < 3; ++i) ws.rowa[i] = c.take<uint4>(M);
+    for (int i = 0; i < 3; ++i) ws.moff[i] = c.take<float>(M);
   }
   ws.mod0 = c.take<float>((size_t)S * adamax);
   ws.mod1 = c.take<float>((size_t)S * adamax);
@@ -411,9 +413,12 @@ static void as_consumer(GemmEpi& e, int mode, const FoldSite& fs, const Workspac
   e.lnc_g = fs.g; e.lnc_b = fs.b; e.lnc_ld = fs.ld;
   e.T = T;
 }
-static void as_producer(GemmEpi& e, int mode, const Workspace& ws, int si, int M, int T, const float* sc0, int ld0, bf16* o0,
+// si: the AdaLN site the GEMM produces for (statistics set); sp: the site before it on the same rows, whose row means
+// serve as the operand offsets
+static void as_producer(GemmEpi& e, int mode, const Workspace& ws, int si, int sp, int M, int T, const float* sc0, int ld0, bf16* o0,
                         const float* sc1 = nullptr, int ld1 = 0, bf16* o1 = nullptr) {
   e.mode = mode;
+  e.lnp_moff_in = ws.moff[sp]; e.lnp_moff_out = ws.moff[si];
   e.lnp_stats = ws.stat[si]; e.lnp_rowa = ws.rowa[si]; e.lnp_pitch = M; e.lnp_T = T;
   e.lnp_scale0 = sc0; e.lnp_ld0 = ld0; e.lnp_out0 = o0;
   e.lnp_scale1 = sc1; e.lnp_ld1 = ld1; e.lnp_out1 = o1;
@@ -454,8 +459,8 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
   er.mode = EPI_RESID; er.out = hres; er.resid = hres; er.ldo = D;
   er.bias = b.sa_out_b;
   if (fold) {   // next AdaLN site on these rows: the cross attention's query norm, or the FFN norm
-    if (has_ca) as_producer(er, EPI_RESID_LN, ws, 1, M, T, m.caq, m.ld_caq, ws.xn);
-    else as_producer(er, EPI_RESID_LN, ws, 1, M, T, m.ffn, m.ld_ffn, ws.xn);
+    if (has_ca) as_producer(er, EPI_RESID_LN, ws, 1, 0, M, T, m.caq, m.ld_caq, ws.xn);
+    else as_producer(er, EPI_RESID_LN, ws, 1, 0, M, T, m.ffn, m.ld_ffn, ws.xn);
   }
   MMDM_TRY(gemm(h, "gemm_proj", ws.att, D, b.sa_out_w, D, M, D, D, er, st));
 
@@ -474,7 +479,7 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
     MMDM_TRY(gemm(h, "gemm_qkv", ws.xf, D, b.ca_kv_w, D, M, 2 * D, D, ek, st, /*flip=*/false));   // same way as the q GEMM
     MMDM_TRY(attention(h, n, S, T, kvsrc == nullptr ? 1 : 0, st));
     er.bias = b.ca_out_b;
-    if (fold) as_producer(er, EPI_RESID_LN, ws, 2, M, T, m.ffn, m.ld_ffn, ws.xn);
+    if (fold) as_producer(er, EPI_RESID_LN, ws, 2, 1, M, T, m.ffn, m.ld_ffn, ws.xn);
     MMDM_TRY(gemm(h, "gemm_proj", ws.att, D, b.ca_out_w, D, M, D, D, er, st));
   }
 
@@ -489,8 +494,9 @@ static int run_block(mmdm_handle* h, int ni, int l, float* hres, const float* kv
   er.out_bf16 = bf16_copy;
   if (fold && l + 1 < n.w.L) {   // operands of the next block
     const Mods mn = block_mods(n, ws, l + 1);
-    if (has_ca && kvsrc == nullptr) as_producer(er, EPI_RESID_LN, ws, 0, M, T, mn.sa, mn.ld_sa, ws.xn, mn.xf, mn.ld_xf, ws.xf);
-    else as_producer(er, EPI_RESID_LN, ws, 0, M, T, mn.sa, mn.ld_sa, ws.xn);
+    const int sp = has_ca ? 2 : 1;
+    if (has_ca && kvsrc == nullptr) as_producer(er, EPI_RESID_LN, ws, 0, sp, M, T, mn.sa, mn.ld_sa, ws.xn, mn.xf, mn.ld_xf, ws.xf);
+    else as_producer(er, EPI_RESID_LN, ws, 0, sp, M, T, mn.sa, mn.ld_sa, ws.xn);
   }
   MMDM_TRY(gemm(h, "gemm_ffn2", ws.mid, F, b.ffn_w2, F, M, D, F, er, st));
   return 0;
@@ -513,9 +519,9 @@ static int run_embed(mmdm_handle* h, int ni, int rows, int ln_rows, int dup, int
     const int Mb = dup ? 2 * ln_rows : ln_rows;   // rows entering the blocks = S * T
     Scope sc(h, "ln_modulate", st);
     if (n.w.kind == MMDM_NET_INTERACTION)
-      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, m0.xf, m0.ld_xf, ws.xf, ws.stat[0], S * T, ws.rowa[0], st, next_dir(h)));
+      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, m0.xf, m0.ld_xf, ws.xf, ws.stat[0], S * T, ws.rowa[0], ws.moff[0], st, next_dir(h)));
     else
-      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, nullptr, 0, nullptr, ws.stat[0], S * T, ws.rowa[0], st, next_dir(h)));
+      MMDM_TRY(launch_ln_fold_first(ws.h, Mb, D, T, m0.sa, m0.ld_sa, ws.xn, nullptr, 0, nullptr, ws.stat[0], S * T, ws.rowa[0], ws.moff[0], st, next_dir(h)));
   }
   return 0;
 }

@@ -317,15 +317,20 @@ struct LnProd {
                 // sequences at most unless T < 32): their scale values are fetched once per chunk, ahead of use
   int bnd;      // first row of sequence sb
   int lim;      // rows >= lim take no part (beyond M or beyond lnp_rows)
+  float m[8];   // row offsets (GemmEpi::lnp_moff_in) of the lane's 8 rows
 };
 __device__ __forceinline__ int ln_prod_seq(const GemmEpi& ep, const LnProd& lp, int row) {
   if (ep.lnp_T < 32) return row / ep.lnp_T;   // (more than two sequences per warp possible)
   return row < lp.bnd ? lp.sa : lp.sb;
 }
 __device__ __forceinline__ void ln_prod_begin(const GemmEpi& ep, LnProd& lp, int m_base, int lane, int M) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) lp.s1[i] = lp.s2[i] = 0.f;
   lp.lim = min(M, ep.lnp_rows);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    lp.s1[i] = lp.s2[i] = 0.f;
+    const int row = m_base + 4 * i + (lane >> 3);
+    lp.m[i] = (ep.lnp_moff_in != nullptr && row < lp.lim) ? __ldg(ep.lnp_moff_in + row) : 0.f;
+  }
   lp.sa = min(m_base, lp.lim - 1) / ep.lnp_T;
   lp.sb = min(m_base + 31, lp.lim - 1) / ep.lnp_T;
   lp.bnd = (lp.sa + 1) * ep.lnp_T;
@@ -419,22 +424,23 @@ __device__ __forceinline__ void epilogue_chunk_resid_t(const GemmEpi& ep, int m_
         *reinterpret_cast<uint2*>(ep.out_bf16 + off) = pk;
       }
       if (mode_ln_producer(MODE) && row < lp.lim) {
-        lp.s1[i] += (o.x + o.y) + (o.z + o.w);
-        lp.s2[i] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+        const float4 os = make_float4(o.x - lp.m[i], o.y - lp.m[i], o.z - lp.m[i], o.w - lp.m[i]);   // h - m_r
+        lp.s1[i] += (os.x + os.y) + (os.z + os.w);
+        lp.s2[i] += fmaf(os.x, os.x, os.y * os.y) + fmaf(os.z, os.z, os.w * os.w);
         const int sq = ln_prod_seq(ep, lp, row);
         *reinterpret_cast<uint2*>(ep.lnp_out0 + off) =
-            ln_prod_pack(o, ln_scale_pick(sc0, ep.lnp_scale0, ep.lnp_ld0, sq, lp.sa, lp.sb, cg));
+            ln_prod_pack(os, ln_scale_pick(sc0, ep.lnp_scale0, ep.lnp_ld0, sq, lp.sa, lp.sb, cg));
         if (ep.lnp_out1 != nullptr)
           *reinterpret_cast<uint2*>(ep.lnp_out1 + off) =
-              ln_prod_pack(o, ln_scale_pick(sc1, ep.lnp_scale1, ep.lnp_ld1, sq, lp.sa, lp.sb, cg));
+              ln_prod_pack(os, ln_scale_pick(sc1, ep.lnp_scale1, ep.lnp_ld1, sq, lp.sa, lp.sb, cg));
         if (mode_embed(MODE) && ep.dup_row_offset != 0) {   // the other CFG half: same h, its own modulation
           const size_t off2 = off + (size_t)ep.dup_row_offset * ep.ldo;
           const int dq = ep.lnp_dup_seq;
           *reinterpret_cast<uint2*>(ep.lnp_out0 + off2) =
-              ln_prod_pack(o, ln_scale_pick(sd0, ep.lnp_scale0, ep.lnp_ld0, sq + dq, lp.sa + dq, lp.sb + dq, cg));
+              ln_prod_pack(os, ln_scale_pick(sd0, ep.lnp_scale0, ep.lnp_ld0, sq + dq, lp.sa + dq, lp.sb + dq, cg));
           if (ep.lnp_out1 != nullptr)
             *reinterpret_cast<uint2*>(ep.lnp_out1 + off2) =
-                ln_prod_pack(o, ln_scale_pick(sd1, ep.lnp_scale1, ep.lnp_ld1, sq + dq, lp.sa + dq, lp.sb + dq, cg));
+                ln_prod_pack(os, ln_scale_pick(sd1, ep.lnp_scale1, ep.lnp_ld1, sq + dq, lp.sa + dq, lp.sb + dq, cg));
         }
       }
     }
@@ -802,7 +808,7 @@ __device__ __forceinline__ uint4 ln_row_finalize(float s1, float s2, float inv_d
 }
 // row pass behind the producers that do not finalise in their epilogue (single-CTA kernels, the embedding modes)
 __global__ void ln_rowstat_kernel(const float2* __restrict__ stats, long long pitch, int rows, int slots, float inv_d,
-                                  uint4* __restrict__ rowa) {
+                                  uint4* __restrict__ rowa, const float* __restrict__ moff_in, float* __restrict__ moff_out) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   float s1 = 0.f, s2 = 0.f;
@@ -818,6 +824,8 @@ __global__ void ln_rowstat_kernel(const float2* __restrict__ stats, long long pi
     }
   }
   rowa[row] = ln_row_finalize(s1, s2, inv_d);
+  // the row's mean (offset the producer subtracted + mean of what was left): the next site's offset
+  if (moff_out != nullptr) moff_out[row] = (moff_in != nullptr ? moff_in[row] : 0.f) + s1 * inv_d;
 }
 
 // L2 policies on the TMA epilogue's traffic (evict-first for the fp32 residual stream, evict-last for the bf16 operands the
@@ -877,10 +885,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, const EpiMa
   bool ln_row = false;
   const float* sc0 = nullptr;
   const float* sc1 = nullptr;
-  float s1 = 0.f, s2 = 0.f;
+  float s1 = 0.f, s2 = 0.f, moff = 0.f;
   if (LN) {
     const int lim = min(M, ep.lnp_rows);
     ln_row = row < lim;
+    if (ep.lnp_moff_in != nullptr && ln_row) moff = __ldg(ep.lnp_moff_in + row);   // operand / row sums of h - m_r
     const int sq = min(row, lim - 1) / ep.lnp_T;
     sc0 = ep.lnp_scale0 + (size_t)sq * ep.lnp_ld0;
     if (dual) sc1 = ep.lnp_scale1 + (size_t)sq * ep.lnp_ld1;
@@ -915,15 +924,16 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, const EpiMa
       const float4 o = make_float4(a.x + __uint_as_float(r[b][4 * j]) + bb.x, a.y + __uint_as_float(r[b][4 * j + 1]) + bb.y,
                                    a.z + __uint_as_float(r[b][4 * j + 2]) + bb.z, a.w + __uint_as_float(r[b][4 * j + 3]) + bb.w);
       sts128(addr, o);
+      const float4 os = make_float4(o.x - moff, o.y - moff, o.z - moff, o.w - moff);
       if (LN) {
-        s1 += (o.x + o.y) + (o.z + o.w);
-        s2 += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+        s1 += (os.x + os.y) + (os.z + os.w);
+        s2 += fmaf(os.x, os.x, os.y * os.y) + fmaf(os.z, os.z, os.w * os.w);
       }
       if (copy16) {
         uint2 p0, p1 = make_uint2(0u, 0u);
         if (LN) {
-          p0 = ln_prod_pack(o, __ldg(reinterpret_cast<const float4*>(sc0 + col0) + j));
-          if (dual) p1 = ln_prod_pack(o, __ldg(reinterpret_cast<const float4*>(sc1 + col0) + j));
+          p0 = ln_prod_pack(os, __ldg(reinterpret_cast<const float4*>(sc0 + col0) + j));
+          if (dual) p1 = ln_prod_pack(os, __ldg(reinterpret_cast<const float4*>(sc1 + col0) + j));
         } else {
           p0.x = pack_bf16x2(o.x, o.y);
           p0.y = pack_bf16x2(o.z, o.w);
@@ -1517,7 +1527,7 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
     const int lim = (ep.lnp_rows > 0 && ep.lnp_rows < M) ? ep.lnp_rows : M;
     const int rows = ep.dup_row_offset != 0 ? (int)ep.dup_row_offset + lim : lim;
     ln_rowstat_kernel<<<(rows + 63) / 64, 64, 0, stream>>>(ep.lnp_stats, ep.lnp_pitch, rows, N / kLnSlotCols, 1.0f / (float)N,
-                                                            ep.lnp_rowa);
+                                                            ep.lnp_rowa, ep.lnp_moff_in, ep.lnp_moff_out);
     MMDM_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1552,6 +1562,7 @@ static int launch_gemm_inner(const __nv_bfloat16* A, int lda, const __nv_bfloat1
   }
   if (mode_ln_producer(ep.mode)) {
     if (e2.lnp_rows <= 0 || e2.lnp_rows > M) e2.lnp_rows = M;
+    MMDM_REQUIRE(ep.lnp_moff_out == nullptr || ep.lnp_rowa != nullptr, "gemm: lnp_moff_out is written by the row pass that fills lnp_rowa");
     MMDM_REQUIRE(ep.lnp_stats && ep.lnp_scale0 && ep.lnp_out0 && ep.lnp_T >= 1 && (N % kLnSlotCols) == 0 && ep.ldo == N &&
                      ep.lnp_pitch >= e2.lnp_rows + ep.dup_row_offset && (ep.lnp_ld0 % 4) == 0 && (ep.lnp_ld1 % 4) == 0 &&
                      (reinterpret_cast<uintptr_t>(ep.lnp_scale0) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.lnp_scale1) & 15) == 0 &&

@@ -70,6 +70,12 @@ struct GemmEpi {
   // optional: finished per-row values for the CTA-pair consumers' aux k step, rowa[r] = (bf16 pairs of -mu and
   // 1/rho packed as the three operand words, rho as float bits), written by a small row pass behind the GEMM
   uint4* lnp_rowa = nullptr;
+  // optional per-row offsets: the operand(s) and the row sums are those of h - m_r, m_r = lnp_moff_in[r] (an estimate of
+  // the row mean: the previous AdaLN site's mean of the same row). The consumers need not know - they see a row whose mean
+  // is small - and the bf16 rounding of the operand no longer carries the row mean (it would be amplified by
+  // sqrt(1 + (mu/sigma)^2)). The row pass stores m_r + mean(h - m_r) = the row's mean in lnp_moff_out for the next site.
+  const float* lnp_moff_in = nullptr;
+  float* lnp_moff_out = nullptr;
   int lnp_dup_seq = 0;                   // EPI_EMBED_PE_LN with dup_row_offset: sequence offset of the duplicated rows
   // LN-fold consumer (EPI_BF16_LN / EPI_GELU_BF16_LN; uses T): K = latent dim of the normalised rows
   const float2* lnc_stats = nullptr;     // [lnc_slots][lnc_pitch]

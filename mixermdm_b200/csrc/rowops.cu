@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128)
 ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq, int run_len, int rev,
                      const float* __restrict__ sc0, int ld0, __nv_bfloat16* __restrict__ out0,
                      const float* __restrict__ sc1, int ld1, __nv_bfloat16* __restrict__ out1,
-                     float2* __restrict__ stats, long long pitch, uint4* __restrict__ rowa) {
+                     float2* __restrict__ stats, long long pitch, uint4* __restrict__ rowa, float* __restrict__ moff_out) {
   constexpr int D = NV * 128;
   constexpr int NM = DUAL ? 2 : 1;
   extern __shared__ float4 ln_smem[];   // [4 warps][NM][D/4]: 1 + scale
@@ -171,6 +171,17 @@ ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq
       for (int i = 0; i < NV; ++i) nx[i] = src[(size_t)(t + 1 - t0) * (D / 4) + i * 32 + lane];
     }
     const size_t row = (size_t)s * T + t;
+    // This pass sees the whole row: operand and row sums are those of the exactly centred row (GemmEpi::lnp_moff_in:
+    // the offset m_r is the row mean itself here), the mean goes to moff_out for the next site's producer.
+    float rsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) rsum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(rsum) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    }
+    if (moff_out != nullptr && lane == 0) moff_out[row] = mean;
     float t1 = 0.f, t2 = 0.f;   // whole-row sums, slots added in order
 #pragma unroll
     for (int i = 0; i < NV; ++i) {   // lanes 0-15 hold slot 2i, lanes 16-31 slot 2i + 1
@@ -216,30 +227,30 @@ ln_fold_first_kernel(const float* __restrict__ h, int S, int T, int runs_per_seq
 template <int NV>
 static void launch_ln_fold_first_t(const float* h, int S, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
                                    const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch,
-                                   uint4* rowa, int rev, cudaStream_t stream) {
+                                   uint4* rowa, float* moff_out, int rev, cudaStream_t stream) {
   const int runs = (T + 23) / 24;
   const int run_len = (T + runs - 1) / runs;
   const int tasks = S * runs;
   const int blocks = (tasks + 3) / 4;
   const size_t smem1 = (size_t)4 * NV * 128 * sizeof(float);
   if (out1 != nullptr)
-    ln_fold_first_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa);
+    ln_fold_first_kernel<NV, true><<<blocks, 128, 2 * smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, moff_out);
   else
-    ln_fold_first_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, nullptr, 0, nullptr, stats, pitch, rowa);
+    ln_fold_first_kernel<NV, false><<<blocks, 128, smem1, stream>>>(h, S, T, runs, run_len, rev, sc0, ld0, out0, nullptr, 0, nullptr, stats, pitch, rowa, moff_out);
 }
 
 int launch_ln_fold_first(const float* h, int M, int D, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
                          const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch, uint4* rowa,
-                         cudaStream_t stream, int rev) {
+                         float* moff_out, cudaStream_t stream, int rev) {
   MMDM_REQUIRE(D == 128 || D == 256 || D == 512 || D == 1024, "ln_fold_first: unsupported latent dim %d", D);
   MMDM_REQUIRE((ld0 % 4) == 0 && (out1 == nullptr || (ld1 % 4) == 0), "ln_fold_first: scale pitch %% 4");
   MMDM_REQUIRE(T > 0 && M % T == 0 && pitch >= M && stats != nullptr, "ln_fold_first: M=%d is not a whole number of T=%d row sequences", M, T);
   const int S = M / T;
   switch (D) {   // (32 KB of shared memory at most: no attribute needed)
-    case 128: launch_ln_fold_first_t<1>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
-    case 256: launch_ln_fold_first_t<2>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
-    case 512: launch_ln_fold_first_t<4>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
-    default: launch_ln_fold_first_t<8>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, rev, stream); break;
+    case 128: launch_ln_fold_first_t<1>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, moff_out, rev, stream); break;
+    case 256: launch_ln_fold_first_t<2>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, moff_out, rev, stream); break;
+    case 512: launch_ln_fold_first_t<4>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, moff_out, rev, stream); break;
+    default: launch_ln_fold_first_t<8>(h, S, T, sc0, ld0, out0, sc1, ld1, out1, stats, pitch, rowa, moff_out, rev, stream); break;
   }
   MMDM_CHECK_CUDA(cudaGetLastError());
   return 0;

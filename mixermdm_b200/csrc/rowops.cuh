@@ -10,10 +10,11 @@ int launch_ln_modulate(const float* h, int M, int D, int T, const float* mod0, i
                        cudaStream_t stream, int rev = 0);
 
 // LN fold, first block: out_m = bf16(h * (1 + sc_m[s, :])) (one or two sites) + per-row (sum, sum of squares) per 64-column
-// slot, stats[slot * pitch + row] - what the residual GEMMs' EPI_RESID_LN epilogue emits for the later blocks
+// slot, stats[slot * pitch + row] - what the residual GEMMs' EPI_RESID_LN epilogue emits for the later blocks; here of
+// the exactly centred row (h - mean), mean -> moff_out[row] (GemmEpi::lnp_moff_in of the next site's producer)
 int launch_ln_fold_first(const float* h, int M, int D, int T, const float* sc0, int ld0, __nv_bfloat16* out0,
                          const float* sc1, int ld1, __nv_bfloat16* out1, float2* stats, long long pitch, uint4* rowa,
-                         cudaStream_t stream, int rev = 0);
+                         float* moff_out, cudaStream_t stream, int rev = 0);
 
 // E[s, 0:D] = E[s, D:2D] = bf16(SiLU(temb[trow,:] + text[text_row[s],:]))   (row pitch 2D)
 // trow = step_ptr ? *step_ptr : temb_idx[s]

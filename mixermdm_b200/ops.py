@@ -54,6 +54,10 @@ def linear_bf16(a, w, *, mode, out, bias=None, resid=None, out_bf16=None, vt=Non
         ep.lnp_T, ep.lnp_rows, ep.lnp_dup_seq = lp["T"], lp.get("rows", 0), lp.get("dup_seq", 0)
         if lp.get("rowa") is not None:   # (M', 4) int32
             ep.lnp_rowa = ptr(lp["rowa"]).value
+        if lp.get("moff_in") is not None:   # (M',) fp32 per-row offsets
+            ep.lnp_moff_in = ptr(lp["moff_in"]).value
+        if lp.get("moff_out") is not None:
+            ep.lnp_moff_out = ptr(lp["moff_out"]).value
     if ln_consume is not None:
         lc = ln_consume
         assert lc["g"].stride(0) == lc["b"].stride(0)

@@ -98,16 +98,24 @@ def test_ln_fold_resid_producer_and_consumers(ops, S, T, D, N2, dual):
     # finished per-row values (-mean, 1 / rstd as bf16 pairs; rstd), written by the row pass behind the GEMM
     rowa = torch.zeros(M, 4, dtype=torch.int32, device="cuda")
     lp = dict(scale0=sc0, out0=hg0, stats=stats, T=T, rowa=rowa)
+    # per-row offsets (dual cases): operand and row sums are those of h - m_r; ANY m_r must give the same consumer output,
+    # a good estimate of the row mean keeps the operand's bf16 rounding free of it. Here: 0.8 x the mean + a constant.
+    moff = None
     if dual:
-        lp.update(scale1=sc1, out1=hg1)
+        moff = 0.8 * (h + a.float() @ w.float().t() + b).mean(1) + 0.05
+        moff_out = torch.zeros(M, device="cuda")
+        lp.update(scale1=sc1, out1=hg1, moff_in=moff.contiguous(), moff_out=moff_out)
     ops.linear_bf16(a, w, mode=EPI_RESID_LN, out=h_out, bias=b, resid=h_out, ln_produce=lp)
     torch.cuda.synchronize()
     ref_h = h + a.float() @ w.float().t() + b
     assert _relerr(h_out, ref_h) < 1e-5
     seq = torch.arange(M, device="cuda") // T
-    assert _relerr(hg0, ref_h * (1 + sc0[seq])) < 4e-3
-    ref_stats = torch.stack([ref_h.view(M, D // 64, 64).sum(-1).t(), (ref_h ** 2).view(M, D // 64, 64).sum(-1).t()], -1)
-    assert (stats - ref_stats).abs().max().item() < 2e-3 and _relerr(stats, ref_stats) < 1e-5
+    ref_c = ref_h - moff[:, None] if moff is not None else ref_h   # what operand and row sums describe
+    assert _relerr(hg0, ref_c * (1 + sc0[seq])) < 4e-3
+    ref_stats = torch.stack([ref_c.view(M, D // 64, 64).sum(-1).t(), (ref_c ** 2).view(M, D // 64, 64).sum(-1).t()], -1)
+    assert (stats - ref_stats).abs().max().item() < 2e-3 and _relerr(stats[..., 1], ref_stats[..., 1]) < 1e-5
+    if moff is not None:
+        assert (moff_out - ref_h.mean(1)).abs().max().item() < 1e-5
     ref_rstd = (ref_h.var(1, unbiased=False) + 1e-6).rsqrt()
     assert _relerr(rowa[:, 3].contiguous().view(torch.float32), ref_rstd) < 1e-5
     def pair(w):   # (low, high) bf16 halves of a 32-bit word as fp32
@@ -115,7 +123,7 @@ def test_ln_fold_resid_producer_and_consumers(ops, S, T, D, N2, dual):
     mh, _ = pair(rowa[:, 0].contiguous())
     ml, sh = pair(rowa[:, 1].contiguous())
     _, sl = pair(rowa[:, 2].contiguous())
-    assert _relerr(-(mh + ml), ref_h.mean(1)) < 1e-4 and _relerr(sh + sl, 1 / ref_rstd) < 1e-4
+    assert _relerr(-(mh + ml), ref_c.mean(1)) < 1e-4 and _relerr(sh + sl, 1 / ref_rstd) < 1e-4
     w2 = _rand((N2, D), 37, 1 / math.sqrt(D), dtype=torch.bfloat16)
     c2 = _rand((N2,), 38)
     cases = [(hg0, sc0, sh0)] + ([(hg1, sc1, sh1)] if dual else [])

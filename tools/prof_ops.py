@@ -37,10 +37,15 @@ stats = torch.zeros(D // 64, M, 2, device=dev)
 gb3 = torch.randn(S, 2 * 3 * D, device=dev, generator=g) * 0.1
 gbf = torch.randn(S, 2 * F, device=dev, generator=g) * 0.1
 rowa = torch.zeros(M, 4, dtype=torch.int32, device=dev)
-lp1 = dict(scale0=mod[:, :D], out0=xn, stats=stats, T=T, rowa=rowa)
-lp2 = dict(scale0=mod[:, :D], out0=xn, scale1=mod[:, 2 * D:3 * D], out1=xf, stats=stats, T=T, rowa=rowa)
+moff = torch.randn(M, device=dev, generator=g) * 0.1
+moff_out = torch.zeros(M, device=dev)
+lp0 = dict(scale0=mod[:, :D], out0=xn, stats=stats, T=T, rowa=rowa)                                   # no per-row offsets
+lp1 = dict(scale0=mod[:, :D], out0=xn, stats=stats, T=T, rowa=rowa, moff_in=moff, moff_out=moff_out)
+lp2 = dict(scale0=mod[:, :D], out0=xn, scale1=mod[:, 2 * D:3 * D], out1=xf, stats=stats, T=T, rowa=rowa, moff_in=moff,
+           moff_out=moff_out)
 
 runs = {
+    "proj_ln0": (lambda: ops.linear_bf16(x, w_o, mode=EPI_RESID_LN, out=h, bias=b1, resid=h, ln_produce=lp0), 2.0 * M * D * D),
     "proj_ln": (lambda: ops.linear_bf16(x, w_o, mode=EPI_RESID_LN, out=h, bias=b1, resid=h, ln_produce=lp1), 2.0 * M * D * D),
     "proj_ln2": (lambda: ops.linear_bf16(x, w_o, mode=EPI_RESID_LN, out=h, bias=b1, resid=h, ln_produce=lp2), 2.0 * M * D * D),
     "ffn2_ln": (lambda: ops.linear_bf16(mid, w2, mode=EPI_RESID_LN, out=h, bias=bd, resid=h, ln_produce=lp1), 2.0 * M * D * F),

@@ -6,6 +6,10 @@
 //               the epilogue of tile i overlaps the MMAs of tile i+1.
 // Replaces every nn.Linear on the hot path of the reference (models/utils/layers.py:11,33,74,95-96,112;
 // models/in2in.py:389; models/mixermdm.py:652) with the listed fused epilogues.
+// File map: fused epilogues (one thread = one output row; bias / GELU / V^T scatter / LN-fold consumer) - residual
+// epilogue with a quarter-warp transpose (single-CTA kernels, embedding modes) and its LN-fold producer part - single-CTA
+// kernel - residual epilogue through TMA (CTA-pair kernel) - CTA-pair kernel (cta_group::2; warps 2 and 3 are the aux
+// warps of the LN-fold consumers: one extra k step of the MMA carries the mean / shift terms) - host launchers.
 #include "gemm.cuh"
 
 #include <stdio.h>

@@ -879,7 +879,7 @@ __device__ __forceinline__ void tma_epi_store(const CUtensorMap* m, uint32_t src
 template <int MODE>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, const EpiMaps& mp, TmaEpi& te, int m0, int n0, int M, int N,
                                                   uint32_t tmem_acc, int q, int c0, int cnt, int lane, int nxt_row0,
-                                                  int nxt_col0) {
+                                                  int nxt_col0, float moff) {
   const int row0 = m0 + q * 32, row = row0 + lane;
   const uint32_t taddr = tmem_acc + (uint32_t)(c0 * 32) + ((uint32_t)(q * 32) << 16);
   const uint32_t sbuf = smem_u32(te.buf);
@@ -889,11 +889,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, const EpiMa
   bool ln_row = false;
   const float* sc0 = nullptr;
   const float* sc1 = nullptr;
-  float s1 = 0.f, s2 = 0.f, moff = 0.f;
+  float s1 = 0.f, s2 = 0.f;   // (moff: this row's offset m_r, loaded by the caller while the accumulator was in the making)
   if (LN) {
     const int lim = min(M, ep.lnp_rows);
     ln_row = row < lim;
-    if (ep.lnp_moff_in != nullptr && ln_row) moff = __ldg(ep.lnp_moff_in + row);   // operand / row sums of h - m_r
     const int sq = min(row, lim - 1) / ep.lnp_T;
     sc0 = ep.lnp_scale0 + (size_t)sq * ep.lnp_ld0;
     if (dual) sc1 = ep.lnp_scale1 + (size_t)sq * ep.lnp_ld1;
@@ -1343,11 +1342,14 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
       RowCtx rc = make_row_ctx<MODE, C::AUX>(ep, m0 + q * 32 + lane, M);
+      float moff = 0.f;   // LN-fold producers: this row's operand offset (GemmEpi::lnp_moff_in)
+      if (mode_ln_producer(MODE) && C::TMA_EPI && ep.lnp_moff_in != nullptr && m0 + q * 32 + lane < min(M, ep.lnp_rows))
+        moff = __ldg(ep.lnp_moff_in + m0 + q * 32 + lane);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (C::AUX) rc.rho = reinterpret_cast<const float*>(stg_ptr)[(titer & 7) * C::BM + q * 32 + lane];   // the aux warp's
       if (C::TMA_EPI) {
-        if (cnt > 0) epilogue_tile_tma<MODE>(ep, emaps, te, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, nxt_row0, nxt_col0);
+        if (cnt > 0) epilogue_tile_tma<MODE>(ep, emaps, te, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, nxt_row0, nxt_col0, moff);
       } else if (cnt > 0) {
         epilogue_tile<BN, MODE, C::AUX>(ep, m0, n0, M, N, tmem_base + (uint32_t)(acc * BN), q, c0, cnt, lane, stg, bias, rc);
       }

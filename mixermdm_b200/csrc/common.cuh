@@ -70,8 +70,8 @@ struct DeviceGuard {
 // Programmatic dependent launch: a kernel launched with it may start - block by block, as the kernel in front of it in
 // the stream frees SMs - before that kernel has finished; it runs its prologue (barrier init, TMEM allocation,
 // descriptor prefetch) and then waits in pdl_wait() for the predecessor's completion and memory flush. The predecessor
-// allows this by calling pdl_trigger() (all blocks, at their start). MMDM_PDL=0 launches such kernels the ordinary way
-// (both device calls are no-ops then). Used by the CTA-pair GEMM and the attention kernel, which follow each other
+// allows this by calling pdl_trigger() (all blocks, at their start). Opt-in with MMDM_PDL=1; otherwise such kernels are
+// launched the ordinary way (both device calls are no-ops then). Used by the CTA-pair GEMM and the attention kernel, which follow each other
 // directly (33.91 / 34.00 against 33.86 / 33.86 samples/s in one job); extending it to the single-CTA GEMM and the row
 // kernels made the step 3 % SLOWER (32.0 against 33.0): their early-resident blocks sit in the wait on SMs the next
 // persistent kernel needs whole.

@@ -122,3 +122,34 @@ def test_model_on_a_non_current_device(golden):
     torch.cuda.synchronize(0)
     torch.cuda.synchronize(1)
     assert b.device == torch.device("cuda:1") and torch.equal(a.cpu(), b.cpu())
+
+
+def test_programmatic_dependent_launch_is_bitwise_neutral(tmp_path):
+    """MMDM_PDL=1 (opt-in: the CTA-pair GEMM and the attention kernel start before their predecessor has finished and wait
+    after their prologue) must not change a single bit of a graph-replayed sampler loop at a geometry that runs those
+    kernels (256 frames, LN fold on). The switch is read once per process, hence two child processes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, torch\n"
+        f"sys.path[:0] = [{root!r}, {os.path.join(root, 'tests')!r}]\n"
+        "from helpers import build_mixer, default_schedule\n"
+        "from oracle import synth\n"
+        "mix, _ = build_mixer(synth.SMALL_DIMS, seed=3)\n"
+        "mix = mix.to('cuda')\n"
+        "cond, noise = synth.inputs(2, 256, seed=5)\n"
+        "eng = mix.engine(4, 256, torch.device('cuda', 0), sched=default_schedule(), cfg_scale=3.5, center=True)\n"
+        "out = eng.sample(cond.cuda(), noise.cuda())\n"
+        "torch.cuda.synchronize()\n"
+        "torch.save(out.cpu(), sys.argv[1])\n")
+    outs = []
+    for flag in ("0", "1"):
+        path = str(tmp_path / f"pdl{flag}.pt")
+        env = dict(os.environ, MMDM_PDL=flag)
+        r = subprocess.run([sys.executable, "-c", script, path], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(path))
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])

@@ -630,6 +630,29 @@ def test_ln_fold_vs_layernorm_kernel_ragged_full_size(full_model, B, T, monkeypa
         assert report("individual denoiser, 300 rows, LayerNorm kernel vs oracle", relerr(outs["0"], ref)) < TOL_BF16
 
 
+@pytest.mark.parametrize("D,H,F", [(256, 2, 512), (512, 8, 2048)])
+def test_ln_fold_vs_layernorm_kernel_other_widths(D, H, F, monkeypatch):
+    """the folded path at other network widths / head sizes (128 and 64) than the BASELINE's, 263 frames x 3 samples
+    (CTA-pair kernels with 4 / 8 statistics slots); tools/fold_sweep.py runs the whole grid"""
+    dims = dict(den=dict(latent_dim=D, ff_size=F, num_layers=2, num_heads=H), mix=synth.SMALL_DIMS["mix"])
+    mix, sd = build_mixer(dims, seed=5)
+    mix = mix.to(DEV)
+    g = torch.Generator().manual_seed(D)
+    x, cond = torch.randn(3, 263, 524, generator=g), torch.randn(3, 2304, generator=g)
+    t = torch.tensor([10, 500, 990])
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MMDM_LN_FOLD", flag)
+        mix.denoiser2._standalone = None
+        outs[flag] = mix.denoiser2(x.to(DEV), t.to(DEV), cond=cond.to(DEV)).clone()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = mixer_oracle.denoiser({k: v.float() for k, v in sd.items()}, "denoiser2.", "interaction", x, t, cond, H)
+    assert report(f"D={D}: folded vs LayerNorm kernel", relerr(outs["1"], outs["0"])) < 1e-2
+    assert report(f"D={D}: folded vs oracle", relerr(outs["1"], ref)) < TOL_BF16
+    assert report(f"D={D}: LayerNorm kernel vs oracle", relerr(outs["0"], ref)) < TOL_BF16
+
+
 @pytest.mark.parametrize("mode", [2, 4])
 def test_full_size_mixer_forward_batch4_vs_oracle(mode):
     """full geometry (D=1024, L=8, T=300), Be=4 rows, temporal and spatio-temporal weights: Mixer.forward (aligned
